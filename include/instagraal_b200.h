@@ -1,0 +1,118 @@
+/* instagraal_b200 -- C ABI of the B200-native scaffolding-MCMC hot path.
+ *
+ * Drop-in boundary for the reference's `sampler` class (src/instagraal/cuda_lib_gl_single.py,
+ * "CL"): every entry point below replaces the pycuda launch sequence of one reference method.
+ * Plain C: borrowed, C-contiguous host buffers in, caller-allocated buffers out; nothing returned
+ * by pointer outlives the call.  One handle = one chain on one GPU, single host thread, all calls
+ * blocking.  Every function returns 0 on success or a negative code (message: ig_last_error).
+ * There is no CPU path: ig_create fails when no CUDA device is usable.
+ */
+#ifndef INSTAGRAAL_B200_H
+#define INSTAGRAAL_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IG_N_FIELDS 13 /* pos, sub_pos, id_c, start_bp, len_bp, sub_len, circ, prev, next, l_cont,
+                          sub_l_cont, l_cont_bp, ori  (struct frag, kernel_sparse_adapt.cu:40-58, minus
+                          the inert id/rep/activ/id_d which the facade synthesises) */
+#define IG_MAX_CANDS 8
+#define IG_N_OPS 24
+
+typedef struct ig_handle ig_handle;
+
+typedef struct ig_config {
+    int32_t device;            /* CUDA ordinal (reference: --device, cli/main.py:74-80) */
+    int32_t n_frags;           /* NF  = n_new_frags        (CL:170-171) */
+    int32_t n_sub_frags;       /* NS  = init_n_sub_frags   (CL:140)     */
+    int64_t nnz;               /* strict-upper non-zeros of the level L-1 matrix (CL:615) */
+    int32_t max_bounds_insert; /* CL:417-420 */
+    float mean_sub_len_kb;     /* float32(mean_len_bp_frags / 1000), CL:231,1120 */
+    double n_pix;              /* n_pixl_sub_mat, CL:366 (caller reproduces the int32 wrap, quirk Q8) */
+    int32_t compat_last_block; /* 1: reproduce the last-64-contact-block quirk of eval_sub_likelihood
+                                  (kernel_sparse_adapt.cu:4362); 0: sum every contact */
+    int32_t reserved;
+} ig_config;
+
+typedef struct ig_level_data {
+    const int32_t* frags13;    /* [13][NF] initial live scaffold, field order of IG_N_FIELDS */
+    const int32_t* sub_parent; /* [NS] parent fragment of each sub-fragment   (sub_frags_2_frags.x) */
+    const float* sub_watson;   /* [NS] kb from fragment start                  (.y)  SS:703-717 */
+    const float* sub_crick;    /* [NS] kb from fragment end                    (.z) */
+    const int32_t* sub_j;      /* [NS] index within parent                     (.w) */
+    const int64_t* row_ptr;    /* [NS+1] CSR of triu(M + M^T, k=1), canonical row-major (CL:592-609) */
+    const int32_t* col;        /* [nnz] */
+    const int32_t* val;        /* [nnz] */
+    const int32_t* init_prev;  /* [NF] CL:269 */
+    const int32_t* init_next;  /* [NF] CL:270 */
+    const int32_t* orientable; /* [NF] CL:271-275 */
+} ig_level_data;
+
+typedef struct ig_step_result {
+    double scores[IG_MAX_CANDS * IG_N_OPS]; /* all_scores, CL:1414-1431 (0.0 = not evaluated) */
+    double likelihood;       /* o = all_scores[argmax], CL:1454 */
+    double lnz_full;         /* gpu_curr_likelihood_nz, CL:1285 */
+    double dist;             /* dist_inter_genome, CL:665-716 */
+    int64_t sum_l_cont;      /* sum of contig lengths over contigs (mean_length_contigs numerator) */
+    int32_t n_contigs;       /* CL:2736 */
+    int32_t op_sampled;      /* CL:1446 */
+    int32_t id_f_sampled;    /* CL:1445 */
+    int32_t cand_index;      /* index of id_f_sampled in the candidate list */
+    int32_t n_uniq[IG_MAX_CANDS];  /* proposals scored per candidate (gpu_n_uniq) */
+    int32_t n_sub[IG_MAX_CANDS];   /* contacts selected by slice_sp_mat per candidate (n_sub_vals) */
+    int32_t q4_hits;         /* fragments that hit the reference's "nothing written" paste case (Q4) */
+    int32_t reserved;
+} ig_step_result;
+
+/* sampler.__init__ device part (CL:92-319: sparse_data_2_gpu, setup_all_gpu_struct, loadProgram) */
+int ig_create(const ig_config* cfg, const ig_level_data* data, ig_handle** out);
+/* sampler.free_gpu (CL:3167-3177) */
+void ig_destroy(ig_handle* h);
+const char* ig_last_error(ig_handle* h);
+/* _check_gpu probe (cli/endtoend.py:51-83): number of usable CUDA devices, name of device 0 */
+int ig_device_count(void);
+
+/* memcpy_htod(gpu_param_simu, ...) (CL:2343-2349, 3033): kuhn, lm, c1, slope, d, d_max, fact, v_inter */
+int ig_set_params(ig_handle* h, const float p[8]);
+/* GPUStruct.copy_from_gpu / copy_to_gpu (gpustruct.py:94-186).  get: contig ids are relabelled the
+ * way modify_gl_cuda_buffer would have left them (0..NC-1, longest contig = NC-1, CL:2715-2806). */
+int ig_get_state(ig_handle* h, int32_t* out13xNF);
+int ig_set_state(ig_handle* h, const int32_t* in13xNF);
+/* gpu_list_valid_insert (CL:421): carried from one get_bounds to the next extract_uniq_mutations (Q3) */
+int ig_get_valid_insert(ig_handle* h, int32_t out12[12]);
+int ig_set_valid_insert(ig_handle* h, const int32_t in12[12]);
+/* bomb_the_genome (CL:1925-1948) with the host-drawn permutation */
+int ig_bomb(ig_handle* h, const int32_t* perm);
+
+/* step_sampler (CL:1401-1465) after the host drew + sorted the candidates (CL:1403-1404) */
+int ig_step(ig_handle* h, int32_t id_frag, const int32_t* cands, int32_t n_cands, ig_step_result* out);
+/* eval = score every mutation of one (A,B) pair without applying: extract_uniq_mutations +
+ * perform_mutations + slice_sparse_mat + extract_current_sub_likelihood + eval_all_sub_likelihood
+ * (CL:1417-1431).  Refreshes the coordinates / full likelihood like the head of step_sampler. */
+int ig_eval_scores(ig_handle* h, int32_t id_frag, int32_t id_cand, int32_t flip_eject, double out24[24],
+                   int32_t* n_uniq, int32_t* n_sub);
+/* apply = test_copy_struct + modify_gl_cuda_buffer (CL:2094-2151, 1453) */
+int ig_apply(ig_handle* h, int32_t id_frag, int32_t id_cand, int32_t op, ig_step_result* out);
+/* eval_likelihood_4_nuisance (CL:1296-1344) when use_stale_coords=1 (coordinates of the last
+ * fill_dist_single, quirk Q5); eval_likelihood on fresh coordinates when 0.
+ * out3 = { nz likelihood, raw zeros sum Z (before *log_e), (double) n_vals_intra }. */
+int ig_full_likelihood(ig_handle* h, const float p[8], int32_t use_stale_coords, double out3[3]);
+/* estimate_parameters_rippe, histogram part (CL:2247-2297): per-bin sum over the first n_rows rows
+ * of the SYMMETRIC level L-1 matrix of intra-contig contacts at distance < max_kb, on the initial
+ * scaffold; hist[n_bins] int64 sums, rows_used = rows whose contig is longer than bin_kb. */
+int ig_distance_histogram(ig_handle* h, double bin_kb, double max_kb, int32_t n_rows, int32_t n_bins,
+                          int64_t* hist, int64_t* rows_used);
+
+/* diagonal of (M + M^T) at level L-1 (self contacts): only the p(s) histogram sees it (CL:2257-2288) */
+int ig_set_sym_diag(ig_handle* h, const int32_t* diag);
+
+/* replica chains (one handle per GPU/process): exchange {likelihood, n_contigs, live id_c/pos/ori...}
+ * is done by the host facade over NCCL; the library only exposes the packed best-state buffer. */
+int ig_device_state_ptr(ig_handle* h, void** dev_ptr, int64_t* n_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,1217 @@
+// instagraal_b200 -- hand-written CUDA (sm_100a) for the scaffolding-MCMC hot path + its C ABI.
+//
+// One ig_step() = one reference step_sampler() (cuda_lib_gl_single.py:1401-1465, "CL") with the
+// ~700 host<->device crossings collapsed into ~14 stream-ordered launches and ONE blocking D2H of
+// a 1.1 KB result record.  Design (DESIGN.md has the long form):
+//   * contacts: CSR by row sub-fragment of the strict upper triangle, (col,val) interleaved int2;
+//     a candidate touches only the rows of the <=2 affected contigs (ordered row list built on
+//     device), never the whole COO, and never through the host.
+//   * the 24 candidate scaffolds are never materialised: mutated coordinates of both endpoints of a
+//     contact are evaluated on the fly from a 3 KB per-candidate descriptor in shared memory
+//     (ig_moves.cuh).  Row endpoints are evaluated once per row by lanes 0..23 of the warp.
+//   * all sums in double, fixed (deterministic) reduction order: lane -> warp shuffle -> block ->
+//     partial array -> single-block tree.  No floating-point atomics anywhere.
+//   * expected contacts in float32 exactly as the reference kernel writes them (same libdevice
+//     powf/expf/log10 calls, same association), so per-contact terms are bit-identical to the
+//     reference's eval_sub_likelihood (kernel_sparse_adapt.cu:4236-4370, "KA").
+// Tensor cores are deliberately unused: sparse gather + transcendental math, no contraction.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/instagraal_b200.h"
+#include "ig_moves.cuh"
+
+#define IG_WARPS_PER_BLOCK 8
+#define IG_THREADS (IG_WARPS_PER_BLOCK * 32)
+#define IG_ROW_CHUNK 1024
+#define IG_LANE_CUR 24  // lane that owns the current-state zero term in the score kernel
+
+struct Params { float kuhn, lm, c1, slope, d, d_max, fact, v_inter; };  // KA:91-100
+struct SubRec { int parent; float watson; float crick; int j; };          // 16 B
+struct CoordRec { float dist; int id_c; int pos; float s_tot; };          // 16 B (uni_fill_vect_dist)
+
+struct CandInfo {  // per-candidate slice description (slice_sp_mat prologue, KA:526-551)
+    int id_a, id_b, same, is_circ;
+    int up_a, down_a, up_b, down_b;
+    int n_rows, n_sub, row_hi, pad;
+};
+
+struct DevScalars {
+    Params p;          // live parameters
+    Params p_test;     // nuisance test parameters
+    double log10_vinter, log10_vinter_test;
+    int max_label;
+    int valid[12];     // gpu_list_valid_insert
+    int n_cands, a;
+    int cands[IG_MAX_CANDS];
+    CandInfo ci[IG_MAX_CANDS];
+    double lnz_full, z_cur, lsub_cur[IG_MAX_CANDS];
+    int nintra_cur;
+    int win_cand, win_op;
+    int q4_hits;
+    int n_heads; long long sum_l_cont; long long dist_half;
+    double scores[IG_MAX_CANDS * IG_N_OPS];
+    double likelihood;
+    double full_out[3];
+    int full_nintra, pad_;
+};
+
+// ------------------------------------------------------------------------------------------------
+// device math: textual twins of KA:111-124, 153-163, 200-225, 251-270
+__device__ __forceinline__ float rippe_contacts(float s, const Params& p) {
+    float result = 0.0f;
+    if ((s > 0.0f) && (s < p.d_max)) {
+        if (p.d == 2.0f)  // exp(0/(x+2)) == 1.0f exactly: skipping it is bit-identical
+            result = (p.c1 * powf(s, p.slope)) * p.fact;
+        else
+            result = (p.c1 * powf(s, p.slope) * expf((p.d - 2) / (powf(s * p.lm / p.kuhn, 2.0f) + p.d))) * p.fact;
+    }
+    return fmaxf(result, p.v_inter);
+}
+__device__ __forceinline__ float rippe_contacts_circ(float s, float s_tot, const Params& p) {
+    float result = 0.0f;
+    if ((s > 0.0f) && (s < p.d_max)) {
+        float K = p.lm / p.kuhn;
+        float n = K * s * (s_tot - s) / s_tot;
+        result = (powf(p.kuhn, -3.0f) * powf(n, p.slope) * expf((p.d - 2.0f) / (powf(n, 2.0f) + p.d))) * p.fact;
+    }
+    return fmaxf(result, p.d_max);  // sic: floored at d_max (quirk Q6, KA:219)
+}
+__device__ float factorial_ref(float n) {
+    float result = 1;
+    n = floorf(n);
+    if (n < 10) { for (int c = 1; c <= n; c++) result = result * c; }
+    else result = powf(n, n) * expf(-n) * sqrtf(2 * M_PI * n);
+    return result;
+}
+__constant__ double c_log10_fact[16];
+__global__ void k_init_tables(double* out16) {
+    int t = threadIdx.x;
+    if (t < 16) out16[t] = t == 0 ? 0.0 : log10((double)factorial_ref((float)t));
+}
+// part of the per-contact term that depends on the observed count only (KA:259,262)
+__device__ __forceinline__ double ob_const(double ob) {
+    if (ob >= 15.0) return ob * log10(ob) - ob + log10(sqrt(ob * 2.0 * M_PI));
+    return c_log10_fact[(int)ob];
+}
+// evaluate_likelihood_pxl_double (KA:251-270) with the ob-only part hoisted
+__device__ __forceinline__ double pxl_term(float exf, double ob, double obc, double log10_vinter, float v_inter) {
+    double ex = (double)exf;
+    if (ex == 0) return 0.0;
+    double lg = (exf == v_inter) ? log10_vinter : log10(ex);
+    return ob * lg - ex - obc;
+}
+#define LOG10E_F 0.43429448190325182f
+
+__device__ __forceinline__ CoordRec coords_of(const Frag& f, const SubRec& s, int* len_out) {
+    CoordRec c;
+    const bool fw = f.ori == 1;
+    c.dist = __int2float_rn(f.start_bp) / 1000.0f + (fw ? s.watson : s.crick);  // KA:3751
+    c.id_c = f.id_c;
+    int st = (int)(__int2float_rn(f.circ) * __int2float_rn(f.l_cont_bp) / 1000.0f);  // int local, KA:3715,3739
+    c.s_tot = (float)st;
+    c.pos = f.sub_pos + (fw ? s.j : f.sub_len - (s.j + 1));  // KA:3745-3749
+    *len_out = f.sub_l_cont;
+    return c;
+}
+
+// one contact's term for one scaffold state (KA:4322-4353)
+__device__ __forceinline__ double contact_term(const CoordRec& ci, const CoordRec& cj, int len_j, double ob, double obc,
+                                               const Params& p, double l10v, float mbar, const float* __restrict__ exz_tab) {
+    float exf, exzf;
+    if (ci.id_c == cj.id_c) {
+        float s = fabsf(ci.dist - cj.dist);
+        int dp = abs(ci.pos - cj.pos);
+        if (ci.s_tot == 0) {
+            exf = rippe_contacts(s, p);
+            exzf = exz_tab[dp];
+        } else {
+            exf = rippe_contacts_circ(s, ci.s_tot, p);
+            float s_z = __int2float_rn(dp) * mbar;
+            if (s_z < p.d_max) exzf = rippe_contacts_circ(s_z, __int2float_rn(len_j) * mbar, p);
+            else exzf = p.v_inter;
+        }
+    } else { exf = p.v_inter; exzf = p.v_inter; }
+    return pxl_term(exf, ob, obc, l10v, p.v_inter) + (double)exzf * LOG10E_F;
+}
+
+// zero-term of one sub-fragment (KA:3955-3972); returns contribution to Z (<= 0)
+__device__ __forceinline__ double zero_term(int pos, int len, float s_tot, const Params& p, float mbar) {
+    if (pos <= 0) return 0.0;
+    float s = __int2float_rn(pos) * mbar;
+    double ex;
+    if (s < p.d_max) {
+        if (s_tot == 0) ex = (double)rippe_contacts(s, p);
+        else ex = (double)rippe_contacts_circ(s, __int2float_rn(len) * mbar, p);
+    } else ex = (double)p.v_inter;
+    return -(ex * __int2double_rn(len - pos));
+}
+__device__ __forceinline__ int intra_pairs(int len) {  // int32 wrap + C division, KA:3950-3953
+    int t = (int)((unsigned)len * (unsigned)(len - 1));
+    return t / 2;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+// deterministic block sum of one double per thread (fixed tree); result valid in thread 0
+__device__ __forceinline__ double block_sum(double v, double* sm /* >= 32 */) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sm[w] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (w == 0) {
+        r = lane < (blockDim.x >> 5) ? sm[lane] : 0.0;
+        r = warp_sum(r);
+    }
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0: coordinates of the current scaffold (uni_fill_vect_dist, KA:3763-3822) + its zero term and
+//     intra pixel count (eval_likelihood_on_zero with the CORRECT float mean, i.e. without Q1).
+__global__ void __launch_bounds__(IG_THREADS)
+k_coords(const FragRec* __restrict__ live, const SubRec* __restrict__ sub, CoordRec* __restrict__ coord,
+         int* __restrict__ clen, int ns, const DevScalars* __restrict__ sc, float mbar, int use_test,
+         double* __restrict__ part_z, int* __restrict__ part_n, int write_coords) {
+    __shared__ double sm[32];
+    __shared__ int sn;
+    const Params p = use_test ? sc->p_test : sc->p;
+    if (threadIdx.x == 0) sn = 0;
+    __syncthreads();
+    double z = 0.0;
+    int nloc = 0;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < ns; r += gridDim.x * blockDim.x) {
+        CoordRec c; int len;
+        if (write_coords) {
+            SubRec s = sub[r];
+            Frag f = live[s.parent].f;
+            c = coords_of(f, s, &len);
+            coord[r] = c; clen[r] = len;
+        } else { c = coord[r]; len = clen[r]; }
+        if (c.pos == 0) nloc += intra_pairs(len);
+        z += zero_term(c.pos, len, c.s_tot, p, mbar);
+    }
+    if (nloc) atomicAdd(&sn, nloc);
+    double tot = block_sum(z, sm);
+    __syncthreads();
+    if (threadIdx.x == 0) { part_z[blockIdx.x] = tot; part_n[blockIdx.x] = sn; }
+}
+
+// K1: full likelihood over every stored contact (evaluate_likelihood_sparse, KA:4374-4488).
+//     Warp per CSR row; lanes stride the row with coalesced 8-byte (col,val) loads.
+__global__ void __launch_bounds__(IG_THREADS)
+k_full_lnz(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, const CoordRec* __restrict__ coord,
+           const int* __restrict__ clen, int ns, const DevScalars* __restrict__ sc, float mbar, int use_test,
+           const float* __restrict__ exz_tab, double* __restrict__ part) {
+    __shared__ double sm[32];
+    const Params p = use_test ? sc->p_test : sc->p;
+    const double l10v = use_test ? sc->log10_vinter_test : sc->log10_vinter;
+    const int lane = threadIdx.x & 31;
+    const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    double acc = 0.0;
+    for (int r = wg; r < ns; r += nw) {
+        const long long b = row_ptr[r], e = row_ptr[r + 1];
+        if (b == e) continue;
+        const CoordRec ci = coord[r];
+        const int len_i = clen[r];
+        for (long long k = b + lane; k < e; k += 32) {
+            const int2 c = __ldg(&cv[k]);
+            const CoordRec cj = coord[c.x];
+            const double ob = (double)c.y;
+            // KA:4428: the circular zero term uses the ROW's contig length
+            acc += contact_term(ci, cj, len_i, ob, ob_const(ob), p, l10v, mbar, exz_tab);
+        }
+    }
+    double tot = block_sum(acc, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = tot;
+}
+
+// generic deterministic final reduction of `n` doubles (and optionally ints) by one block
+__global__ void k_reduce(const double* __restrict__ part, int n, double* out, const int* __restrict__ ipart, int* iout) {
+    __shared__ double sm[32];
+    __shared__ int smi;
+    if (threadIdx.x == 0) smi = 0;
+    __syncthreads();
+    double v = 0.0;
+    int iv = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { v += part[i]; if (ipart) iv += ipart[i]; }
+    if (ipart && iv) atomicAdd(&smi, iv);
+    double tot = block_sum(v, sm);
+    __syncthreads();
+    if (threadIdx.x == 0) { *out = tot; if (iout) *iout = smi; }
+}
+
+// exz table: expected contacts at integer sub-fragment separation (linear contigs), KA:4330-4335
+__global__ void k_exz_table(float* __restrict__ tab, int n, const DevScalars* __restrict__ sc, float mbar, int use_test) {
+    const Params p = use_test ? sc->p_test : sc->p;
+    for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < n; d += gridDim.x * blockDim.x) {
+        float s_z = __int2float_rn(d) * mbar;
+        tab[d] = (s_z < p.d_max) ? rippe_contacts(s_z, p) : p.v_inter;
+    }
+}
+__global__ void k_set_params(DevScalars* sc, Params p, int test) {
+    if (test) { sc->p_test = p; sc->log10_vinter_test = log10((double)p.v_inter); }
+    else { sc->p = p; sc->log10_vinter = log10((double)p.v_inter); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: per-candidate setup.  Thread 0 walks the candidates IN ORDER because extract_uniq_mutations
+//     of candidate k reads the list_valid_insert left by get_bounds of candidate k-1 (quirk Q3).
+__global__ void k_cand_setup(const FragRec* __restrict__ live, DevScalars* sc, IgDescriptor* desc, int n_bounds,
+                             int first_flip_eject) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int a = sc->a;
+    const Frag A = live[a].f;
+    int prev_valid[12];
+    for (int i = 0; i < 12; i++) prev_valid[i] = sc->valid[i];
+    for (int k = 0; k < sc->n_cands; k++) {
+        IgDescriptor& d = desc[k];
+        const int b = sc->cands[k];
+        const Frag B = live[b].f;
+        d.a = a; d.b = b; d.max_id = sc->max_label;
+        d.A = A; d.B = B;
+        d.n_uniq = ig_uniq_mutations(A, B, prev_valid, (k == 0) ? first_flip_eject : 0, d.uniq);
+        ig_get_bounds_positions(A, B, d.valid, d.cut_pos_up, d.cut_pos_down);
+        for (int i = 0; i < IG_N_CUT; i++) { d.f_up[i] = -1; d.f_down[i] = -1; }
+        for (int i = 0; i < 12; i++) prev_valid[i] = d.valid[i];
+        // slice windows, KA:526-551 (sub-fragment units of the live scaffold)
+        CandInfo& c = sc->ci[k];
+        int pfa = A.sub_pos * (A.ori == 1) + (A.sub_pos - A.sub_len) * (A.ori == -1); if (pfa < 0) pfa = 0;
+        int pfb = B.sub_pos * (B.ori == 1) + (B.sub_pos - B.sub_len) * (B.ori == -1); if (pfb < 0) pfb = 0;
+        c.id_a = A.id_c; c.id_b = B.id_c; c.same = A.id_c == B.id_c; c.is_circ = A.circ;
+        c.up_a = max(0, pfa - n_bounds - A.sub_len); c.down_a = min(A.sub_l_cont - 1, pfa + n_bounds + A.sub_len);
+        c.up_b = max(0, pfb - B.sub_len); c.down_b = min(B.sub_l_cont - 1, pfb + B.sub_len);
+        c.n_rows = 0; c.n_sub = 0; c.row_hi = -1;
+    }
+    for (int i = 0; i < 12; i++) sc->valid[i] = prev_valid[i];  // state after the last candidate (CL:1854-1870)
+}
+// K3: cut fragments of get_bounds (KA:2255-2269), all candidates at once
+__global__ void k_find_cuts(const FragRec* __restrict__ live, int nf, const DevScalars* __restrict__ sc, IgDescriptor* desc) {
+    const int k = blockIdx.y;
+    if (k >= sc->n_cands) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf) return;
+    IgDescriptor& d = desc[k];
+    const Frag f = live[i].f;
+    if (f.id_c != d.A.id_c) return;
+#pragma unroll
+    for (int c = 0; c < IG_N_CUT; c++) {
+        if (f.pos == d.cut_pos_down[c]) d.f_down[c] = i;
+        if (f.pos == d.cut_pos_up[c]) d.f_up[c] = i;
+    }
+}
+// K4: all pivots (one thread per candidate)
+__global__ void k_build_desc(const FragRec* __restrict__ live, const DevScalars* __restrict__ sc, IgDescriptor* desc) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= sc->n_cands) return;
+    ig_build_descriptor(desc[k], [&](int i) { return live[i].f; });
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5-7: ORDERED list of the CSR rows (sub-fragments) that belong to the <=2 affected contigs.
+__device__ __forceinline__ bool row_affected(const CoordRec& c, const CandInfo& ci) { return c.id_c == ci.id_a || c.id_c == ci.id_b; }
+__global__ void __launch_bounds__(IG_ROW_CHUNK)
+k_rows_count(const CoordRec* __restrict__ coord, int ns, const DevScalars* __restrict__ sc, int* __restrict__ chunk_cnt, int n_chunks) {
+    const int k = blockIdx.y;
+    if (k >= sc->n_cands) return;
+    const int r = blockIdx.x * IG_ROW_CHUNK + threadIdx.x;
+    const bool f = r < ns && row_affected(coord[r], sc->ci[k]);
+    const int c = __syncthreads_count(f);
+    if (threadIdx.x == 0) chunk_cnt[k * n_chunks + blockIdx.x] = c;
+}
+__global__ void k_rows_scan(int* __restrict__ chunk_cnt, int n_chunks, DevScalars* sc) {
+    const int k = blockIdx.x;
+    if (k >= sc->n_cands) return;
+    __shared__ int carry;
+    __shared__ int wsum[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    int* c = chunk_cnt + k * n_chunks;
+    for (int base = 0; base < n_chunks; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int v = i < n_chunks ? c[i] : 0;
+        int x = v;
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) wsum[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            int s = lane < (blockDim.x >> 5) ? wsum[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+            wsum[lane] = s;
+        }
+        __syncthreads();
+        const int excl = carry + (w ? wsum[w - 1] : 0) + x - v;
+        if (i < n_chunks) c[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sc->ci[k].n_rows = carry;
+}
+__global__ void __launch_bounds__(IG_ROW_CHUNK)
+k_rows_write(const CoordRec* __restrict__ coord, int ns, const DevScalars* __restrict__ sc, const int* __restrict__ chunk_off,
+             int n_chunks, int* __restrict__ rows, int rows_stride) {
+    const int k = blockIdx.y;
+    if (k >= sc->n_cands) return;
+    __shared__ int wsum[32];
+    const int r = blockIdx.x * IG_ROW_CHUNK + threadIdx.x;
+    const bool f = r < ns && row_affected(coord[r], sc->ci[k]);
+    const unsigned b = __ballot_sync(0xffffffffu, f);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) wsum[w] = __popc(b);
+    __syncthreads();
+    if (w == 0) {
+        int s = wsum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+        wsum[lane] = s;
+    }
+    __syncthreads();
+    if (f) {
+        const int off = chunk_off[k * n_chunks + blockIdx.x] + (w ? wsum[w - 1] : 0) + __popc(b & ((1u << lane) - 1));
+        rows[(size_t)k * rows_stride + off] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// slice_sp_mat membership of one contact (KA:557-606, incl. the precedence quirk Q11 and dat>0)
+__device__ __forceinline__ bool contact_selected(const CoordRec& ci, const CoordRec& cj, int val, const CandInfo& c) {
+    bool sel;
+    if ((cj.id_c == ci.id_c) && c.same && (c.is_circ == 0)) {
+        const int x = min(ci.pos, cj.pos), y = max(ci.pos, cj.pos);
+        sel = ((x <= c.down_a) && (y >= c.up_a)) || ((y >= c.up_b) && (x <= c.down_b));
+    } else {
+        sel = ((!c.same) && (cj.id_c == c.id_a)) || (cj.id_c == c.id_b);
+    }
+    return sel && (val > 0);
+}
+
+struct RowMut { float dist; int id_c; int pos; float s_tot; };  // row endpoint under one mutation
+
+// K8: THE scoring kernel (replaces fill_vect_dist x24, slice_sp_mat, host sort, prepare_sparse_call,
+//     extract_sub_likelihood, eval_all_likelihood_on_zero_1st, eval_sub_likelihood).
+//     grid = (G, n_cands); warp per affected row; lanes stride that row's contacts.
+__global__ void __launch_bounds__(IG_THREADS, 2)
+k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, const CoordRec* __restrict__ coord,
+        const int* __restrict__ clen, const FragRec* __restrict__ live, const SubRec* __restrict__ sub,
+        const DevScalars* __restrict__ sc, const IgDescriptor* __restrict__ desc_g, const int* __restrict__ rows,
+        int rows_stride, int* __restrict__ row_cnt, float mbar, const float* __restrict__ exz_tab,
+        double* __restrict__ part_nz,   // [cand][gridDim.x][25]  (24 uniq slots + current)
+        double* __restrict__ part_z,    // [cand][gridDim.x][25]
+        int* __restrict__ part_i)       // [cand][gridDim.x][26]  (24 intra + current intra + n_sub)
+{
+    const int k = blockIdx.y;
+    if (k >= sc->n_cands) return;
+    __shared__ IgDescriptor d;
+    __shared__ RowMut rm[IG_WARPS_PER_BLOCK][IG_N_OPS];
+    __shared__ double red[IG_WARPS_PER_BLOCK][26];
+    __shared__ int redi[IG_WARPS_PER_BLOCK][26];
+    {
+        const int* src = reinterpret_cast<const int*>(desc_g + k);
+        int* dst = reinterpret_cast<int*>(&d);
+        for (int i = threadIdx.x; i < (int)(sizeof(IgDescriptor) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const Params p = sc->p;
+    const double l10v = sc->log10_vinter;
+    const CandInfo ci_k = sc->ci[k];
+    const int n_uniq = d.n_uniq;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int wg = blockIdx.x * IG_WARPS_PER_BLOCK + w, nw = gridDim.x * IG_WARPS_PER_BLOCK;
+    const int* my_rows = rows + (size_t)k * rows_stride;
+
+    double acc[IG_N_OPS];
+#pragma unroll
+    for (int m = 0; m < IG_N_OPS; m++) acc[m] = 0.0;
+    double acc_cur = 0.0;
+    double zacc = 0.0;   // lane u < n_uniq: zero term of mutation uniq[u]; lane 24: current state
+    int iacc = 0;        // idem for the intra pixel count
+    int nsel = 0;
+    const int my_op = lane < n_uniq ? d.uniq[lane] : -1;
+
+    for (int ri = wg; ri < ci_k.n_rows; ri += nw) {
+        const int r = my_rows[ri];
+        const CoordRec ci = coord[r];
+        const SubRec si = sub[r];
+        const Frag fi = live[si.parent].f;
+        __syncwarp();
+        if (my_op >= 0) {
+            Frag fm = ig_eval_op(d, my_op, fi, si.parent);
+            int len;
+            CoordRec c = coords_of(fm, si, &len);
+            rm[w][lane].dist = c.dist; rm[w][lane].id_c = c.id_c; rm[w][lane].pos = c.pos; rm[w][lane].s_tot = c.s_tot;
+            if (c.pos == 0) iacc += intra_pairs(len);
+            zacc += zero_term(c.pos, len, c.s_tot, p, mbar);
+        } else if (lane == IG_LANE_CUR) {
+            const int len = clen[r];
+            if (ci.pos == 0) iacc += intra_pairs(len);
+            zacc += zero_term(ci.pos, len, ci.s_tot, p, mbar);
+        }
+        __syncwarp();
+        const long long b = row_ptr[r], e = row_ptr[r + 1];
+        int row_sel = 0;
+        for (long long q = b + lane; q < e; q += 32) {
+            const int2 c = __ldg(&cv[q]);
+            const CoordRec cj = coord[c.x];
+            if (!(cj.id_c == ci_k.id_a || cj.id_c == ci_k.id_b)) continue;
+            if (!contact_selected(ci, cj, c.y, ci_k)) continue;
+            row_sel++;
+            const double ob = (double)c.y, obc = ob_const(ob);
+            const int len_j_cur = clen[c.x];
+            const double t_cur = contact_term(ci, cj, len_j_cur, ob, obc, p, l10v, mbar, exz_tab);
+            acc_cur += t_cur;
+            const SubRec sj = sub[c.x];
+            const Frag fj = live[sj.parent].f;
+#pragma unroll 1
+            for (int u = 0; u < n_uniq; u++) {
+                const Frag fm = ig_eval_op(d, d.uniq[u], fj, sj.parent);
+                int len_j;
+                const CoordRec cjm = coords_of(fm, sj, &len_j);
+                CoordRec cim;
+                cim.dist = rm[w][u].dist; cim.id_c = rm[w][u].id_c; cim.pos = rm[w][u].pos; cim.s_tot = rm[w][u].s_tot;
+                double t;
+                // bit-exact shortcut: identical inputs give the identical term
+                const bool same_in = (cim.id_c == cjm.id_c) == (ci.id_c == cj.id_c) && cim.s_tot == ci.s_tot &&
+                                     (cim.id_c != cjm.id_c ||
+                                      (fabsf(cim.dist - cjm.dist) == fabsf(ci.dist - cj.dist) &&
+                                       abs(cim.pos - cjm.pos) == abs(ci.pos - cj.pos) &&
+                                       (ci.s_tot == 0 || len_j == len_j_cur)));
+                if (same_in) t = t_cur;
+                else t = contact_term(cim, cjm, len_j, ob, obc, p, l10v, mbar, exz_tab);
+#pragma unroll
+                for (int m = 0; m < IG_N_OPS; m++) if (m == u) acc[m] += t;  // keeps acc[] in registers
+            }
+        }
+        row_sel = __reduce_add_sync(0xffffffffu, row_sel);
+        if (lane == 0) row_cnt[(size_t)k * rows_stride + ri] = row_sel;
+        nsel += (lane == 0) ? row_sel : 0;
+    }
+    // ---- deterministic block reduction: lane -> warp -> block
+#pragma unroll
+    for (int u = 0; u < IG_N_OPS; u++) {
+        double v = warp_sum(acc[u]);
+        if (lane == 0) red[w][u] = v;
+    }
+    {
+        double v = warp_sum(acc_cur);
+        if (lane == 0) red[w][24] = v;
+    }
+    __syncthreads();
+    const size_t pb = ((size_t)k * gridDim.x + blockIdx.x);
+    if (threadIdx.x < 25) {
+        double v = 0.0;
+        for (int ww = 0; ww < IG_WARPS_PER_BLOCK; ww++) v += red[ww][threadIdx.x];
+        part_nz[pb * 25 + threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (lane < 25) { red[w][lane] = zacc; redi[w][lane] = iacc; }
+    if (lane == 0) redi[w][25] = nsel;
+    __syncthreads();
+    if (threadIdx.x < 26) {
+        int iv = 0;
+        for (int ww = 0; ww < IG_WARPS_PER_BLOCK; ww++) iv += redi[ww][threadIdx.x];
+        part_i[pb * 26 + threadIdx.x] = iv;
+        if (threadIdx.x < 25) {
+            double v = 0.0;
+            for (int ww = 0; ww < IG_WARPS_PER_BLOCK; ww++) v += red[ww][threadIdx.x];
+            part_z[pb * 25 + threadIdx.x] = v;
+        }
+    }
+}
+
+// K9: per-candidate finalisation: fixed-order reduction of the block partials, the reference's
+//     last-block quirk (KA:4362), zero terms (eval_all_likelihood_on_zero_2nd KA:4005-4027) and
+//     score assembly (eval_all_scores KA:4029-4046).  One block of 256 threads per candidate.
+__global__ void __launch_bounds__(256)
+k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, const CoordRec* __restrict__ coord,
+           const int* __restrict__ clen, const FragRec* __restrict__ live, const SubRec* __restrict__ sub,
+           DevScalars* sc, const IgDescriptor* __restrict__ desc_g, const int* __restrict__ rows, int rows_stride,
+           const int* __restrict__ row_cnt, float mbar, const float* __restrict__ exz_tab,
+           const double* __restrict__ part_nz, const double* __restrict__ part_z, const int* __restrict__ part_i,
+           int n_part, double n_pix, int compat_last_block, int* __restrict__ n_uniq_out, int* __restrict__ n_sub_out) {
+    const int k = blockIdx.x;
+    if (k >= sc->n_cands) return;
+    __shared__ double sm[32];
+    __shared__ double s_nz[25], s_z[25], s_corr[IG_N_OPS];
+    __shared__ int s_i[26];
+    __shared__ double t_val[IG_N_OPS][64];
+    __shared__ int2 t_cv[64];
+    __shared__ int t_row[64];
+    __shared__ int t_cnt;
+    const IgDescriptor& d = desc_g[k];
+    const Params p = sc->p;
+    const double l10v = sc->log10_vinter;
+    const CandInfo ci_k = sc->ci[k];
+    const int n_uniq = d.n_uniq;
+    for (int s = 0; s < 25; s++) {
+        double v = 0.0, z = 0.0;
+        for (int i = threadIdx.x; i < n_part; i += blockDim.x) {
+            v += part_nz[((size_t)k * n_part + i) * 25 + s];
+            z += part_z[((size_t)k * n_part + i) * 25 + s];
+        }
+        double tv = block_sum(v, sm);
+        if (threadIdx.x == 0) s_nz[s] = tv;
+        double tz = block_sum(z, sm);
+        if (threadIdx.x == 0) s_z[s] = tz;
+    }
+    if (threadIdx.x < 26) {
+        int iv = 0;
+        for (int i = 0; i < n_part; i++) iv += part_i[((size_t)k * n_part + i) * 26 + threadIdx.x];
+        s_i[threadIdx.x] = iv;
+    }
+    if (threadIdx.x < IG_N_OPS) s_corr[threadIdx.x] = 0.0;
+    __syncthreads();
+    const int n_sub = s_i[25];
+    const int t = n_sub % 64;
+    // ---- last-block quirk: uniq slots u >= t lose the final (n_sub % 64) contacts of the row-sorted slice
+    if (compat_last_block && t > 0 && t < n_uniq) {
+        if (threadIdx.x == 0) {  // serial, hence deterministic, collection of the last t selected contacts
+            int need = t, n = 0;
+            for (int ri = ci_k.n_rows - 1; ri >= 0 && need > 0; ri--) {
+                if (row_cnt[(size_t)k * rows_stride + ri] == 0) continue;
+                const int r = rows[(size_t)k * rows_stride + ri];
+                const CoordRec ci = coord[r];
+                for (long long q = row_ptr[r + 1] - 1; q >= row_ptr[r] && need > 0; q--) {
+                    const int2 c = cv[q];
+                    const CoordRec cj = coord[c.x];
+                    if (!(cj.id_c == ci_k.id_a || cj.id_c == ci_k.id_b)) continue;
+                    if (!contact_selected(ci, cj, c.y, ci_k)) continue;
+                    t_cv[n] = c; t_row[n] = r; n++; need--;
+                }
+            }
+            t_cnt = n;
+        }
+        __syncthreads();
+        const int n_items = t_cnt * (n_uniq - t);
+        for (int idx = threadIdx.x; idx < n_items; idx += blockDim.x) {
+            const int e = idx % t_cnt, u = t + idx / t_cnt;
+            const int r = t_row[e];
+            const int2 c = t_cv[e];
+            const SubRec si = sub[r], sj = sub[c.x];
+            const Frag fim = ig_eval_op(d, d.uniq[u], live[si.parent].f, si.parent);
+            const Frag fjm = ig_eval_op(d, d.uniq[u], live[sj.parent].f, sj.parent);
+            int li, lj;
+            const CoordRec cim = coords_of(fim, si, &li), cjm = coords_of(fjm, sj, &lj);
+            const double ob = (double)c.y;
+            t_val[u][e] = contact_term(cim, cjm, lj, ob, ob_const(ob), p, l10v, mbar, exz_tab);
+        }
+        __syncthreads();
+        if (threadIdx.x >= t && threadIdx.x < n_uniq) {
+            double ssum = 0.0;
+            for (int e = 0; e < t_cnt; e++) ssum += t_val[threadIdx.x][e];
+            s_corr[threadIdx.x] = ssum;
+        }
+        __syncthreads();
+    }
+    // ---- scores
+    if (threadIdx.x == 0) {
+        const double log_e = (double)LOG10E_F;
+        const double lnz_full = sc->lnz_full;
+        const double lsub_cur = s_nz[24];
+        sc->lsub_cur[k] = lsub_cur;
+        sc->ci[k].n_sub = n_sub;
+        n_uniq_out[k] = n_uniq;
+        n_sub_out[k] = n_sub;
+        for (int m = 0; m < IG_N_OPS; m++) sc->scores[k * IG_N_OPS + m] = 0.0;
+        for (int u = 0; u < n_uniq; u++) {
+            const int m = d.uniq[u];
+            // Z[m] = Z(all sub-frags under m) = Z_cur_total - Z_cur(affected rows) + Z_m(affected rows)
+            const double z = sc->z_cur - s_z[24] + s_z[u];
+            const int n_intra = sc->nintra_cur - s_i[24] + s_i[u];  // int32 wrap-consistent
+            const double val_inter = -1.0 * log_e * (n_pix - __int2double_rn(n_intra)) * p.v_inter;
+            const double lz = z * log_e + val_inter;
+            const double lnz = s_nz[u] - ((u >= t && compat_last_block && t > 0) ? s_corr[u] : 0.0);
+            sc->scores[k * IG_N_OPS + m] = lnz + lz + lnz_full - lsub_cur;
+        }
+    }
+}
+
+// K10: move selection (CL:1435-1446): scores==0 -> -inf; first index of the maximum.
+__global__ void k_select(DevScalars* sc) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int n = sc->n_cands * IG_N_OPS;
+    int best = -1;
+    double bv = 0.0;
+    for (int i = 0; i < n; i++) {
+        const double v = sc->scores[i];
+        if (v == 0.0) continue;
+        if (best < 0 || v > bv) { best = i; bv = v; }
+    }
+    if (best < 0) best = 0;  // np.argmax of an all-zero filtered vector
+    sc->win_cand = best / IG_N_OPS;
+    sc->win_op = best % IG_N_OPS;
+    sc->likelihood = sc->scores[best];
+}
+
+// K11: apply the winning move to every fragment (test_copy_struct + copy_struct, CL:2094-2151)
+__global__ void __launch_bounds__(256)
+k_apply(const FragRec* __restrict__ live, FragRec* __restrict__ next, int nf, DevScalars* sc, const IgDescriptor* __restrict__ desc_g,
+        int forced_cand, int forced_op) {
+    __shared__ IgDescriptor d;
+    const int kc = forced_cand >= 0 ? forced_cand : sc->win_cand;
+    const int op = forced_op >= 0 ? forced_op : sc->win_op;
+    {
+        const int* src = reinterpret_cast<const int*>(desc_g + kc);
+        int* dst = reinterpret_cast<int*>(&d);
+        for (int i = threadIdx.x; i < (int)(sizeof(IgDescriptor) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nf) {
+        const Frag f = live[i].f;
+        Frag o;
+        if (op >= 8 && op < 12) {  // paste may leave a fragment unwritten (Q4): keep + count
+            const int ua = (op - 8) >> 1, ub = (op - 8) & 1;
+            Frag t1 = ig_split(f, i, d.A, ua, d.max_id);
+            Frag t2 = ig_split(t1, i, d.T1B[ua], ub, d.max_id1[ua]);
+            int written;
+            o = ig_paste(t2, i, d.T2A[ua][ub], d.a, d.T2B[ua][ub], d.b, &written);
+            if (!written) atomicAdd(&sc->q4_hits, 1);
+        } else {
+            o = ig_eval_op(d, op, f, i);
+        }
+        FragRec r; r.f = o; r.pad[0] = r.pad[1] = r.pad[2] = 0;
+        next[i] = r;
+    }
+}
+// K12: bookkeeping after apply: label counter, list_valid_insert (CL:2125-2126 re-runs get_bounds
+//      for ops >= 12), contig count / total length (modify_gl_cuda_buffer), dist_inter_genome.
+__global__ void k_post_scalars(DevScalars* sc, const IgDescriptor* __restrict__ desc_g, int forced_cand, int forced_op) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int kc = forced_cand >= 0 ? forced_cand : sc->win_cand;
+    const int op = forced_op >= 0 ? forced_op : sc->win_op;
+    if (op >= 12) for (int i = 0; i < 12; i++) sc->valid[i] = desc_g[kc].valid[i];
+    sc->max_label += 2;
+    sc->n_heads = 0; sc->sum_l_cont = 0; sc->dist_half = 0;
+}
+__global__ void __launch_bounds__(256)
+k_post(const FragRec* __restrict__ live, int nf, const int* __restrict__ init_prev, const int* __restrict__ init_next,
+       const int* __restrict__ orientable, DevScalars* sc) {
+    __shared__ int s_heads;
+    __shared__ long long s_len, s_half;
+    if (threadIdx.x == 0) { s_heads = 0; s_len = 0; s_half = 0; }
+    __syncthreads();
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    int heads = 0; long long len = 0; int half = 0;  // half = decrement of d in units of 1/2
+    if (f < nf) {
+        const Frag g = live[f].f;
+        if (g.pos == 0) { heads = 1; len = g.l_cont; }
+        // dist_inter_genome, CL:672-715 (init_ori == +1, blacklist empty)
+        const int p0 = init_prev[f], n0 = init_next[f];
+        int p1 = g.prev, n1 = g.next;
+        int swap = 1;
+        if ((p1 == p0 && n1 == n0) || (p1 == n0 && n1 == p0)) half += 2;
+        if (orientable[f]) {
+            if (1 != g.ori) { int tmp = p1; p1 = n1; n1 = tmp; swap = -1; }
+            if (p0 == p1) {
+                if (p0 == -1 || !orientable[p1]) half += 2;
+                else { half += 1; if (1 == swap * live[p1].f.ori) half += 1; }
+            }
+            if (n0 == n1) {
+                if (n0 == -1 || !orientable[n1]) half += 2;
+                else { half += 1; if (1 == swap * live[n1].f.ori) half += 1; }
+            }
+        } else {
+            if (p1 == p0 || p1 == n0) half += 2;
+            if (n1 == n0 || n1 == p0) half += 2;
+        }
+    }
+    if (heads) { atomicAdd(&s_heads, 1); atomicAdd((unsigned long long*)&s_len, (unsigned long long)len); }
+    if (half) atomicAdd((unsigned long long*)&s_half, (unsigned long long)half);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_heads) atomicAdd(&sc->n_heads, s_heads);
+        if (s_len) atomicAdd((unsigned long long*)&sc->sum_l_cont, (unsigned long long)s_len);
+        if (s_half) atomicAdd((unsigned long long*)&sc->dist_half, (unsigned long long)s_half);
+    }
+}
+__global__ void k_explode(FragRec* live, int nf, const int* __restrict__ perm) {  // KA:409-426
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf) return;
+    Frag f = live[i].f;
+    f.pos = 0; f.start_bp = 0; f.sub_pos = 0; f.id_c = perm[i]; f.prev = -1; f.next = -1;
+    f.l_cont = 1; f.l_cont_bp = f.len_bp; f.sub_l_cont = f.sub_len;
+    live[i].f = f;
+}
+// histogram for the initial p(s) fit (CL:2253-2293) on the INITIAL scaffold; integer-exact sums
+__global__ void __launch_bounds__(IG_THREADS)
+k_histogram(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, const int* __restrict__ sym_diag,
+            const FragRec* __restrict__ init, const SubRec* __restrict__ sub, int n_rows, double bin_kb, double max_kb,
+            int n_bins, unsigned long long* __restrict__ hist, unsigned long long* __restrict__ rows_used) {
+    const int lane = threadIdx.x & 31;
+    const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int r = wg; r < n_rows; r += nw) {
+        const SubRec si = sub[r];
+        const Frag fi = init[si.parent].f;
+        const bool used = bin_kb < (double)fi.l_cont_bp / 1000.0;
+        if (!used) continue;
+        const double s_i = (double)fi.start_bp / 1000.0 + (double)si.watson;
+        if (lane == 0) {
+            atomicAdd(rows_used, 1ULL);
+            if (sym_diag && sym_diag[r] != 0 && 0.0 < max_kb) atomicAdd(&hist[0], (unsigned long long)sym_diag[r]);
+        }
+        for (long long q = row_ptr[r] + lane; q < row_ptr[r + 1]; q += 32) {
+            const int2 c = cv[q];
+            const SubRec sj = sub[c.x];
+            const Frag fj = init[sj.parent].f;
+            if (fj.id_c != fi.id_c) continue;
+            const double s_j = (double)fj.start_bp / 1000.0 + (double)sj.watson;
+            const double dd = fabs(s_i - s_j);
+            if (!(dd < max_kb)) continue;
+            const int b = (int)(dd / bin_kb);
+            if (b < 0 || b >= n_bins) continue;
+            const int mult = 1 + (c.x < n_rows ? 1 : 0);  // symmetric matrix: row r and row c.x both see it
+            atomicAdd(&hist[b], (unsigned long long)((long long)c.y * mult));
+        }
+    }
+}
+
+// ================================================================================================
+// host side
+struct ig_handle {
+    ig_config cfg;
+    int nf, ns;
+    long long nnz;
+    cudaStream_t stream;
+    FragRec *live[2], *init_live;
+    int cur;
+    SubRec* sub;
+    CoordRec* coord;
+    int* clen;
+    long long* row_ptr;
+    int2* cv;
+    int* sym_diag;
+    int *init_prev, *init_next, *orientable;
+    DevScalars* sc;
+    IgDescriptor* desc;
+    float *exz, *exz_test;
+    int n_chunks, *chunk_cnt, *rows, *row_cnt;
+    int grid_score;
+    double *part_nz, *part_z; int* part_i;
+    double *part_full; int n_part_full;
+    double *part_zc; int* part_nc; int n_part_zc;
+    int *d_nuniq, *d_nsub, *d_perm;
+    unsigned long long* d_hist;
+    DevScalars* h_sc;  // pinned mirror
+    int* h_small;      // pinned scratch (cands, nuniq, nsub)
+    bool params_set, coords_fresh, coords_ever;
+    std::string err;
+};
+
+static thread_local std::string g_err;
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char buf[512];                                                                         \
+            snprintf(buf, sizeof buf, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            if (h) h->err = buf; else g_err = buf;                                                 \
+            return -2;                                                                             \
+        }                                                                                          \
+    } while (0)
+
+extern "C" const char* ig_last_error(ig_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
+extern "C" int ig_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+template <class T> static int dev_alloc(ig_handle* h, T** p, size_t n) {
+    CK(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+    return 0;
+}
+
+static int upload_state(ig_handle* h, const int32_t* in13, FragRec* dst) {
+    const int nf = h->nf;
+    std::vector<FragRec> tmp(nf);
+    for (int i = 0; i < nf; i++) {
+        int* v = reinterpret_cast<int*>(&tmp[i].f);
+        for (int k = 0; k < IG_N_FIELDS; k++) v[k] = in13[(size_t)k * nf + i];
+        tmp[i].pad[0] = tmp[i].pad[1] = tmp[i].pad[2] = 0;
+    }
+    CK(cudaMemcpyAsync(dst, tmp.data(), sizeof(FragRec) * nf, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_handle** out) {
+    ig_handle* h = nullptr;
+    if (!cfg || !data || !out) { g_err = "ig_create: null argument"; return -1; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        g_err = "ig_create: no CUDA device available (this library has no CPU path)";
+        return -3;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { g_err = "ig_create: bad device ordinal"; return -1; }
+    if (cfg->n_frags <= 0 || cfg->n_sub_frags <= 0 || cfg->nnz < 0) { g_err = "ig_create: bad sizes"; return -1; }
+    h = new ig_handle();
+    h->cfg = *cfg; h->nf = cfg->n_frags; h->ns = cfg->n_sub_frags; h->nnz = cfg->nnz;
+    h->cur = 0; h->params_set = false; h->coords_fresh = false; h->coords_ever = false;
+    cudaError_t e0 = cudaSetDevice(cfg->device);
+    if (e0 != cudaSuccess) { g_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e0); delete h; return -2; }
+#define CKC(x) do { int r_ = (x); if (r_) { g_err = h->err; ig_destroy(h); return r_; } } while (0)
+    auto body = [&]() -> int {
+        CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        const int nf = h->nf, ns = h->ns;
+        if (dev_alloc(h, &h->live[0], nf) || dev_alloc(h, &h->live[1], nf) || dev_alloc(h, &h->init_live, nf)) return -2;
+        if (dev_alloc(h, &h->sub, ns) || dev_alloc(h, &h->coord, ns) || dev_alloc(h, &h->clen, ns)) return -2;
+        if (dev_alloc(h, &h->row_ptr, (size_t)ns + 1) || dev_alloc(h, &h->cv, (size_t)h->nnz)) return -2;
+        if (dev_alloc(h, &h->init_prev, nf) || dev_alloc(h, &h->init_next, nf) || dev_alloc(h, &h->orientable, nf)) return -2;
+        if (dev_alloc(h, &h->sc, 1) || dev_alloc(h, &h->desc, IG_MAX_CANDS)) return -2;
+        if (dev_alloc(h, &h->exz, (size_t)ns + 1) || dev_alloc(h, &h->exz_test, (size_t)ns + 1)) return -2;
+        h->n_chunks = (ns + IG_ROW_CHUNK - 1) / IG_ROW_CHUNK;
+        if (dev_alloc(h, &h->chunk_cnt, (size_t)IG_MAX_CANDS * h->n_chunks)) return -2;
+        if (dev_alloc(h, &h->rows, (size_t)IG_MAX_CANDS * ns) || dev_alloc(h, &h->row_cnt, (size_t)IG_MAX_CANDS * ns)) return -2;
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, cfg->device));
+        const int sms = prop.multiProcessorCount;
+        h->grid_score = sms * 2;  // 2 resident CTAs of 8 warps per SM (launch bounds)
+        if (dev_alloc(h, &h->part_nz, (size_t)IG_MAX_CANDS * h->grid_score * 25)) return -2;
+        if (dev_alloc(h, &h->part_z, (size_t)IG_MAX_CANDS * h->grid_score * 25)) return -2;
+        if (dev_alloc(h, &h->part_i, (size_t)IG_MAX_CANDS * h->grid_score * 26)) return -2;
+        h->n_part_full = sms * 8;
+        if (dev_alloc(h, &h->part_full, h->n_part_full)) return -2;
+        h->n_part_zc = sms * 2;
+        if (dev_alloc(h, &h->part_zc, h->n_part_zc) || dev_alloc(h, &h->part_nc, h->n_part_zc)) return -2;
+        if (dev_alloc(h, &h->d_nuniq, IG_MAX_CANDS) || dev_alloc(h, &h->d_nsub, IG_MAX_CANDS) || dev_alloc(h, &h->d_perm, nf)) return -2;
+        if (dev_alloc(h, &h->d_hist, 1 << 16)) return -2;
+        h->sym_diag = nullptr;
+        CK(cudaMallocHost((void**)&h->h_sc, sizeof(DevScalars)));
+        CK(cudaMallocHost((void**)&h->h_small, 64 * sizeof(int)));
+        CK(cudaMemsetAsync(h->sc, 0, sizeof(DevScalars), h->stream));
+        // uploads
+        if (upload_state(h, data->frags13, h->live[0])) return -2;
+        CK(cudaMemcpy(h->init_live, h->live[0], sizeof(FragRec) * nf, cudaMemcpyDeviceToDevice));
+        {
+            std::vector<SubRec> s(ns);
+            for (int i = 0; i < ns; i++) {
+                s[i].parent = data->sub_parent[i]; s[i].watson = data->sub_watson[i];
+                s[i].crick = data->sub_crick[i]; s[i].j = data->sub_j[i];
+                if (s[i].parent < 0 || s[i].parent >= nf) { h->err = "ig_create: sub_parent out of range"; return -1; }
+            }
+            CK(cudaMemcpy(h->sub, s.data(), sizeof(SubRec) * ns, cudaMemcpyHostToDevice));
+        }
+        if (data->row_ptr[0] != 0 || data->row_ptr[ns] != h->nnz) { h->err = "ig_create: row_ptr inconsistent with nnz"; return -1; }
+        CK(cudaMemcpy(h->row_ptr, data->row_ptr, sizeof(long long) * ((size_t)ns + 1), cudaMemcpyHostToDevice));
+        {
+            const size_t chunk = 1 << 24;
+            std::vector<int2> buf(std::min<size_t>(chunk, (size_t)h->nnz));
+            for (size_t off = 0; off < (size_t)h->nnz; off += chunk) {
+                const size_t n = std::min(chunk, (size_t)h->nnz - off);
+                for (size_t i = 0; i < n; i++) { buf[i].x = data->col[off + i]; buf[i].y = data->val[off + i]; }
+                CK(cudaMemcpy(h->cv + off, buf.data(), n * sizeof(int2), cudaMemcpyHostToDevice));
+            }
+        }
+        CK(cudaMemcpy(h->init_prev, data->init_prev, sizeof(int) * nf, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->init_next, data->init_next, sizeof(int) * nf, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->orientable, data->orientable, sizeof(int) * nf, cudaMemcpyHostToDevice));
+        // factorial table on the device (same libdevice calls as the reference's factorial())
+        double* d16;
+        CK(cudaMalloc((void**)&d16, 16 * sizeof(double)));
+        k_init_tables<<<1, 32, 0, h->stream>>>(d16);
+        double h16[16];
+        CK(cudaMemcpyAsync(h16, d16, sizeof h16, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaMemcpyToSymbol(c_log10_fact, h16, sizeof h16));
+        CK(cudaFree(d16));
+        // label counter: labels in the initial scaffold are arbitrary; start above their maximum
+        int maxlab = 0;
+        for (int i = 0; i < nf; i++) maxlab = std::max(maxlab, data->frags13[(size_t)2 * nf + i]);
+        CK(cudaMemcpy(&h->sc->max_label, &maxlab, sizeof(int), cudaMemcpyHostToDevice));
+        return 0;
+    };
+    int rc = body();
+    if (rc) { g_err = h->err; ig_destroy(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+extern "C" void ig_destroy(ig_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    void* ptrs[] = {h->live[0], h->live[1], h->init_live, h->sub, h->coord, h->clen, h->row_ptr, h->cv, h->sym_diag,
+                    h->init_prev, h->init_next, h->orientable, h->sc, h->desc, h->exz, h->exz_test, h->chunk_cnt,
+                    h->rows, h->row_cnt, h->part_nz, h->part_z, h->part_i, h->part_full, h->part_zc, h->part_nc,
+                    h->d_nuniq, h->d_nsub, h->d_perm, h->d_hist};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (h->h_sc) cudaFreeHost(h->h_sc);
+    if (h->h_small) cudaFreeHost(h->h_small);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+static int use(ig_handle* h) {
+    if (!h) { g_err = "null handle"; return -1; }
+    CK(cudaSetDevice(h->cfg.device));
+    return 0;
+}
+static int launch_ok(ig_handle* h, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { h->err = std::string(what) + ": " + cudaGetErrorString(e); return -2; }
+    return 0;
+}
+
+extern "C" int ig_set_params(ig_handle* h, const float p8[8]) {
+    if (use(h)) return -1;
+    Params p; memcpy(&p, p8, sizeof p);
+    k_set_params<<<1, 1, 0, h->stream>>>(h->sc, p, 0);
+    k_exz_table<<<std::min(1024, (h->ns + 256) / 256), 256, 0, h->stream>>>(h->exz, h->ns + 1, h->sc, h->cfg.mean_sub_len_kb, 0);
+    if (launch_ok(h, "set_params")) return -2;
+    CK(cudaStreamSynchronize(h->stream));
+    h->params_set = true;
+    return 0;
+}
+
+// renumber like modify_gl_cuda_buffer (CL:2715-2806): contigs listed in ascending index of their
+// head fragment (sequential select_uniq_id_c), stable sort by length descending, id = NC-1-rank.
+static void canonical_labels(int nf, int32_t* st13) {
+    int32_t* pos = st13; int32_t* id_c = st13 + (size_t)2 * nf; int32_t* l_cont = st13 + (size_t)9 * nf;
+    std::vector<int> heads;
+    for (int i = 0; i < nf; i++) if (pos[i] == 0) heads.push_back(i);
+    std::vector<int> order(heads.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return l_cont[heads[x]] > l_cont[heads[y]]; });
+    std::vector<std::pair<int, int>> lut;  // (old label, rank)
+    lut.reserve(heads.size());
+    for (size_t r = 0; r < order.size(); r++) lut.push_back({id_c[heads[order[r]]], (int)r});
+    std::stable_sort(lut.begin(), lut.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first < b.first; });
+    const int nc = (int)heads.size();
+    for (int i = 0; i < nf; i++) {
+        auto it = std::upper_bound(lut.begin(), lut.end(), std::make_pair(id_c[i], INT32_MAX));
+        if (it != lut.begin() && (it - 1)->first == id_c[i]) id_c[i] = (nc - 1) - (it - 1)->second;
+    }
+}
+
+extern "C" int ig_get_state(ig_handle* h, int32_t* out13) {
+    if (use(h)) return -1;
+    const int nf = h->nf;
+    std::vector<FragRec> tmp(nf);
+    CK(cudaMemcpyAsync(tmp.data(), h->live[h->cur], sizeof(FragRec) * nf, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < nf; i++) {
+        const int* v = reinterpret_cast<const int*>(&tmp[i].f);
+        for (int k = 0; k < IG_N_FIELDS; k++) out13[(size_t)k * nf + i] = v[k];
+    }
+    canonical_labels(nf, out13);
+    return 0;
+}
+extern "C" int ig_set_state(ig_handle* h, const int32_t* in13) {
+    if (use(h)) return -1;
+    if (upload_state(h, in13, h->live[h->cur])) return -2;
+    int maxlab = 0;
+    for (int i = 0; i < h->nf; i++) maxlab = std::max(maxlab, in13[(size_t)2 * h->nf + i]);
+    CK(cudaMemcpy(&h->sc->max_label, &maxlab, sizeof(int), cudaMemcpyHostToDevice));
+    h->coords_fresh = false;
+    return 0;
+}
+extern "C" int ig_get_valid_insert(ig_handle* h, int32_t out12[12]) {
+    if (use(h)) return -1;
+    CK(cudaMemcpy(out12, h->sc->valid, 12 * sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+extern "C" int ig_set_valid_insert(ig_handle* h, const int32_t in12[12]) {
+    if (use(h)) return -1;
+    CK(cudaMemcpy(h->sc->valid, in12, 12 * sizeof(int), cudaMemcpyHostToDevice));
+    return 0;
+}
+extern "C" int ig_bomb(ig_handle* h, const int32_t* perm) {
+    if (use(h)) return -1;
+    CK(cudaMemcpyAsync(h->d_perm, perm, sizeof(int) * h->nf, cudaMemcpyHostToDevice, h->stream));
+    k_explode<<<(h->nf + 255) / 256, 256, 0, h->stream>>>(h->live[h->cur], h->nf, h->d_perm);
+    if (launch_ok(h, "explode")) return -2;
+    int maxlab = h->nf;  // perm values are 0..NF-1
+    CK(cudaMemcpyAsync(&h->sc->max_label, &maxlab, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->coords_fresh = false;
+    return 0;
+}
+
+// head of step_sampler: fill_dist_single + eval_likelihood (CL:1407-1409)
+static int refresh_current(ig_handle* h) {
+    const float mbar = h->cfg.mean_sub_len_kb;
+    k_coords<<<h->n_part_zc, IG_THREADS, 0, h->stream>>>(h->live[h->cur], h->sub, h->coord, h->clen, h->ns, h->sc, mbar, 0,
+                                                        h->part_zc, h->part_nc, 1);
+    k_reduce<<<1, 256, 0, h->stream>>>(h->part_zc, h->n_part_zc, &h->sc->z_cur, h->part_nc, &h->sc->nintra_cur);
+    k_full_lnz<<<h->n_part_full, IG_THREADS, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->ns, h->sc, mbar, 0, h->exz,
+                                                            h->part_full);
+    k_reduce<<<1, 256, 0, h->stream>>>(h->part_full, h->n_part_full, &h->sc->lnz_full, nullptr, nullptr);
+    h->coords_fresh = true; h->coords_ever = true;
+    return launch_ok(h, "refresh_current");
+}
+
+static int score_candidates(ig_handle* h, int a, const int32_t* cands, int n, int first_flip_eject) {
+    if (n <= 0 || n > IG_MAX_CANDS) { h->err = "n_cands out of range"; return -1; }
+    if (a < 0 || a >= h->nf) { h->err = "id_frag out of range"; return -1; }
+    for (int i = 0; i < n; i++) if (cands[i] < 0 || cands[i] >= h->nf) { h->err = "candidate out of range"; return -1; }
+    const float mbar = h->cfg.mean_sub_len_kb;
+    int* hs = h->h_small;
+    hs[0] = n; hs[1] = a;
+    for (int i = 0; i < IG_MAX_CANDS; i++) hs[2 + i] = i < n ? cands[i] : 0;
+    CK(cudaMemcpyAsync(&h->sc->n_cands, hs, (2 + IG_MAX_CANDS) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    const FragRec* live = h->live[h->cur];
+    k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, first_flip_eject);
+    k_find_cuts<<<dim3((h->nf + 255) / 256, n), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc);
+    k_build_desc<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc);
+    k_rows_count<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks);
+    k_rows_scan<<<n, 256, 0, h->stream>>>(h->chunk_cnt, h->n_chunks, h->sc);
+    k_rows_write<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks, h->rows, h->ns);
+    k_score<<<dim3(h->grid_score, n), IG_THREADS, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, live, h->sub, h->sc, h->desc,
+                                                                 h->rows, h->ns, h->row_cnt, mbar, h->exz, h->part_nz, h->part_z,
+                                                                 h->part_i);
+    k_finalize<<<n, 256, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, live, h->sub, h->sc, h->desc, h->rows, h->ns,
+                                         h->row_cnt, mbar, h->exz, h->part_nz, h->part_z, h->part_i, h->grid_score, h->cfg.n_pix,
+                                         h->cfg.compat_last_block, h->d_nuniq, h->d_nsub);
+    return launch_ok(h, "score_candidates");
+}
+
+static int apply_and_post(ig_handle* h, int forced_cand, int forced_op) {
+    const int nf = h->nf;
+    k_apply<<<(nf + 255) / 256, 256, 0, h->stream>>>(h->live[h->cur], h->live[h->cur ^ 1], nf, h->sc, h->desc, forced_cand, forced_op);
+    k_post_scalars<<<1, 1, 0, h->stream>>>(h->sc, h->desc, forced_cand, forced_op);
+    h->cur ^= 1;
+    k_post<<<(nf + 255) / 256, 256, 0, h->stream>>>(h->live[h->cur], nf, h->init_prev, h->init_next, h->orientable, h->sc);
+    h->coords_fresh = false;
+    return launch_ok(h, "apply");
+}
+
+static int fetch_result(ig_handle* h, int n, const int32_t* cands, ig_step_result* out, bool applied) {
+    CK(cudaMemcpyAsync(h->h_sc, h->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_small + 16, h->d_nuniq, IG_MAX_CANDS * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_small + 32, h->d_nsub, IG_MAX_CANDS * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const DevScalars& s = *h->h_sc;
+    memset(out, 0, sizeof *out);
+    for (int i = 0; i < n * IG_N_OPS; i++) out->scores[i] = s.scores[i];
+    out->lnz_full = s.lnz_full;
+    for (int i = 0; i < n; i++) { out->n_uniq[i] = h->h_small[16 + i]; out->n_sub[i] = h->h_small[32 + i]; }
+    out->q4_hits = s.q4_hits;
+    if (applied) {
+        out->likelihood = s.likelihood;
+        out->cand_index = s.win_cand; out->op_sampled = s.win_op;
+        out->id_f_sampled = cands ? cands[s.win_cand] : -1;
+        out->n_contigs = s.n_heads; out->sum_l_cont = s.sum_l_cont;
+        out->dist = (3.0 * h->nf - 0.5 * (double)s.dist_half) / (3.0 * h->nf);
+    }
+    return 0;
+}
+
+extern "C" int ig_step(ig_handle* h, int32_t id_frag, const int32_t* cands, int32_t n_cands, ig_step_result* out) {
+    if (use(h)) return -1;
+    if (!h->params_set) { h->err = "ig_step: parameters not set (ig_set_params)"; return -1; }
+    if (!out) { h->err = "ig_step: null result"; return -1; }
+    if (refresh_current(h)) return -2;
+    if (int rc = score_candidates(h, id_frag, cands, n_cands, 1)) return rc;
+    k_select<<<1, 32, 0, h->stream>>>(h->sc);
+    if (apply_and_post(h, -1, -1)) return -2;
+    return fetch_result(h, n_cands, cands, out, true);
+}
+
+extern "C" int ig_eval_scores(ig_handle* h, int32_t id_frag, int32_t id_cand, int32_t flip_eject, double out24[24],
+                              int32_t* n_uniq, int32_t* n_sub) {
+    if (use(h)) return -1;
+    if (!h->params_set) { h->err = "ig_eval_scores: parameters not set"; return -1; }
+    if (refresh_current(h)) return -2;
+    if (int rc = score_candidates(h, id_frag, &id_cand, 1, flip_eject)) return rc;
+    ig_step_result r;
+    if (fetch_result(h, 1, &id_cand, &r, false)) return -2;
+    for (int i = 0; i < 24; i++) out24[i] = r.scores[i];
+    if (n_uniq) *n_uniq = r.n_uniq[0];
+    if (n_sub) *n_sub = r.n_sub[0];
+    return 0;
+}
+
+extern "C" int ig_apply(ig_handle* h, int32_t id_frag, int32_t id_cand, int32_t op, ig_step_result* out) {
+    if (use(h)) return -1;
+    if (op < 0 || op >= IG_N_OPS) { h->err = "ig_apply: bad op"; return -1; }
+    if (id_frag < 0 || id_frag >= h->nf || id_cand < 0 || id_cand >= h->nf) { h->err = "ig_apply: fragment out of range"; return -1; }
+    int* hs = h->h_small;
+    hs[0] = 1; hs[1] = id_frag; hs[2] = id_cand;
+    CK(cudaMemcpyAsync(&h->sc->n_cands, hs, 3 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    int32_t saved[12];
+    CK(cudaMemcpyAsync(saved, h->sc->valid, sizeof saved, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const FragRec* live = h->live[h->cur];
+    k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, 0);
+    k_find_cuts<<<dim3((h->nf + 255) / 256, 1), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc);
+    k_build_desc<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc);
+    // test_copy_struct only re-runs get_bounds for op >= 12 (CL:2121-2126): restore the list otherwise
+    CK(cudaMemcpyAsync(h->sc->valid, saved, sizeof saved, cudaMemcpyHostToDevice, h->stream));
+    if (apply_and_post(h, 0, op)) return -2;
+    ig_step_result r;
+    if (fetch_result(h, 1, &id_cand, &r, true)) return -2;
+    r.op_sampled = op; r.id_f_sampled = id_cand; r.cand_index = 0;
+    if (out) *out = r;
+    return 0;
+}
+
+extern "C" int ig_full_likelihood(ig_handle* h, const float p8[8], int32_t use_stale_coords, double out3[3]) {
+    if (use(h)) return -1;
+    const float mbar = h->cfg.mean_sub_len_kb;
+    Params p; memcpy(&p, p8, sizeof p);
+    k_set_params<<<1, 1, 0, h->stream>>>(h->sc, p, 1);
+    k_exz_table<<<std::min(1024, (h->ns + 256) / 256), 256, 0, h->stream>>>(h->exz_test, h->ns + 1, h->sc, mbar, 1);
+    const int write = (use_stale_coords && h->coords_ever) ? 0 : 1;
+    if (write) { h->coords_ever = true; h->coords_fresh = true; }
+    k_coords<<<h->n_part_zc, IG_THREADS, 0, h->stream>>>(h->live[h->cur], h->sub, h->coord, h->clen, h->ns, h->sc, mbar, 1,
+                                                        h->part_zc, h->part_nc, write);
+    k_reduce<<<1, 256, 0, h->stream>>>(h->part_zc, h->n_part_zc, &h->sc->full_out[1], h->part_nc, &h->sc->full_nintra);
+    k_full_lnz<<<h->n_part_full, IG_THREADS, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->ns, h->sc, mbar, 1,
+                                                            h->exz_test, h->part_full);
+    k_reduce<<<1, 256, 0, h->stream>>>(h->part_full, h->n_part_full, &h->sc->full_out[0], nullptr, nullptr);
+    if (launch_ok(h, "full_likelihood")) return -2;
+    CK(cudaMemcpyAsync(h->h_sc, h->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    out3[0] = h->h_sc->full_out[0];
+    out3[1] = h->h_sc->full_out[1];
+    out3[2] = (double)h->h_sc->full_nintra;
+    return 0;
+}
+
+extern "C" int ig_distance_histogram(ig_handle* h, double bin_kb, double max_kb, int32_t n_rows, int32_t n_bins,
+                                     int64_t* hist, int64_t* rows_used) {
+    if (use(h)) return -1;
+    if (n_bins <= 0 || n_bins > (1 << 16) - 1) { h->err = "ig_distance_histogram: n_bins out of range"; return -1; }
+    if (n_rows > h->ns) n_rows = h->ns;
+    CK(cudaMemsetAsync(h->d_hist, 0, sizeof(unsigned long long) * (n_bins + 1), h->stream));
+    k_histogram<<<h->n_part_full, IG_THREADS, 0, h->stream>>>(h->row_ptr, h->cv, h->sym_diag, h->init_live, h->sub, n_rows, bin_kb,
+                                                             max_kb, n_bins, h->d_hist, h->d_hist + n_bins);
+    if (launch_ok(h, "histogram")) return -2;
+    std::vector<unsigned long long> tmp(n_bins + 1);
+    CK(cudaMemcpyAsync(tmp.data(), h->d_hist, sizeof(unsigned long long) * (n_bins + 1), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < n_bins; i++) hist[i] = (int64_t)tmp[i];
+    *rows_used = (int64_t)tmp[n_bins];
+    return 0;
+}
+
+extern "C" int ig_set_sym_diag(ig_handle* h, const int32_t* diag) {
+    if (use(h)) return -1;
+    if (!h->sym_diag) { if (dev_alloc(h, &h->sym_diag, h->ns)) return -2; }
+    CK(cudaMemcpy(h->sym_diag, diag, sizeof(int) * h->ns, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int ig_device_state_ptr(ig_handle* h, void** dev_ptr, int64_t* n_bytes) {
+    if (use(h)) return -1;
+    CK(cudaStreamSynchronize(h->stream));
+    *dev_ptr = h->live[h->cur];
+    *n_bytes = (int64_t)sizeof(FragRec) * h->nf;
+    return 0;
+}

@@ -1,0 +1,216 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes facade), against
+(1) golden trajectories recorded from the reference, (2) the oracle on seeded random scaffolds
+(incl. circular contigs), (3) size-independent properties at a larger size."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, load_golden
+from instagraal_b200.synth import WORKLOADS, SynthSpec, make_level
+from parity_common import FIELDS13, replay
+
+pytestmark = pytest.mark.gpu
+
+P8 = np.array([2.2354, 1.4933294, 0.06928191, -0.9384134, 2.0, 386.88467, 65.71848, 0.01698581], dtype=np.float32)
+P8_RIPPE = np.array([50.0, 9.6, np.float32(0.53 * (9.6 / 50.0) ** -1.5 * 50.0 ** -3), -1.5, 2.0, 900.0, 4.0e5, 0.02],
+                    dtype=np.float32)
+
+
+def make_sampler(level, **kw):
+    from instagraal_b200.cuda_lib_gl_single import sampler
+    return sampler(*level.sampler_args(), **kw)
+
+
+class GpuImpl:
+    def __init__(self, level):
+        self.s = make_sampler(level)
+        self.dt = np.float32(0.01)
+
+    def set_state(self, st):
+        self.s._set_state(st)
+
+    def set_valid(self, v):
+        self.s.set_valid_insert(v)
+
+    def set_params(self, p8):
+        self.s.set_param_simu(p8)
+
+    def get_state(self):
+        return self.s._get_state()
+
+    def eval_nuisance(self, p8):
+        from instagraal_b200.cuda_lib_gl_single import PARAM_SIMU_RIPPE
+        self.s.param_simu_test = np.array([tuple(np.asarray(p8, dtype=np.float32).tolist())], dtype=PARAM_SIMU_RIPPE)
+        return self.s.eval_likelihood_4_nuisance()
+
+    def step(self, a, cands):
+        r = self.s.step_sampler(a, 5, self.dt, candidates=cands)
+        return dict(scores=self.s.all_scores, op=r[2], B=r[3], o=r[0], dist=r[1], mean_len=r[4], n_contigs=r[5])
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_cuda_replays_reference_trajectory(built, name):
+    g = load_golden(name)
+    level = make_level(WORKLOADS[str(g["workload"])])
+    impl = GpuImpl(level)
+    res = replay(g, impl)
+    assert not res.errors, res.errors[:4]
+    assert res.same_choice >= 0.9 * res.steps
+    assert res.nuis_checked > 0
+    assert res.max_rel < 1e-7
+    impl.s.free_gpu()
+
+
+def _oracle(level, p8):
+    from oracle.sampler_oracle import OracleSampler
+    return OracleSampler(level, p8)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_cuda_vs_oracle_random_scaffolds_with_circular_contigs(built, seed):
+    """eval (score) + apply on random scaffolds the trajectories never reach (circular contigs,
+    reversed fragments), every op forced once through ig_apply."""
+    from oracle import moves as mv
+    from oracle.fuzz import random_state
+    level = make_level(WORKLOADS["micro"])
+    rng = np.random.RandomState(seed)
+    s = make_sampler(level)
+    s.set_param_simu(P8)
+    o = _oracle(level, P8)
+    nf = level.n_frags
+    for it in range(12):
+        st = random_state(nf, rng, p_circ=0.4)
+        # keep the real fragment lengths so coordinates stay meaningful
+        for k in ("len_bp", "sub_len"):
+            st[k] = np.asarray(level.S_o_A_frags[k], dtype=np.int32).copy()
+        st = _rebuild_offsets(st)
+        st13 = np.stack([st[k] for k in FIELDS13]).astype(np.int32)
+        a, b = [int(x) for x in rng.choice(nf, 2, replace=False)]
+        valid0 = rng.choice([-1, 1], 12).astype(np.int32)
+        s._set_state(st13)
+        s.set_valid_insert(valid0)
+        got = s.eval_all_sub_likelihood(a, b, 1)
+        o.live = {k: st[k].copy() for k in FIELDS13}
+        o.valid = valid0.tolist()
+        import oracle.score as sc
+        o.v_cur = sc.fill_vect_dist(o.live, o.sub)
+        lnz = sc.full_likelihood_nz(o.v_cur, o.coo, o.params, o.mbar)
+        id_host = o.live["id_c"].copy()
+        max_id = int(o.live["id_c"].max())
+        want, uniq, n_sub = o.score_candidate(a, b, max_id, 1, id_host, lnz)
+        assert np.array_equal(want != 0, got != 0), (it, a, b)
+        nz = want != 0
+        assert s.n_sub_vals[0] == n_sub
+        tol = 1e-5 * np.abs(want[nz] - want[nz].max()) + 2e-8 * np.abs(want[nz]) + 1e-9
+        assert np.all(np.abs(got[nz] - want[nz]) <= tol), (it, a, b, np.max(np.abs(got[nz] - want[nz])))
+        assert np.array_equal(s.get_valid_insert(), np.array(o.valid, dtype=np.int32))
+        # apply one op (cycling through all 24) and compare the whole integer state
+        op = (it * 2 + seed) % 24
+        s._set_state(st13)
+        s.set_valid_insert(valid0)
+        s.test_copy_struct(a, b, op)
+        new, _ = mv.apply_family({k: st[k].copy() for k in FIELDS13}, a, b, op, max_id)
+        new, _, _ = mv.renumber_contigs(new)
+        got_state = s._get_state()
+        for i, k in enumerate(FIELDS13):
+            assert np.array_equal(got_state[i], new[k]), (it, op, k)
+    s.free_gpu()
+
+
+def _rebuild_offsets(st):
+    """recompute start_bp / sub_pos / contig totals after swapping in real fragment lengths"""
+    for c in np.unique(st["id_c"]):
+        mem = np.flatnonzero(st["id_c"] == c)
+        mem = mem[np.argsort(st["pos"][mem])]
+        bp = np.cumsum(st["len_bp"][mem]) - st["len_bp"][mem]
+        sp = np.cumsum(st["sub_len"][mem]) - st["sub_len"][mem]
+        st["start_bp"][mem] = bp
+        st["sub_pos"][mem] = sp
+        st["l_cont_bp"][mem] = st["len_bp"][mem].sum()
+        st["sub_l_cont"][mem] = st["sub_len"][mem].sum()
+    return st
+
+
+def test_cuda_histogram_matches_oracle(built):
+    from oracle.sampler_oracle import distance_histogram
+    level = make_level(WORKLOADS["toy"])
+    s = make_sampler(level)
+    id_start = np.nonzero(level.S_o_A_frags["start_bp"] == 0)[0]
+    max_kb = level.S_o_A_frags["l_cont_bp"][id_start].max() / 1000.0
+    bin_kb = level.S_o_A_sub_frags["len_bp"].mean() / 1000.0 / 2.0
+    n_rows = level.n_frags // 10
+    bins, hist, used = s.distance_histogram(max_kb, bin_kb, n_rows)
+    obins, omean, oused = distance_histogram(level.sparse_matrix, level.S_o_A_frags, level.np_sub_frags_2_frags,
+                                             n_rows, max_kb, bin_kb)
+    assert used == oused and len(bins) == len(obins)
+    assert np.array_equal(hist, np.round(omean * oused).astype(np.int64))  # integer-exact sums
+    s.free_gpu()
+
+
+def test_full_fit_path_runs_like_the_reference(built):
+    """estimate_parameters_rippe -> param_simu identical to the reference's fit on the same data."""
+    g = load_golden("toy_bomb_seed2")
+    level = make_level(WORKLOADS["toy"])
+    s = make_sampler(level)
+    max_kb, bin_kb, _ = g["hist_args"]
+    s.estimate_parameters_rippe(max_kb, bin_kb, False)
+    got = np.array(list(s.param_simu[0]), dtype=np.float32)
+    assert np.allclose(got, g["params8"], rtol=1e-5), (got, g["params8"])
+    s.free_gpu()
+
+
+def test_free_running_chain_determinism_and_invariants(built):
+    """Size-independent properties on a yeast-like level (config T): two chains with the same seed
+    produce bit-identical trajectories (deterministic reductions), scaffold invariants
+    hold after every cycle, the incremental bookkeeping (n_contigs) matches a recount."""
+    level = make_level(WORKLOADS["T"])
+    outs = []
+    for rep in range(2):
+        s = make_sampler(level)
+        s.set_param_simu(P8_RIPPE)
+        np.random.seed(5)
+        s.bomb_the_genome()
+        traj = []
+        frs = np.arange(level.n_frags)
+        np.random.shuffle(frs)
+        for f in frs[:300]:
+            r = s.step_sampler(int(f), 5, np.float32(0.01))
+            traj.append((float(r[0]), int(r[2]), int(r[3]), int(r[5])))
+        st = s._get_state()
+        outs.append((traj, st))
+        d = {k: st[i] for i, k in enumerate(FIELDS13)}
+        assert (d["pos"] >= 0).all() and (d["l_cont"] > 0).all()
+        assert ((d["start_bp"] == 0) == (d["pos"] == 0)).all()
+        assert (d["l_cont_bp"] > d["start_bp"]).all()
+        assert int((d["pos"] == 0).sum()) == int(s.n_contigs)
+        for c in np.unique(d["id_c"])[:50]:
+            mem = np.flatnonzero(d["id_c"] == c)
+            assert sorted(d["pos"][mem].tolist()) == list(range(len(mem)))
+            o = mem[np.argsort(d["pos"][mem])]
+            assert np.array_equal(d["start_bp"][o], np.cumsum(d["len_bp"][o]) - d["len_bp"][o])
+        assert s.q4_hits == 0
+        s.free_gpu()
+    assert outs[0][0] == outs[1][0]
+    assert np.array_equal(outs[0][1], outs[1][1])
+    # the chain must actually assemble something
+    assert outs[0][0][-1][3] < level.n_frags
+
+
+def test_last_block_quirk_switch(built):
+    """compat_last_block=False sums every contact: scores may only differ for uniq slots >= n_sub % 64."""
+    level = make_level(WORKLOADS["micro"])
+    a, b = 3, 4
+    res = []
+    for compat in (True, False):
+        s = make_sampler(level, compat_last_block=compat)
+        s.set_param_simu(P8)
+        res.append((s.eval_all_sub_likelihood(a, b, 1), s.n_sub_vals[0]))
+        s.free_gpu()
+    (s1, n1), (s0, n0) = res
+    assert n1 == n0
+    t = n1 % 64
+    order = [m for m in range(24) if s1[m] != 0]
+    for k, m in enumerate(order):
+        if k < t or t == 0:
+            assert s1[m] == s0[m]
+        else:
+            assert s1[m] >= s0[m]  # the quirk drops (negative) terms
