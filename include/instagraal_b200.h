@@ -108,6 +108,11 @@ int ig_distance_histogram(ig_handle* h, double bin_kb, double max_kb, int32_t n_
 /* diagonal of (M + M^T) at level L-1 (self contacts): only the p(s) histogram sees it (CL:2257-2288) */
 int ig_set_sym_diag(ig_handle* h, const int32_t* diag);
 
+/* measurement hooks (no reference counterpart): per-kernel CUDA-event timing on the handle's stream
+ * and the scoring kernel's algorithmic traffic counters; see bench.py */
+int ig_set_profiling(ig_handle* h, int32_t on);
+int ig_get_stats(ig_handle* h, double out10[10], int32_t reset);
+
 /* replica chains (one handle per GPU/process): exchange {likelihood, n_contigs, live id_c/pos/ori...}
  * is done by the host facade over NCCL; the library only exposes the packed best-state buffer. */
 int ig_device_state_ptr(ig_handle* h, void** dev_ptr, int64_t* n_bytes);

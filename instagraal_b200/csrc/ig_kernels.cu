@@ -61,6 +61,8 @@ struct DevScalars {
     double likelihood;
     double full_out[3];
     int full_nintra, pad_;
+    // measurement: algorithmic traffic of the scoring kernel, accumulated over steps
+    unsigned long long st_contacts, st_rows, st_frags, st_selected, st_proposals;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -414,14 +416,14 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
         int rows_stride, int* __restrict__ row_cnt, float mbar, const float* __restrict__ exz_tab,
         double* __restrict__ part_nz,   // [cand][gridDim.x][25]  (24 uniq slots + current)
         double* __restrict__ part_z,    // [cand][gridDim.x][25]
-        int* __restrict__ part_i)       // [cand][gridDim.x][26]  (24 intra + current intra + n_sub)
+        int* __restrict__ part_i)       // [cand][gridDim.x][27]  (24 intra + current intra + n_sub + contacts read)
 {
     const int k = blockIdx.y;
     if (k >= sc->n_cands) return;
     __shared__ IgDescriptor d;
     __shared__ RowMut rm[IG_WARPS_PER_BLOCK][IG_N_OPS];
     __shared__ double red[IG_WARPS_PER_BLOCK][26];
-    __shared__ int redi[IG_WARPS_PER_BLOCK][26];
+    __shared__ int redi[IG_WARPS_PER_BLOCK][27];
     {
         const int* src = reinterpret_cast<const int*>(desc_g + k);
         int* dst = reinterpret_cast<int*>(&d);
@@ -442,7 +444,7 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
     double acc_cur = 0.0;
     double zacc = 0.0;   // lane u < n_uniq: zero term of mutation uniq[u]; lane 24: current state
     int iacc = 0;        // idem for the intra pixel count
-    int nsel = 0;
+    int nsel = 0, nread = 0;
     const int my_op = lane < n_uniq ? d.uniq[lane] : -1;
 
     for (int ri = wg; ri < ci_k.n_rows; ri += nw) {
@@ -465,6 +467,7 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
         }
         __syncwarp();
         const long long b = row_ptr[r], e = row_ptr[r + 1];
+        if (lane == 0) nread += (int)(e - b);
         int row_sel = 0;
         for (long long q = b + lane; q < e; q += 32) {
             const int2 c = __ldg(&cv[q]);
@@ -521,12 +524,12 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
     }
     __syncthreads();
     if (lane < 25) { red[w][lane] = zacc; redi[w][lane] = iacc; }
-    if (lane == 0) redi[w][25] = nsel;
+    if (lane == 0) { redi[w][25] = nsel; redi[w][26] = nread; }
     __syncthreads();
-    if (threadIdx.x < 26) {
+    if (threadIdx.x < 27) {
         int iv = 0;
         for (int ww = 0; ww < IG_WARPS_PER_BLOCK; ww++) iv += redi[ww][threadIdx.x];
-        part_i[pb * 26 + threadIdx.x] = iv;
+        part_i[pb * 27 + threadIdx.x] = iv;
         if (threadIdx.x < 25) {
             double v = 0.0;
             for (int ww = 0; ww < IG_WARPS_PER_BLOCK; ww++) v += red[ww][threadIdx.x];
@@ -549,7 +552,7 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
     if (k >= sc->n_cands) return;
     __shared__ double sm[32];
     __shared__ double s_nz[25], s_z[25], s_corr[IG_N_OPS];
-    __shared__ int s_i[26];
+    __shared__ int s_i[27];
     __shared__ double t_val[IG_N_OPS][64];
     __shared__ int2 t_cv[64];
     __shared__ int t_row[64];
@@ -570,9 +573,9 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
         double tz = block_sum(z, sm);
         if (threadIdx.x == 0) s_z[s] = tz;
     }
-    if (threadIdx.x < 26) {
+    if (threadIdx.x < 27) {
         int iv = 0;
-        for (int i = 0; i < n_part; i++) iv += part_i[((size_t)k * n_part + i) * 26 + threadIdx.x];
+        for (int i = 0; i < n_part; i++) iv += part_i[((size_t)k * n_part + i) * 27 + threadIdx.x];
         s_i[threadIdx.x] = iv;
     }
     if (threadIdx.x < IG_N_OPS) s_corr[threadIdx.x] = 0.0;
@@ -628,6 +631,11 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
         sc->ci[k].n_sub = n_sub;
         n_uniq_out[k] = n_uniq;
         n_sub_out[k] = n_sub;
+        atomicAdd(&sc->st_contacts, (unsigned long long)s_i[26]);
+        atomicAdd(&sc->st_rows, (unsigned long long)ci_k.n_rows);
+        atomicAdd(&sc->st_frags, (unsigned long long)(d.A.l_cont + (ci_k.same ? 0 : d.B.l_cont)));
+        atomicAdd(&sc->st_selected, (unsigned long long)n_sub);
+        atomicAdd(&sc->st_proposals, (unsigned long long)n_uniq);
         for (int m = 0; m < IG_N_OPS; m++) sc->scores[k * IG_N_OPS + m] = 0.0;
         for (int u = 0; u < n_uniq; u++) {
             const int m = d.uniq[u];
@@ -811,6 +819,11 @@ struct ig_handle {
     DevScalars* h_sc;  // pinned mirror
     int* h_small;      // pinned scratch (cands, nuniq, nsub)
     bool params_set, coords_fresh, coords_ever;
+    // measurement (CUDA events on the launching stream)
+    cudaEvent_t ev[6];
+    double ms_step, ms_score, ms_full;
+    long long n_launches, n_steps;
+    int profile;
     std::string err;
 };
 
@@ -869,6 +882,8 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
 #define CKC(x) do { int r_ = (x); if (r_) { g_err = h->err; ig_destroy(h); return r_; } } while (0)
     auto body = [&]() -> int {
         CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 6; i++) CK(cudaEventCreate(&h->ev[i]));
+        h->ms_step = h->ms_score = h->ms_full = 0.0; h->n_launches = 0; h->n_steps = 0; h->profile = 0;
         const int nf = h->nf, ns = h->ns;
         if (dev_alloc(h, &h->live[0], nf) || dev_alloc(h, &h->live[1], nf) || dev_alloc(h, &h->init_live, nf)) return -2;
         if (dev_alloc(h, &h->sub, ns) || dev_alloc(h, &h->coord, ns) || dev_alloc(h, &h->clen, ns)) return -2;
@@ -885,7 +900,7 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
         h->grid_score = sms * 2;  // 2 resident CTAs of 8 warps per SM (launch bounds)
         if (dev_alloc(h, &h->part_nz, (size_t)IG_MAX_CANDS * h->grid_score * 25)) return -2;
         if (dev_alloc(h, &h->part_z, (size_t)IG_MAX_CANDS * h->grid_score * 25)) return -2;
-        if (dev_alloc(h, &h->part_i, (size_t)IG_MAX_CANDS * h->grid_score * 26)) return -2;
+        if (dev_alloc(h, &h->part_i, (size_t)IG_MAX_CANDS * h->grid_score * 27)) return -2;
         h->n_part_full = sms * 8;
         if (dev_alloc(h, &h->part_full, h->n_part_full)) return -2;
         h->n_part_zc = sms * 2;
@@ -953,6 +968,7 @@ extern "C" void ig_destroy(ig_handle* h) {
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_sc) cudaFreeHost(h->h_sc);
     if (h->h_small) cudaFreeHost(h->h_small);
+    for (int i = 0; i < 6; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -1049,9 +1065,12 @@ static int refresh_current(ig_handle* h) {
     k_coords<<<h->n_part_zc, IG_THREADS, 0, h->stream>>>(h->live[h->cur], h->sub, h->coord, h->clen, h->ns, h->sc, mbar, 0,
                                                         h->part_zc, h->part_nc, 1);
     k_reduce<<<1, 256, 0, h->stream>>>(h->part_zc, h->n_part_zc, &h->sc->z_cur, h->part_nc, &h->sc->nintra_cur);
+    if (h->profile) cudaEventRecord(h->ev[2], h->stream);
     k_full_lnz<<<h->n_part_full, IG_THREADS, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->ns, h->sc, mbar, 0, h->exz,
                                                             h->part_full);
+    if (h->profile) cudaEventRecord(h->ev[3], h->stream);
     k_reduce<<<1, 256, 0, h->stream>>>(h->part_full, h->n_part_full, &h->sc->lnz_full, nullptr, nullptr);
+    h->n_launches += 4;
     h->coords_fresh = true; h->coords_ever = true;
     return launch_ok(h, "refresh_current");
 }
@@ -1072,9 +1091,12 @@ static int score_candidates(ig_handle* h, int a, const int32_t* cands, int n, in
     k_rows_count<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks);
     k_rows_scan<<<n, 256, 0, h->stream>>>(h->chunk_cnt, h->n_chunks, h->sc);
     k_rows_write<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks, h->rows, h->ns);
+    if (h->profile) cudaEventRecord(h->ev[4], h->stream);
     k_score<<<dim3(h->grid_score, n), IG_THREADS, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, live, h->sub, h->sc, h->desc,
                                                                  h->rows, h->ns, h->row_cnt, mbar, h->exz, h->part_nz, h->part_z,
                                                                  h->part_i);
+    if (h->profile) cudaEventRecord(h->ev[5], h->stream);
+    h->n_launches += 8;
     k_finalize<<<n, 256, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, live, h->sub, h->sc, h->desc, h->rows, h->ns,
                                          h->row_cnt, mbar, h->exz, h->part_nz, h->part_z, h->part_i, h->grid_score, h->cfg.n_pix,
                                          h->cfg.compat_last_block, h->d_nuniq, h->d_nsub);
@@ -1088,6 +1110,7 @@ static int apply_and_post(ig_handle* h, int forced_cand, int forced_op) {
     h->cur ^= 1;
     k_post<<<(nf + 255) / 256, 256, 0, h->stream>>>(h->live[h->cur], nf, h->init_prev, h->init_next, h->orientable, h->sc);
     h->coords_fresh = false;
+    h->n_launches += 3;
     return launch_ok(h, "apply");
 }
 
@@ -1116,11 +1139,23 @@ extern "C" int ig_step(ig_handle* h, int32_t id_frag, const int32_t* cands, int3
     if (use(h)) return -1;
     if (!h->params_set) { h->err = "ig_step: parameters not set (ig_set_params)"; return -1; }
     if (!out) { h->err = "ig_step: null result"; return -1; }
+    cudaEventRecord(h->ev[0], h->stream);
     if (refresh_current(h)) return -2;
     if (int rc = score_candidates(h, id_frag, cands, n_cands, 1)) return rc;
     k_select<<<1, 32, 0, h->stream>>>(h->sc);
+    h->n_launches += 1;
     if (apply_and_post(h, -1, -1)) return -2;
-    return fetch_result(h, n_cands, cands, out, true);
+    cudaEventRecord(h->ev[1], h->stream);
+    int rc = fetch_result(h, n_cands, cands, out, true);
+    if (rc) return rc;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->ms_step += ms;
+    if (h->profile) {
+        if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) h->ms_full += ms;
+        if (cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]) == cudaSuccess) h->ms_score += ms;
+    }
+    h->n_steps++;
+    return 0;
 }
 
 extern "C" int ig_eval_scores(ig_handle* h, int32_t id_frag, int32_t id_cand, int32_t flip_eject, double out24[24],
@@ -1213,5 +1248,29 @@ extern "C" int ig_device_state_ptr(ig_handle* h, void** dev_ptr, int64_t* n_byte
     CK(cudaStreamSynchronize(h->stream));
     *dev_ptr = h->live[h->cur];
     *n_bytes = (int64_t)sizeof(FragRec) * h->nf;
+    return 0;
+}
+
+// measurement: device time (CUDA events on the handle's stream) and algorithmic traffic counters.
+// out[0..2] = ms in ig_step total / in k_score / in k_full_lnz (the latter two only while
+// profiling is on); out[3] = kernel launches; out[4] = steps; out[5..9] = contacts read, rows,
+// fragments, contacts selected, proposals scored by the scoring kernel.
+extern "C" int ig_get_stats(ig_handle* h, double out10[10], int32_t reset) {
+    if (use(h)) return -1;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(h->h_sc, h->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost));
+    out10[0] = h->ms_step; out10[1] = h->ms_score; out10[2] = h->ms_full;
+    out10[3] = (double)h->n_launches; out10[4] = (double)h->n_steps;
+    out10[5] = (double)h->h_sc->st_contacts; out10[6] = (double)h->h_sc->st_rows; out10[7] = (double)h->h_sc->st_frags;
+    out10[8] = (double)h->h_sc->st_selected; out10[9] = (double)h->h_sc->st_proposals;
+    if (reset) {
+        h->ms_step = h->ms_score = h->ms_full = 0.0; h->n_launches = 0; h->n_steps = 0;
+        CK(cudaMemset(&h->sc->st_contacts, 0, 5 * sizeof(unsigned long long)));
+    }
+    return 0;
+}
+extern "C" int ig_set_profiling(ig_handle* h, int32_t on) {
+    if (!h) return -1;
+    h->profile = on ? 1 : 0;
     return 0;
 }

@@ -200,6 +200,22 @@ class sampler:
         L.check(self._h, L.lib().ig_set_params(self._h, _ptr(p)), "ig_set_params")
         self.param_simu = np.array([tuple(p.tolist())], dtype=PARAM_SIMU_RIPPE)
 
+    def device_state(self):
+        """(device pointer, n_bytes) of the live scaffold records (64 B per fragment) for replica exchange."""
+        ptr, n = C.c_void_p(), C.c_int64(0)
+        L.check(self._h, L.lib().ig_device_state_ptr(self._h, C.byref(ptr), C.byref(n)), "ig_device_state_ptr")
+        return int(ptr.value), int(n.value)
+
+    def set_profiling(self, on):
+        L.check(self._h, L.lib().ig_set_profiling(self._h, int(bool(on))), "ig_set_profiling")
+
+    def get_stats(self, reset=False):
+        out = np.zeros(10, dtype=np.float64)
+        L.check(self._h, L.lib().ig_get_stats(self._h, _ptr(out), int(bool(reset))), "ig_get_stats")
+        keys = ("ms_step", "ms_score", "ms_full", "launches", "steps", "contacts_read", "rows", "frags",
+                "contacts_selected", "proposals")
+        return dict(zip(keys, out.tolist()))
+
     def free_gpu(self):
         if self._h is not None:
             L.lib().ig_destroy(self._h)
