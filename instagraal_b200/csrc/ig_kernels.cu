@@ -58,9 +58,12 @@ struct DevScalars {
     int q4_hits;
     int n_heads; long long sum_l_cont; long long dist_half;
     double scores[IG_MAX_CANDS * IG_N_OPS];
+    double z_new[IG_MAX_CANDS * IG_N_OPS];    // zero-term sum Z of the whole scaffold under each scored move
+    int nintra_new[IG_MAX_CANDS * IG_N_OPS];  // intra pixel count under each scored move
     double likelihood;
     double full_out[3];
     int full_nintra, pad_;
+    unsigned int ticket_cuts[IG_MAX_CANDS], ticket_rows[IG_MAX_CANDS];  // last-block-done counters
     // measurement: algorithmic traffic of the scoring kernel, accumulated over steps
     unsigned long long st_contacts, st_rows, st_frags, st_selected, st_proposals;
 };
@@ -297,51 +300,62 @@ __global__ void k_cand_setup(const FragRec* __restrict__ live, DevScalars* sc, I
         c.up_a = max(0, pfa - n_bounds - A.sub_len); c.down_a = min(A.sub_l_cont - 1, pfa + n_bounds + A.sub_len);
         c.up_b = max(0, pfb - B.sub_len); c.down_b = min(B.sub_l_cont - 1, pfb + B.sub_len);
         c.n_rows = 0; c.n_sub = 0; c.row_hi = -1;
+        sc->ticket_cuts[k] = 0; sc->ticket_rows[k] = 0;
     }
     for (int i = 0; i < 12; i++) sc->valid[i] = prev_valid[i];  // state after the last candidate (CL:1854-1870)
 }
-// K3: cut fragments of get_bounds (KA:2255-2269), all candidates at once
-__global__ void k_find_cuts(const FragRec* __restrict__ live, int nf, const DevScalars* __restrict__ sc, IgDescriptor* desc) {
+// K3: cut fragments of get_bounds (KA:2255-2269), all candidates at once; the LAST block to finish a
+//     candidate then evaluates every pivot of its descriptor (one thread).
+__global__ void __launch_bounds__(256)
+k_find_cuts(const FragRec* __restrict__ live, int nf, DevScalars* sc, IgDescriptor* desc) {
     const int k = blockIdx.y;
     if (k >= sc->n_cands) return;
+    __shared__ int is_last;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nf) return;
     IgDescriptor& d = desc[k];
-    const Frag f = live[i].f;
-    if (f.id_c != d.A.id_c) return;
+    if (i < nf) {
+        const Frag f = live[i].f;
+        if (f.id_c == d.A.id_c) {
 #pragma unroll
-    for (int c = 0; c < IG_N_CUT; c++) {
-        if (f.pos == d.cut_pos_down[c]) d.f_down[c] = i;
-        if (f.pos == d.cut_pos_up[c]) d.f_up[c] = i;
+            for (int c = 0; c < IG_N_CUT; c++) {
+                if (f.pos == d.cut_pos_down[c]) d.f_down[c] = i;
+                if (f.pos == d.cut_pos_up[c]) d.f_up[c] = i;
+            }
+        }
     }
-}
-// K4: all pivots (one thread per candidate)
-__global__ void k_build_desc(const FragRec* __restrict__ live, const DevScalars* __restrict__ sc, IgDescriptor* desc) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= sc->n_cands) return;
-    ig_build_descriptor(desc[k], [&](int i) { return live[i].f; });
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&sc->ticket_cuts[k], 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        __threadfence();
+        ig_build_descriptor(desc[k], [&](int j) { return live[j].f; });
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
 // K5-7: ORDERED list of the CSR rows (sub-fragments) that belong to the <=2 affected contigs.
 __device__ __forceinline__ bool row_affected(const CoordRec& c, const CandInfo& ci) { return c.id_c == ci.id_a || c.id_c == ci.id_b; }
 __global__ void __launch_bounds__(IG_ROW_CHUNK)
-k_rows_count(const CoordRec* __restrict__ coord, int ns, const DevScalars* __restrict__ sc, int* __restrict__ chunk_cnt, int n_chunks) {
+k_rows_count(const CoordRec* __restrict__ coord, int ns, DevScalars* sc, int* __restrict__ chunk_cnt, int n_chunks) {
     const int k = blockIdx.y;
     if (k >= sc->n_cands) return;
+    __shared__ int is_last, carry;
+    __shared__ int wsum[32];
     const int r = blockIdx.x * IG_ROW_CHUNK + threadIdx.x;
     const bool f = r < ns && row_affected(coord[r], sc->ci[k]);
-    const int c = __syncthreads_count(f);
-    if (threadIdx.x == 0) chunk_cnt[k * n_chunks + blockIdx.x] = c;
-}
-__global__ void k_rows_scan(int* __restrict__ chunk_cnt, int n_chunks, DevScalars* sc) {
-    const int k = blockIdx.x;
-    if (k >= sc->n_cands) return;
-    __shared__ int carry;
-    __shared__ int wsum[32];
-    if (threadIdx.x == 0) carry = 0;
+    const int cnt = __syncthreads_count(f);
+    if (threadIdx.x == 0) {
+        chunk_cnt[k * n_chunks + blockIdx.x] = cnt;
+        __threadfence();
+        is_last = (atomicAdd(&sc->ticket_rows[k], 1u) == gridDim.x - 1);
+        carry = 0;
+    }
     __syncthreads();
-    int* c = chunk_cnt + k * n_chunks;
+    if (!is_last) return;
+    // the last block to finish this candidate turns the chunk counts into exclusive offsets
+    __threadfence();
+    volatile int* c = chunk_cnt + k * n_chunks;
     for (int base = 0; base < n_chunks; base += blockDim.x) {
         const int i = base + threadIdx.x;
         const int v = i < n_chunks ? c[i] : 0;
@@ -352,10 +366,10 @@ __global__ void k_rows_scan(int* __restrict__ chunk_cnt, int n_chunks, DevScalar
         if (lane == 31) wsum[w] = x;
         __syncthreads();
         if (w == 0) {
-            int s = lane < (blockDim.x >> 5) ? wsum[lane] : 0;
+            int s2 = lane < (blockDim.x >> 5) ? wsum[lane] : 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
-            wsum[lane] = s;
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s2, o); if (lane >= o) s2 += y; }
+            wsum[lane] = s2;
         }
         __syncthreads();
         const int excl = carry + (w ? wsum[w - 1] : 0) + x - v;
@@ -368,7 +382,7 @@ __global__ void k_rows_scan(int* __restrict__ chunk_cnt, int n_chunks, DevScalar
 }
 __global__ void __launch_bounds__(IG_ROW_CHUNK)
 k_rows_write(const CoordRec* __restrict__ coord, int ns, const DevScalars* __restrict__ sc, const int* __restrict__ chunk_off,
-             int n_chunks, int* __restrict__ rows, int rows_stride) {
+             int n_chunks, int* __restrict__ rows, int* __restrict__ rowidx, int rows_stride) {
     const int k = blockIdx.y;
     if (k >= sc->n_cands) return;
     __shared__ int wsum[32];
@@ -388,6 +402,7 @@ k_rows_write(const CoordRec* __restrict__ coord, int ns, const DevScalars* __res
     if (f) {
         const int off = chunk_off[k * n_chunks + blockIdx.x] + (w ? wsum[w - 1] : 0) + __popc(b & ((1u << lane) - 1));
         rows[(size_t)k * rows_stride + off] = r;
+        rowidx[(size_t)k * rows_stride + r] = off;
     }
 }
 
@@ -404,26 +419,27 @@ __device__ __forceinline__ bool contact_selected(const CoordRec& ci, const Coord
     return sel && (val > 0);
 }
 
-struct RowMut { float dist; int id_c; int pos; float s_tot; };  // row endpoint under one mutation
+struct RowMut { float dist; int id_c; int pos; float s_tot; };  // one sub-fragment under one mutation
 
-// K8: THE scoring kernel (replaces fill_vect_dist x24, slice_sp_mat, host sort, prepare_sparse_call,
-//     extract_sub_likelihood, eval_all_likelihood_on_zero_1st, eval_sub_likelihood).
-//     grid = (G, n_cands); warp per affected row; lanes stride that row's contacts.
-__global__ void __launch_bounds__(IG_THREADS, 2)
-k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, const CoordRec* __restrict__ coord,
-        const int* __restrict__ clen, const FragRec* __restrict__ live, const SubRec* __restrict__ sub,
-        const DevScalars* __restrict__ sc, const IgDescriptor* __restrict__ desc_g, const int* __restrict__ rows,
-        int rows_stride, int* __restrict__ row_cnt, float mbar, const float* __restrict__ exz_tab,
-        double* __restrict__ part_nz,   // [cand][gridDim.x][25]  (24 uniq slots + current)
-        double* __restrict__ part_z,    // [cand][gridDim.x][25]
-        int* __restrict__ part_i)       // [cand][gridDim.x][27]  (24 intra + current intra + n_sub + contacts read)
+// transposed partial layout: part[(k * n_slots + slot) * n_blocks + block]
+#define PART_IDX(k, nslots, slot, nblocks, blk) ((((size_t)(k) * (nslots) + (slot)) * (nblocks)) + (blk))
+
+// K8a: mutated coordinates of every affected sub-fragment under every scored mutation, evaluated
+//      ONCE per (row, mutation) (replaces fill_vect_dist x24, KA:3699-3760) + the zero terms
+//      (eval_all_likelihood_on_zero_1st, KA:3919-4002) restricted to the affected contigs.
+//      Warp per affected row, lane u = uniq slot u, lane 24 = current state.
+__global__ void __launch_bounds__(IG_THREADS)
+k_precompute(const CoordRec* __restrict__ coord, const int* __restrict__ clen, const FragRec* __restrict__ live,
+             const SubRec* __restrict__ sub, const DevScalars* __restrict__ sc, const IgDescriptor* __restrict__ desc_g,
+             const int* __restrict__ rows, int ns, RowMut* __restrict__ table, int* __restrict__ table_len, float mbar,
+             double* __restrict__ part_z,  // [cand][25][gridDim.x]
+             int* __restrict__ part_i)     // [cand][25][gridDim.x]
 {
     const int k = blockIdx.y;
     if (k >= sc->n_cands) return;
     __shared__ IgDescriptor d;
-    __shared__ RowMut rm[IG_WARPS_PER_BLOCK][IG_N_OPS];
-    __shared__ double red[IG_WARPS_PER_BLOCK][26];
-    __shared__ int redi[IG_WARPS_PER_BLOCK][27];
+    __shared__ double red[IG_WARPS_PER_BLOCK][25];
+    __shared__ int redi[IG_WARPS_PER_BLOCK][25];
     {
         const int* src = reinterpret_cast<const int*>(desc_g + k);
         int* dst = reinterpret_cast<int*>(&d);
@@ -431,43 +447,74 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
     }
     __syncthreads();
     const Params p = sc->p;
-    const double l10v = sc->log10_vinter;
-    const CandInfo ci_k = sc->ci[k];
+    const int n_rows = sc->ci[k].n_rows;
     const int n_uniq = d.n_uniq;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int wg = blockIdx.x * IG_WARPS_PER_BLOCK + w, nw = gridDim.x * IG_WARPS_PER_BLOCK;
-    const int* my_rows = rows + (size_t)k * rows_stride;
-
-    double acc[IG_N_OPS];
-#pragma unroll
-    for (int m = 0; m < IG_N_OPS; m++) acc[m] = 0.0;
-    double acc_cur = 0.0;
-    double zacc = 0.0;   // lane u < n_uniq: zero term of mutation uniq[u]; lane 24: current state
-    int iacc = 0;        // idem for the intra pixel count
-    int nsel = 0, nread = 0;
+    const int* my_rows = rows + (size_t)k * ns;
     const int my_op = lane < n_uniq ? d.uniq[lane] : -1;
-
-    for (int ri = wg; ri < ci_k.n_rows; ri += nw) {
+    double zacc = 0.0;
+    int iacc = 0;
+    for (int ri = wg; ri < n_rows; ri += nw) {
         const int r = my_rows[ri];
-        const CoordRec ci = coord[r];
         const SubRec si = sub[r];
-        const Frag fi = live[si.parent].f;
-        __syncwarp();
         if (my_op >= 0) {
-            Frag fm = ig_eval_op(d, my_op, fi, si.parent);
+            const Frag fi = live[si.parent].f;
+            const Frag fm = ig_eval_op(d, my_op, fi, si.parent);
             int len;
-            CoordRec c = coords_of(fm, si, &len);
-            rm[w][lane].dist = c.dist; rm[w][lane].id_c = c.id_c; rm[w][lane].pos = c.pos; rm[w][lane].s_tot = c.s_tot;
+            const CoordRec c = coords_of(fm, si, &len);
+            RowMut m; m.dist = c.dist; m.id_c = c.id_c; m.pos = c.pos; m.s_tot = c.s_tot;
+            const size_t ti = ((size_t)k * IG_N_OPS + lane) * ns + ri;
+            table[ti] = m; table_len[ti] = len;
             if (c.pos == 0) iacc += intra_pairs(len);
             zacc += zero_term(c.pos, len, c.s_tot, p, mbar);
         } else if (lane == IG_LANE_CUR) {
+            const CoordRec ci = coord[r];
             const int len = clen[r];
             if (ci.pos == 0) iacc += intra_pairs(len);
             zacc += zero_term(ci.pos, len, ci.s_tot, p, mbar);
         }
-        __syncwarp();
+    }
+    if (lane < 25) { red[w][lane] = zacc; redi[w][lane] = iacc; }
+    __syncthreads();
+    if (threadIdx.x < 25) {
+        double v = 0.0; int iv = 0;
+        for (int ww = 0; ww < IG_WARPS_PER_BLOCK; ww++) { v += red[ww][threadIdx.x]; iv += redi[ww][threadIdx.x]; }
+        part_z[PART_IDX(k, 25, threadIdx.x, gridDim.x, blockIdx.x)] = v;
+        part_i[PART_IDX(k, 25, threadIdx.x, gridDim.x, blockIdx.x)] = iv;
+    }
+}
+
+// K8b: THE scoring kernel (replaces slice_sp_mat + host sort + prepare_sparse_call +
+//      extract_sub_likelihood + eval_sub_likelihood).  grid = (G, n_cands).  Work item = (affected
+//      CSR row, group of GS uniq slots); a warp takes one item at a time, its lanes stride the row's
+//      contacts with coalesced 8-byte (col,val) loads.  The group size adapts to the amount of work
+//      (GS = 24 when there are more rows than warps, down to 1 when a candidate has only a handful
+//      of rows) so small assemblies still fill the 148 SMs.  Mutated coordinates of both endpoints
+//      come from the table written by k_precompute (row side: warp-uniform broadcast loads; column
+//      side: rowidx gather, contiguous across neighbouring contacts).
+template <int GS>
+__device__ __forceinline__ void score_items(
+    const long long* __restrict__ row_ptr, const int2* __restrict__ cv, const CoordRec* __restrict__ coord,
+    const int* __restrict__ clen, const int* __restrict__ my_rows, const int* __restrict__ my_idx, int ns,
+    int* __restrict__ my_row_cnt, const RowMut* __restrict__ tab, const int* __restrict__ tlen, float mbar,
+    const float* __restrict__ exz_tab, const Params& p, double l10v, const CandInfo& ci_k, int n_uniq,
+    double* __restrict__ wred /* [25] this warp's slot sums */, int* __restrict__ wredi /* [2] */) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int wg = blockIdx.x * IG_WARPS_PER_BLOCK + w, nw = gridDim.x * IG_WARPS_PER_BLOCK;
+    constexpr int NG = IG_N_OPS / GS;
+    const int n_items = ci_k.n_rows * NG;
+    for (int it = wg; it < n_items; it += nw) {
+        const int ri = it / NG, g = it - ri * NG;
+        const int u0 = g * GS;
+        if (u0 >= n_uniq && g != 0) continue;
+        const int r = my_rows[ri];
+        const CoordRec ci = coord[r];
         const long long b = row_ptr[r], e = row_ptr[r + 1];
-        if (lane == 0) nread += (int)(e - b);
+        double acc[GS];
+#pragma unroll
+        for (int j = 0; j < GS; j++) acc[j] = 0.0;
+        double acc_cur = 0.0;
         int row_sel = 0;
         for (long long q = b + lane; q < e; q += 32) {
             const int2 c = __ldg(&cv[q]);
@@ -476,126 +523,162 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
             if (!contact_selected(ci, cj, c.y, ci_k)) continue;
             row_sel++;
             const double ob = (double)c.y, obc = ob_const(ob);
-            const int len_j_cur = clen[c.x];
-            const double t_cur = contact_term(ci, cj, len_j_cur, ob, obc, p, l10v, mbar, exz_tab);
+            const double t_cur = contact_term(ci, cj, clen[c.x], ob, obc, p, l10v, mbar, exz_tab);
             acc_cur += t_cur;
-            const SubRec sj = sub[c.x];
-            const Frag fj = live[sj.parent].f;
-#pragma unroll 1
-            for (int u = 0; u < n_uniq; u++) {
-                const Frag fm = ig_eval_op(d, d.uniq[u], fj, sj.parent);
-                int len_j;
-                const CoordRec cjm = coords_of(fm, sj, &len_j);
-                CoordRec cim;
-                cim.dist = rm[w][u].dist; cim.id_c = rm[w][u].id_c; cim.pos = rm[w][u].pos; cim.s_tot = rm[w][u].s_tot;
-                double t;
-                // bit-exact shortcut: identical inputs give the identical term
-                const bool same_in = (cim.id_c == cjm.id_c) == (ci.id_c == cj.id_c) && cim.s_tot == ci.s_tot &&
-                                     (cim.id_c != cjm.id_c ||
-                                      (fabsf(cim.dist - cjm.dist) == fabsf(ci.dist - cj.dist) &&
-                                       abs(cim.pos - cjm.pos) == abs(ci.pos - cj.pos) &&
-                                       (ci.s_tot == 0 || len_j == len_j_cur)));
-                if (same_in) t = t_cur;
-                else t = contact_term(cim, cjm, len_j, ob, obc, p, l10v, mbar, exz_tab);
+            const int rj = my_idx[c.x];
+            const bool cur_same = ci.id_c == cj.id_c;
+            const float cur_s = fabsf(ci.dist - cj.dist);
+            const int cur_dp = abs(ci.pos - cj.pos);
 #pragma unroll
-                for (int m = 0; m < IG_N_OPS; m++) if (m == u) acc[m] += t;  // keeps acc[] in registers
+            for (int j = 0; j < GS; j++) {
+                const int u = u0 + j;
+                if (u < n_uniq) {
+                    const RowMut a = tab[(size_t)u * ns + ri];
+                    const RowMut bm = tab[(size_t)u * ns + rj];
+                    CoordRec cim, cjm;
+                    cim.dist = a.dist; cim.id_c = a.id_c; cim.pos = a.pos; cim.s_tot = a.s_tot;
+                    cjm.dist = bm.dist; cjm.id_c = bm.id_c; cjm.pos = bm.pos; cjm.s_tot = bm.s_tot;
+                    const bool m_same = cim.id_c == cjm.id_c;
+                    double t;
+                    if (m_same == cur_same && cim.s_tot == ci.s_tot &&
+                        (!m_same || (cim.s_tot == 0 && fabsf(cim.dist - cjm.dist) == cur_s && abs(cim.pos - cjm.pos) == cur_dp))) {
+                        t = t_cur;  // bit-exact shortcut: identical inputs give the identical term
+                    } else {
+                        const int len_j = (m_same && cim.s_tot != 0) ? tlen[(size_t)u * ns + rj] : 0;
+                        t = contact_term(cim, cjm, len_j, ob, obc, p, l10v, mbar, exz_tab);
+                    }
+                    acc[j] += t;
+                }
             }
         }
-        row_sel = __reduce_add_sync(0xffffffffu, row_sel);
-        if (lane == 0) row_cnt[(size_t)k * rows_stride + ri] = row_sel;
-        nsel += (lane == 0) ? row_sel : 0;
-    }
-    // ---- deterministic block reduction: lane -> warp -> block
+        // fixed-order accumulation into this warp's slot sums (work items are visited in a fixed order)
 #pragma unroll
-    for (int u = 0; u < IG_N_OPS; u++) {
-        double v = warp_sum(acc[u]);
-        if (lane == 0) red[w][u] = v;
-    }
-    {
-        double v = warp_sum(acc_cur);
-        if (lane == 0) red[w][24] = v;
-    }
-    __syncthreads();
-    const size_t pb = ((size_t)k * gridDim.x + blockIdx.x);
-    if (threadIdx.x < 25) {
-        double v = 0.0;
-        for (int ww = 0; ww < IG_WARPS_PER_BLOCK; ww++) v += red[ww][threadIdx.x];
-        part_nz[pb * 25 + threadIdx.x] = v;
-    }
-    __syncthreads();
-    if (lane < 25) { red[w][lane] = zacc; redi[w][lane] = iacc; }
-    if (lane == 0) { redi[w][25] = nsel; redi[w][26] = nread; }
-    __syncthreads();
-    if (threadIdx.x < 27) {
-        int iv = 0;
-        for (int ww = 0; ww < IG_WARPS_PER_BLOCK; ww++) iv += redi[ww][threadIdx.x];
-        part_i[pb * 27 + threadIdx.x] = iv;
-        if (threadIdx.x < 25) {
-            double v = 0.0;
-            for (int ww = 0; ww < IG_WARPS_PER_BLOCK; ww++) v += red[ww][threadIdx.x];
-            part_z[pb * 25 + threadIdx.x] = v;
+        for (int j = 0; j < GS; j++) {
+            const double v = warp_sum(acc[j]);
+            if (lane == 0 && u0 + j < n_uniq) wred[u0 + j] += v;
+        }
+        if (g == 0) {
+            const double v = warp_sum(acc_cur);
+            row_sel = __reduce_add_sync(0xffffffffu, row_sel);
+            if (lane == 0) { wred[24] += v; my_row_cnt[ri] = row_sel; wredi[0] += row_sel; wredi[1] += (int)(e - b); }
         }
     }
 }
 
-// K9: per-candidate finalisation: fixed-order reduction of the block partials, the reference's
-//     last-block quirk (KA:4362), zero terms (eval_all_likelihood_on_zero_2nd KA:4005-4027) and
-//     score assembly (eval_all_scores KA:4029-4046).  One block of 256 threads per candidate.
+__global__ void __launch_bounds__(IG_THREADS, 2)
+k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, const CoordRec* __restrict__ coord,
+        const int* __restrict__ clen, const DevScalars* __restrict__ sc, const IgDescriptor* __restrict__ desc_g,
+        const int* __restrict__ rows, const int* __restrict__ rowidx, int ns, int* __restrict__ row_cnt,
+        const RowMut* __restrict__ table, const int* __restrict__ table_len, float mbar, const float* __restrict__ exz_tab,
+        double* __restrict__ part_nz,   // [cand][25][gridDim.x]  (24 uniq slots + current)
+        int* __restrict__ part_c)       // [cand][2][gridDim.x]   (contacts selected, contacts read)
+{
+    const int k = blockIdx.y;
+    if (k >= sc->n_cands) return;
+    __shared__ double red[IG_WARPS_PER_BLOCK][25];
+    __shared__ int redi[IG_WARPS_PER_BLOCK][2];
+    const Params p = sc->p;
+    const double l10v = sc->log10_vinter;
+    const CandInfo ci_k = sc->ci[k];
+    const int n_uniq = desc_g[k].n_uniq;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane < 25) red[w][lane] = 0.0;
+    if (lane < 2) redi[w][lane] = 0;
+    __syncwarp();
+    const int* my_rows = rows + (size_t)k * ns;
+    const int* my_idx = rowidx + (size_t)k * ns;
+    int* my_cnt = row_cnt + (size_t)k * ns;
+    const RowMut* tab = table + (size_t)k * IG_N_OPS * ns;
+    const int* tlen = table_len + (size_t)k * IG_N_OPS * ns;
+    const int nw = gridDim.x * IG_WARPS_PER_BLOCK;
+#define IG_SCORE(GS) score_items<GS>(row_ptr, cv, coord, clen, my_rows, my_idx, ns, my_cnt, tab, tlen, mbar, exz_tab, p, l10v, \
+                                     ci_k, n_uniq, red[w], redi[w])
+    if (ci_k.n_rows >= nw) IG_SCORE(24);
+    else if (ci_k.n_rows * 4 >= nw) IG_SCORE(6);
+    else if (ci_k.n_rows * 8 >= nw) IG_SCORE(3);
+    else IG_SCORE(1);
+#undef IG_SCORE
+    __syncthreads();
+    if (threadIdx.x < 25) {
+        double v = 0.0;
+        for (int ww = 0; ww < IG_WARPS_PER_BLOCK; ww++) v += red[ww][threadIdx.x];
+        part_nz[PART_IDX(k, 25, threadIdx.x, gridDim.x, blockIdx.x)] = v;
+    }
+    if (threadIdx.x < 2) {
+        int iv = 0;
+        for (int ww = 0; ww < IG_WARPS_PER_BLOCK; ww++) iv += redi[ww][threadIdx.x];
+        part_c[PART_IDX(k, 2, threadIdx.x, gridDim.x, blockIdx.x)] = iv;
+    }
+}
+
+// K9: per-candidate finalisation: fixed-order parallel reduction of the block partials, the
+//     reference's last-block quirk (KA:4362), zero terms (eval_all_likelihood_on_zero_2nd
+//     KA:4005-4027) and score assembly (eval_all_scores KA:4029-4046).  One block per candidate.
 __global__ void __launch_bounds__(256)
 k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, const CoordRec* __restrict__ coord,
-           const int* __restrict__ clen, const FragRec* __restrict__ live, const SubRec* __restrict__ sub,
-           DevScalars* sc, const IgDescriptor* __restrict__ desc_g, const int* __restrict__ rows, int rows_stride,
-           const int* __restrict__ row_cnt, float mbar, const float* __restrict__ exz_tab,
-           const double* __restrict__ part_nz, const double* __restrict__ part_z, const int* __restrict__ part_i,
-           int n_part, double n_pix, int compat_last_block, int* __restrict__ n_uniq_out, int* __restrict__ n_sub_out) {
+           DevScalars* sc, const IgDescriptor* __restrict__ desc_g, const int* __restrict__ rows, const int* __restrict__ rowidx,
+           int ns, const int* __restrict__ row_cnt, const RowMut* __restrict__ table, const int* __restrict__ table_len,
+           float mbar, const float* __restrict__ exz_tab, const double* __restrict__ part_nz, const int* __restrict__ part_c,
+           int n_part, const double* __restrict__ part_z, const int* __restrict__ part_i, int n_part_z, double n_pix,
+           int compat_last_block, int* __restrict__ n_uniq_out, int* __restrict__ n_sub_out) {
     const int k = blockIdx.x;
     if (k >= sc->n_cands) return;
-    __shared__ double sm[32];
     __shared__ double s_nz[25], s_z[25], s_corr[IG_N_OPS];
-    __shared__ int s_i[27];
+    __shared__ int s_i[25], s_c[2];
     __shared__ double t_val[IG_N_OPS][64];
     __shared__ int2 t_cv[64];
-    __shared__ int t_row[64];
+    __shared__ int t_ri[64];
     __shared__ int t_cnt;
     const IgDescriptor& d = desc_g[k];
     const Params p = sc->p;
     const double l10v = sc->log10_vinter;
     const CandInfo ci_k = sc->ci[k];
     const int n_uniq = d.n_uniq;
-    for (int s = 0; s < 25; s++) {
-        double v = 0.0, z = 0.0;
-        for (int i = threadIdx.x; i < n_part; i += blockDim.x) {
-            v += part_nz[((size_t)k * n_part + i) * 25 + s];
-            z += part_z[((size_t)k * n_part + i) * 25 + s];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    // 25 + 25 + 25 + 2 slots, one warp per slot, lanes stride the partial blocks, fixed shuffle tree
+    for (int slot = w; slot < 77; slot += nwarp) {
+        if (slot < 25) {
+            double v = 0.0;
+            for (int i = lane; i < n_part; i += 32) v += part_nz[PART_IDX(k, 25, slot, n_part, i)];
+            v = warp_sum(v);
+            if (lane == 0) s_nz[slot] = v;
+        } else if (slot < 50) {
+            double v = 0.0;
+            for (int i = lane; i < n_part_z; i += 32) v += part_z[PART_IDX(k, 25, slot - 25, n_part_z, i)];
+            v = warp_sum(v);
+            if (lane == 0) s_z[slot - 25] = v;
+        } else if (slot < 75) {
+            int v = 0;
+            for (int i = lane; i < n_part_z; i += 32) v += part_i[PART_IDX(k, 25, slot - 50, n_part_z, i)];
+            v = __reduce_add_sync(0xffffffffu, v);
+            if (lane == 0) s_i[slot - 50] = v;
+        } else {
+            int v = 0;
+            for (int i = lane; i < n_part; i += 32) v += part_c[PART_IDX(k, 2, slot - 75, n_part, i)];
+            v = __reduce_add_sync(0xffffffffu, v);
+            if (lane == 0) s_c[slot - 75] = v;
         }
-        double tv = block_sum(v, sm);
-        if (threadIdx.x == 0) s_nz[s] = tv;
-        double tz = block_sum(z, sm);
-        if (threadIdx.x == 0) s_z[s] = tz;
-    }
-    if (threadIdx.x < 27) {
-        int iv = 0;
-        for (int i = 0; i < n_part; i++) iv += part_i[((size_t)k * n_part + i) * 27 + threadIdx.x];
-        s_i[threadIdx.x] = iv;
     }
     if (threadIdx.x < IG_N_OPS) s_corr[threadIdx.x] = 0.0;
     __syncthreads();
-    const int n_sub = s_i[25];
+    const int n_sub = s_c[0];
     const int t = n_sub % 64;
+    const RowMut* tab = table + (size_t)k * IG_N_OPS * ns;
+    const int* tlen = table_len + (size_t)k * IG_N_OPS * ns;
     // ---- last-block quirk: uniq slots u >= t lose the final (n_sub % 64) contacts of the row-sorted slice
     if (compat_last_block && t > 0 && t < n_uniq) {
         if (threadIdx.x == 0) {  // serial, hence deterministic, collection of the last t selected contacts
             int need = t, n = 0;
             for (int ri = ci_k.n_rows - 1; ri >= 0 && need > 0; ri--) {
-                if (row_cnt[(size_t)k * rows_stride + ri] == 0) continue;
-                const int r = rows[(size_t)k * rows_stride + ri];
+                if (row_cnt[(size_t)k * ns + ri] == 0) continue;
+                const int r = rows[(size_t)k * ns + ri];
                 const CoordRec ci = coord[r];
                 for (long long q = row_ptr[r + 1] - 1; q >= row_ptr[r] && need > 0; q--) {
                     const int2 c = cv[q];
                     const CoordRec cj = coord[c.x];
                     if (!(cj.id_c == ci_k.id_a || cj.id_c == ci_k.id_b)) continue;
                     if (!contact_selected(ci, cj, c.y, ci_k)) continue;
-                    t_cv[n] = c; t_row[n] = r; n++; need--;
+                    t_cv[n] = c; t_ri[n] = ri; n++; need--;
                 }
             }
             t_cnt = n;
@@ -604,15 +687,15 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
         const int n_items = t_cnt * (n_uniq - t);
         for (int idx = threadIdx.x; idx < n_items; idx += blockDim.x) {
             const int e = idx % t_cnt, u = t + idx / t_cnt;
-            const int r = t_row[e];
             const int2 c = t_cv[e];
-            const SubRec si = sub[r], sj = sub[c.x];
-            const Frag fim = ig_eval_op(d, d.uniq[u], live[si.parent].f, si.parent);
-            const Frag fjm = ig_eval_op(d, d.uniq[u], live[sj.parent].f, sj.parent);
-            int li, lj;
-            const CoordRec cim = coords_of(fim, si, &li), cjm = coords_of(fjm, sj, &lj);
+            const RowMut a = tab[(size_t)u * ns + t_ri[e]];
+            const int rj = rowidx[(size_t)k * ns + c.x];
+            const RowMut bm = tab[(size_t)u * ns + rj];
+            CoordRec cim, cjm;
+            cim.dist = a.dist; cim.id_c = a.id_c; cim.pos = a.pos; cim.s_tot = a.s_tot;
+            cjm.dist = bm.dist; cjm.id_c = bm.id_c; cjm.pos = bm.pos; cjm.s_tot = bm.s_tot;
             const double ob = (double)c.y;
-            t_val[u][e] = contact_term(cim, cjm, lj, ob, ob_const(ob), p, l10v, mbar, exz_tab);
+            t_val[u][e] = contact_term(cim, cjm, tlen[(size_t)u * ns + rj], ob, ob_const(ob), p, l10v, mbar, exz_tab);
         }
         __syncthreads();
         if (threadIdx.x >= t && threadIdx.x < n_uniq) {
@@ -623,54 +706,81 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
         __syncthreads();
     }
     // ---- scores
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < IG_N_OPS) sc->scores[k * IG_N_OPS + threadIdx.x] = 0.0;
+    __syncthreads();
+    if (threadIdx.x < n_uniq) {
+        const int u = threadIdx.x;
         const double log_e = (double)LOG10E_F;
-        const double lnz_full = sc->lnz_full;
-        const double lsub_cur = s_nz[24];
-        sc->lsub_cur[k] = lsub_cur;
+        const int m = d.uniq[u];
+        // Z[m] over ALL sub-fragments = Z_cur(all) - Z_cur(affected rows) + Z_m(affected rows)
+        const double z = sc->z_cur - s_z[24] + s_z[u];
+        const int n_intra = sc->nintra_cur - s_i[24] + s_i[u];  // int32 wrap-consistent
+        const double val_inter = -1.0 * log_e * (n_pix - __int2double_rn(n_intra)) * p.v_inter;
+        const double lz = z * log_e + val_inter;
+        const double lnz = s_nz[u] - ((u >= t && compat_last_block && t > 0) ? s_corr[u] : 0.0);
+        sc->scores[k * IG_N_OPS + m] = lnz + lz + sc->lnz_full - s_nz[24];
+        sc->z_new[k * IG_N_OPS + m] = z;
+        sc->nintra_new[k * IG_N_OPS + m] = n_intra;
+    }
+    if (threadIdx.x == 0) {
+        sc->lsub_cur[k] = s_nz[24];
         sc->ci[k].n_sub = n_sub;
         n_uniq_out[k] = n_uniq;
         n_sub_out[k] = n_sub;
-        atomicAdd(&sc->st_contacts, (unsigned long long)s_i[26]);
+        atomicAdd(&sc->st_contacts, (unsigned long long)s_c[1]);
         atomicAdd(&sc->st_rows, (unsigned long long)ci_k.n_rows);
         atomicAdd(&sc->st_frags, (unsigned long long)(d.A.l_cont + (ci_k.same ? 0 : d.B.l_cont)));
         atomicAdd(&sc->st_selected, (unsigned long long)n_sub);
         atomicAdd(&sc->st_proposals, (unsigned long long)n_uniq);
-        for (int m = 0; m < IG_N_OPS; m++) sc->scores[k * IG_N_OPS + m] = 0.0;
-        for (int u = 0; u < n_uniq; u++) {
-            const int m = d.uniq[u];
-            // Z[m] = Z(all sub-frags under m) = Z_cur_total - Z_cur(affected rows) + Z_m(affected rows)
-            const double z = sc->z_cur - s_z[24] + s_z[u];
-            const int n_intra = sc->nintra_cur - s_i[24] + s_i[u];  // int32 wrap-consistent
-            const double val_inter = -1.0 * log_e * (n_pix - __int2double_rn(n_intra)) * p.v_inter;
-            const double lz = z * log_e + val_inter;
-            const double lnz = s_nz[u] - ((u >= t && compat_last_block && t > 0) ? s_corr[u] : 0.0);
-            sc->scores[k * IG_N_OPS + m] = lnz + lz + lnz_full - lsub_cur;
-        }
     }
 }
 
 // K10: move selection (CL:1435-1446): scores==0 -> -inf; first index of the maximum.
 __global__ void k_select(DevScalars* sc) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    __shared__ double sm[IG_MAX_CANDS * IG_N_OPS];
     const int n = sc->n_cands * IG_N_OPS;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = sc->scores[i];
+    __syncthreads();
+    if (threadIdx.x != 0) return;
     int best = -1;
     double bv = 0.0;
     for (int i = 0; i < n; i++) {
-        const double v = sc->scores[i];
+        const double v = sm[i];
         if (v == 0.0) continue;
         if (best < 0 || v > bv) { best = i; bv = v; }
     }
     if (best < 0) best = 0;  // np.argmax of an all-zero filtered vector
     sc->win_cand = best / IG_N_OPS;
     sc->win_op = best % IG_N_OPS;
-    sc->likelihood = sc->scores[best];
+    sc->likelihood = sm[best];
+    sc->n_heads = 0; sc->sum_l_cont = 0; sc->dist_half = 0;  // accumulators of k_post
+}
+// step path: selection + the bookkeeping of k_post_scalars in one launch (k_apply reads the label base
+// from the descriptor, not from sc->max_label, so bumping it here cannot race)
+__global__ void k_select_step(DevScalars* sc, const IgDescriptor* __restrict__ desc_g) {
+    __shared__ double sm[IG_MAX_CANDS * IG_N_OPS];
+    const int n = sc->n_cands * IG_N_OPS;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = sc->scores[i];
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    int best = -1;
+    double bv = 0.0;
+    for (int i = 0; i < n; i++) {
+        const double v = sm[i];
+        if (v == 0.0) continue;
+        if (best < 0 || v > bv) { best = i; bv = v; }
+    }
+    if (best < 0) best = 0;
+    const int kc = best / IG_N_OPS, op = best % IG_N_OPS;
+    sc->win_cand = kc; sc->win_op = op; sc->likelihood = sm[best];
+    sc->n_heads = 0; sc->sum_l_cont = 0; sc->dist_half = 0;
+    if (op >= 12) for (int i = 0; i < 12; i++) sc->valid[i] = desc_g[kc].valid[i];
+    sc->max_label += 2;
 }
 
 // K11: apply the winning move to every fragment (test_copy_struct + copy_struct, CL:2094-2151)
 __global__ void __launch_bounds__(256)
-k_apply(const FragRec* __restrict__ live, FragRec* __restrict__ next, int nf, DevScalars* sc, const IgDescriptor* __restrict__ desc_g,
-        int forced_cand, int forced_op) {
+k_apply(FragRec* __restrict__ live, int nf, DevScalars* sc, const IgDescriptor* __restrict__ desc_g, int forced_cand, int forced_op) {
     __shared__ IgDescriptor d;
     const int kc = forced_cand >= 0 ? forced_cand : sc->win_cand;
     const int op = forced_op >= 0 ? forced_op : sc->win_op;
@@ -680,6 +790,7 @@ k_apply(const FragRec* __restrict__ live, FragRec* __restrict__ next, int nf, De
         for (int i = threadIdx.x; i < (int)(sizeof(IgDescriptor) / 4); i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
+    // every thread reads only its own fragment + the descriptor's pivots (loaded before any write): in place is safe
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nf) {
         const Frag f = live[i].f;
@@ -694,19 +805,18 @@ k_apply(const FragRec* __restrict__ live, FragRec* __restrict__ next, int nf, De
         } else {
             o = ig_eval_op(d, op, f, i);
         }
-        FragRec r; r.f = o; r.pad[0] = r.pad[1] = r.pad[2] = 0;
-        next[i] = r;
+        live[i].f = o;
     }
 }
-// K12: bookkeeping after apply: label counter, list_valid_insert (CL:2125-2126 re-runs get_bounds
-//      for ops >= 12), contig count / total length (modify_gl_cuda_buffer), dist_inter_genome.
+// bookkeeping that must not race with k_apply's reads of sc->max_label (through the descriptor it does not: the
+// descriptor carries max_id) -- label counter and list_valid_insert (CL:2125-2126 re-runs get_bounds for ops >= 12)
 __global__ void k_post_scalars(DevScalars* sc, const IgDescriptor* __restrict__ desc_g, int forced_cand, int forced_op) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const int kc = forced_cand >= 0 ? forced_cand : sc->win_cand;
     const int op = forced_op >= 0 ? forced_op : sc->win_op;
     if (op >= 12) for (int i = 0; i < 12; i++) sc->valid[i] = desc_g[kc].valid[i];
     sc->max_label += 2;
-    sc->n_heads = 0; sc->sum_l_cont = 0; sc->dist_half = 0;
+    if (forced_cand >= 0) { sc->n_heads = 0; sc->sum_l_cont = 0; sc->dist_half = 0; }
 }
 __global__ void __launch_bounds__(256)
 k_post(const FragRec* __restrict__ live, int nf, const int* __restrict__ init_prev, const int* __restrict__ init_next,
@@ -796,9 +906,9 @@ struct ig_handle {
     ig_config cfg;
     int nf, ns;
     long long nnz;
-    cudaStream_t stream;
-    FragRec *live[2], *init_live;
-    int cur;
+    cudaStream_t stream, side;
+    cudaEvent_t ev_coords, ev_lnz, ev_fork;
+    FragRec *live, *init_live;
     SubRec* sub;
     CoordRec* coord;
     int* clen;
@@ -811,7 +921,9 @@ struct ig_handle {
     float *exz, *exz_test;
     int n_chunks, *chunk_cnt, *rows, *row_cnt;
     int grid_score;
-    double *part_nz, *part_z; int* part_i;
+    double *part_nz, *part_z; int *part_i, *part_c;
+    int grid_pre;
+    RowMut* table; int *table_len, *rowidx;
     double *part_full; int n_part_full;
     double *part_zc; int* part_nc; int n_part_zc;
     int *d_nuniq, *d_nsub, *d_perm;
@@ -876,16 +988,20 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
     if (cfg->n_frags <= 0 || cfg->n_sub_frags <= 0 || cfg->nnz < 0) { g_err = "ig_create: bad sizes"; return -1; }
     h = new ig_handle();
     h->cfg = *cfg; h->nf = cfg->n_frags; h->ns = cfg->n_sub_frags; h->nnz = cfg->nnz;
-    h->cur = 0; h->params_set = false; h->coords_fresh = false; h->coords_ever = false;
+    h->params_set = false; h->coords_fresh = false; h->coords_ever = false;
     cudaError_t e0 = cudaSetDevice(cfg->device);
     if (e0 != cudaSuccess) { g_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e0); delete h; return -2; }
 #define CKC(x) do { int r_ = (x); if (r_) { g_err = h->err; ig_destroy(h); return r_; } } while (0)
     auto body = [&]() -> int {
         CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->ev_coords, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_lnz, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
         for (int i = 0; i < 6; i++) CK(cudaEventCreate(&h->ev[i]));
         h->ms_step = h->ms_score = h->ms_full = 0.0; h->n_launches = 0; h->n_steps = 0; h->profile = 0;
         const int nf = h->nf, ns = h->ns;
-        if (dev_alloc(h, &h->live[0], nf) || dev_alloc(h, &h->live[1], nf) || dev_alloc(h, &h->init_live, nf)) return -2;
+        if (dev_alloc(h, &h->live, nf) || dev_alloc(h, &h->init_live, nf)) return -2;
         if (dev_alloc(h, &h->sub, ns) || dev_alloc(h, &h->coord, ns) || dev_alloc(h, &h->clen, ns)) return -2;
         if (dev_alloc(h, &h->row_ptr, (size_t)ns + 1) || dev_alloc(h, &h->cv, (size_t)h->nnz)) return -2;
         if (dev_alloc(h, &h->init_prev, nf) || dev_alloc(h, &h->init_next, nf) || dev_alloc(h, &h->orientable, nf)) return -2;
@@ -898,9 +1014,14 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
         CK(cudaGetDeviceProperties(&prop, cfg->device));
         const int sms = prop.multiProcessorCount;
         h->grid_score = sms * 2;  // 2 resident CTAs of 8 warps per SM (launch bounds)
+        h->grid_pre = sms;
         if (dev_alloc(h, &h->part_nz, (size_t)IG_MAX_CANDS * h->grid_score * 25)) return -2;
-        if (dev_alloc(h, &h->part_z, (size_t)IG_MAX_CANDS * h->grid_score * 25)) return -2;
-        if (dev_alloc(h, &h->part_i, (size_t)IG_MAX_CANDS * h->grid_score * 27)) return -2;
+        if (dev_alloc(h, &h->part_c, (size_t)IG_MAX_CANDS * h->grid_score * 2)) return -2;
+        if (dev_alloc(h, &h->part_z, (size_t)IG_MAX_CANDS * h->grid_pre * 25)) return -2;
+        if (dev_alloc(h, &h->part_i, (size_t)IG_MAX_CANDS * h->grid_pre * 25)) return -2;
+        if (dev_alloc(h, &h->table, (size_t)IG_MAX_CANDS * IG_N_OPS * ns)) return -2;
+        if (dev_alloc(h, &h->table_len, (size_t)IG_MAX_CANDS * IG_N_OPS * ns)) return -2;
+        if (dev_alloc(h, &h->rowidx, (size_t)IG_MAX_CANDS * ns)) return -2;
         h->n_part_full = sms * 8;
         if (dev_alloc(h, &h->part_full, h->n_part_full)) return -2;
         h->n_part_zc = sms * 2;
@@ -912,8 +1033,8 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
         CK(cudaMallocHost((void**)&h->h_small, 64 * sizeof(int)));
         CK(cudaMemsetAsync(h->sc, 0, sizeof(DevScalars), h->stream));
         // uploads
-        if (upload_state(h, data->frags13, h->live[0])) return -2;
-        CK(cudaMemcpy(h->init_live, h->live[0], sizeof(FragRec) * nf, cudaMemcpyDeviceToDevice));
+        if (upload_state(h, data->frags13, h->live)) return -2;
+        CK(cudaMemcpy(h->init_live, h->live, sizeof(FragRec) * nf, cudaMemcpyDeviceToDevice));
         {
             std::vector<SubRec> s(ns);
             for (int i = 0; i < ns; i++) {
@@ -961,7 +1082,7 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
 extern "C" void ig_destroy(ig_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
-    void* ptrs[] = {h->live[0], h->live[1], h->init_live, h->sub, h->coord, h->clen, h->row_ptr, h->cv, h->sym_diag,
+    void* ptrs[] = {h->live, h->part_c, h->table, h->table_len, h->rowidx, h->init_live, h->sub, h->coord, h->clen, h->row_ptr, h->cv, h->sym_diag,
                     h->init_prev, h->init_next, h->orientable, h->sc, h->desc, h->exz, h->exz_test, h->chunk_cnt,
                     h->rows, h->row_cnt, h->part_nz, h->part_z, h->part_i, h->part_full, h->part_zc, h->part_nc,
                     h->d_nuniq, h->d_nsub, h->d_perm, h->d_hist};
@@ -969,6 +1090,10 @@ extern "C" void ig_destroy(ig_handle* h) {
     if (h->h_sc) cudaFreeHost(h->h_sc);
     if (h->h_small) cudaFreeHost(h->h_small);
     for (int i = 0; i < 6; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->ev_coords) cudaEventDestroy(h->ev_coords);
+    if (h->ev_lnz) cudaEventDestroy(h->ev_lnz);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -1019,7 +1144,7 @@ extern "C" int ig_get_state(ig_handle* h, int32_t* out13) {
     if (use(h)) return -1;
     const int nf = h->nf;
     std::vector<FragRec> tmp(nf);
-    CK(cudaMemcpyAsync(tmp.data(), h->live[h->cur], sizeof(FragRec) * nf, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(tmp.data(), h->live, sizeof(FragRec) * nf, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     for (int i = 0; i < nf; i++) {
         const int* v = reinterpret_cast<const int*>(&tmp[i].f);
@@ -1030,7 +1155,7 @@ extern "C" int ig_get_state(ig_handle* h, int32_t* out13) {
 }
 extern "C" int ig_set_state(ig_handle* h, const int32_t* in13) {
     if (use(h)) return -1;
-    if (upload_state(h, in13, h->live[h->cur])) return -2;
+    if (upload_state(h, in13, h->live)) return -2;
     int maxlab = 0;
     for (int i = 0; i < h->nf; i++) maxlab = std::max(maxlab, in13[(size_t)2 * h->nf + i]);
     CK(cudaMemcpy(&h->sc->max_label, &maxlab, sizeof(int), cudaMemcpyHostToDevice));
@@ -1050,7 +1175,7 @@ extern "C" int ig_set_valid_insert(ig_handle* h, const int32_t in12[12]) {
 extern "C" int ig_bomb(ig_handle* h, const int32_t* perm) {
     if (use(h)) return -1;
     CK(cudaMemcpyAsync(h->d_perm, perm, sizeof(int) * h->nf, cudaMemcpyHostToDevice, h->stream));
-    k_explode<<<(h->nf + 255) / 256, 256, 0, h->stream>>>(h->live[h->cur], h->nf, h->d_perm);
+    k_explode<<<(h->nf + 255) / 256, 256, 0, h->stream>>>(h->live, h->nf, h->d_perm);
     if (launch_ok(h, "explode")) return -2;
     int maxlab = h->nf;  // perm values are 0..NF-1
     CK(cudaMemcpyAsync(&h->sc->max_label, &maxlab, sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -1060,22 +1185,26 @@ extern "C" int ig_bomb(ig_handle* h, const int32_t* perm) {
 }
 
 // head of step_sampler: fill_dist_single + eval_likelihood (CL:1407-1409)
-static int refresh_current(ig_handle* h) {
+static int refresh_current(ig_handle* h, cudaStream_t st, bool fork) {
     const float mbar = h->cfg.mean_sub_len_kb;
-    k_coords<<<h->n_part_zc, IG_THREADS, 0, h->stream>>>(h->live[h->cur], h->sub, h->coord, h->clen, h->ns, h->sc, mbar, 0,
-                                                        h->part_zc, h->part_nc, 1);
-    k_reduce<<<1, 256, 0, h->stream>>>(h->part_zc, h->n_part_zc, &h->sc->z_cur, h->part_nc, &h->sc->nintra_cur);
-    if (h->profile) cudaEventRecord(h->ev[2], h->stream);
-    k_full_lnz<<<h->n_part_full, IG_THREADS, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->ns, h->sc, mbar, 0, h->exz,
-                                                            h->part_full);
-    if (h->profile) cudaEventRecord(h->ev[3], h->stream);
-    k_reduce<<<1, 256, 0, h->stream>>>(h->part_full, h->n_part_full, &h->sc->lnz_full, nullptr, nullptr);
+    if (fork) {  // side stream: starts after everything already queued on the main stream
+        cudaEventRecord(h->ev_fork, h->stream);
+        cudaStreamWaitEvent(st, h->ev_fork, 0);
+    }
+    k_coords<<<h->n_part_zc, IG_THREADS, 0, st>>>(h->live, h->sub, h->coord, h->clen, h->ns, h->sc, mbar, 0, h->part_zc, h->part_nc, 1);
+    k_reduce<<<1, 256, 0, st>>>(h->part_zc, h->n_part_zc, &h->sc->z_cur, h->part_nc, &h->sc->nintra_cur);
+    if (fork) cudaEventRecord(h->ev_coords, st);
+    if (h->profile) cudaEventRecord(h->ev[2], st);
+    k_full_lnz<<<h->n_part_full, IG_THREADS, 0, st>>>(h->row_ptr, h->cv, h->coord, h->clen, h->ns, h->sc, mbar, 0, h->exz, h->part_full);
+    if (h->profile) cudaEventRecord(h->ev[3], st);
+    k_reduce<<<1, 256, 0, st>>>(h->part_full, h->n_part_full, &h->sc->lnz_full, nullptr, nullptr);
+    if (fork) cudaEventRecord(h->ev_lnz, st);
     h->n_launches += 4;
     h->coords_fresh = true; h->coords_ever = true;
     return launch_ok(h, "refresh_current");
 }
 
-static int score_candidates(ig_handle* h, int a, const int32_t* cands, int n, int first_flip_eject) {
+static int score_candidates(ig_handle* h, int a, const int32_t* cands, int n, int first_flip_eject, bool overlap) {
     if (n <= 0 || n > IG_MAX_CANDS) { h->err = "n_cands out of range"; return -1; }
     if (a < 0 || a >= h->nf) { h->err = "id_frag out of range"; return -1; }
     for (int i = 0; i < n; i++) if (cands[i] < 0 || cands[i] >= h->nf) { h->err = "candidate out of range"; return -1; }
@@ -1084,31 +1213,33 @@ static int score_candidates(ig_handle* h, int a, const int32_t* cands, int n, in
     hs[0] = n; hs[1] = a;
     for (int i = 0; i < IG_MAX_CANDS; i++) hs[2 + i] = i < n ? cands[i] : 0;
     CK(cudaMemcpyAsync(&h->sc->n_cands, hs, (2 + IG_MAX_CANDS) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    const FragRec* live = h->live[h->cur];
+    const FragRec* live = h->live;
     k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, first_flip_eject);
     k_find_cuts<<<dim3((h->nf + 255) / 256, n), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc);
-    k_build_desc<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc);
+    if (overlap) cudaStreamWaitEvent(h->stream, h->ev_coords, 0);
     k_rows_count<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks);
-    k_rows_scan<<<n, 256, 0, h->stream>>>(h->chunk_cnt, h->n_chunks, h->sc);
-    k_rows_write<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks, h->rows, h->ns);
+    k_rows_write<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks, h->rows,
+                                                                       h->rowidx, h->ns);
+    k_precompute<<<dim3(h->grid_pre, n), IG_THREADS, 0, h->stream>>>(h->coord, h->clen, live, h->sub, h->sc, h->desc, h->rows, h->ns,
+                                                                    h->table, h->table_len, mbar, h->part_z, h->part_i);
     if (h->profile) cudaEventRecord(h->ev[4], h->stream);
-    k_score<<<dim3(h->grid_score, n), IG_THREADS, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, live, h->sub, h->sc, h->desc,
-                                                                 h->rows, h->ns, h->row_cnt, mbar, h->exz, h->part_nz, h->part_z,
-                                                                 h->part_i);
+    k_score<<<dim3(h->grid_score, n), IG_THREADS, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
+                                                                 h->ns, h->row_cnt, h->table, h->table_len, mbar, h->exz, h->part_nz,
+                                                                 h->part_c);
     if (h->profile) cudaEventRecord(h->ev[5], h->stream);
-    h->n_launches += 8;
-    k_finalize<<<n, 256, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, live, h->sub, h->sc, h->desc, h->rows, h->ns,
-                                         h->row_cnt, mbar, h->exz, h->part_nz, h->part_z, h->part_i, h->grid_score, h->cfg.n_pix,
-                                         h->cfg.compat_last_block, h->d_nuniq, h->d_nsub);
+    h->n_launches += 7;
+    if (overlap) cudaStreamWaitEvent(h->stream, h->ev_lnz, 0);
+    k_finalize<<<n, 256, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->sc, h->desc, h->rows, h->rowidx, h->ns, h->row_cnt, h->table,
+                                         h->table_len, mbar, h->exz, h->part_nz, h->part_c, h->grid_score, h->part_z, h->part_i,
+                                         h->grid_pre, h->cfg.n_pix, h->cfg.compat_last_block, h->d_nuniq, h->d_nsub);
     return launch_ok(h, "score_candidates");
 }
 
 static int apply_and_post(ig_handle* h, int forced_cand, int forced_op) {
     const int nf = h->nf;
-    k_apply<<<(nf + 255) / 256, 256, 0, h->stream>>>(h->live[h->cur], h->live[h->cur ^ 1], nf, h->sc, h->desc, forced_cand, forced_op);
+    k_apply<<<(nf + 255) / 256, 256, 0, h->stream>>>(h->live, nf, h->sc, h->desc, forced_cand, forced_op);
     k_post_scalars<<<1, 1, 0, h->stream>>>(h->sc, h->desc, forced_cand, forced_op);
-    h->cur ^= 1;
-    k_post<<<(nf + 255) / 256, 256, 0, h->stream>>>(h->live[h->cur], nf, h->init_prev, h->init_next, h->orientable, h->sc);
+    k_post<<<(nf + 255) / 256, 256, 0, h->stream>>>(h->live, nf, h->init_prev, h->init_next, h->orientable, h->sc);
     h->coords_fresh = false;
     h->n_launches += 3;
     return launch_ok(h, "apply");
@@ -1140,11 +1271,14 @@ extern "C" int ig_step(ig_handle* h, int32_t id_frag, const int32_t* cands, int3
     if (!h->params_set) { h->err = "ig_step: parameters not set (ig_set_params)"; return -1; }
     if (!out) { h->err = "ig_step: null result"; return -1; }
     cudaEventRecord(h->ev[0], h->stream);
-    if (refresh_current(h)) return -2;
-    if (int rc = score_candidates(h, id_frag, cands, n_cands, 1)) return rc;
-    k_select<<<1, 32, 0, h->stream>>>(h->sc);
-    h->n_launches += 1;
-    if (apply_and_post(h, -1, -1)) return -2;
+    if (refresh_current(h, h->side, true)) return -2;
+    if (int rc = score_candidates(h, id_frag, cands, n_cands, 1, true)) return rc;
+    k_select_step<<<1, 128, 0, h->stream>>>(h->sc, h->desc);
+    k_apply<<<(h->nf + 255) / 256, 256, 0, h->stream>>>(h->live, h->nf, h->sc, h->desc, -1, -1);
+    k_post<<<(h->nf + 255) / 256, 256, 0, h->stream>>>(h->live, h->nf, h->init_prev, h->init_next, h->orientable, h->sc);
+    h->n_launches += 3;
+    h->coords_fresh = false;
+    if (launch_ok(h, "step")) return -2;
     cudaEventRecord(h->ev[1], h->stream);
     int rc = fetch_result(h, n_cands, cands, out, true);
     if (rc) return rc;
@@ -1162,8 +1296,8 @@ extern "C" int ig_eval_scores(ig_handle* h, int32_t id_frag, int32_t id_cand, in
                               int32_t* n_uniq, int32_t* n_sub) {
     if (use(h)) return -1;
     if (!h->params_set) { h->err = "ig_eval_scores: parameters not set"; return -1; }
-    if (refresh_current(h)) return -2;
-    if (int rc = score_candidates(h, id_frag, &id_cand, 1, flip_eject)) return rc;
+    if (refresh_current(h, h->stream, false)) return -2;
+    if (int rc = score_candidates(h, id_frag, &id_cand, 1, flip_eject, false)) return rc;
     ig_step_result r;
     if (fetch_result(h, 1, &id_cand, &r, false)) return -2;
     for (int i = 0; i < 24; i++) out24[i] = r.scores[i];
@@ -1182,10 +1316,9 @@ extern "C" int ig_apply(ig_handle* h, int32_t id_frag, int32_t id_cand, int32_t 
     int32_t saved[12];
     CK(cudaMemcpyAsync(saved, h->sc->valid, sizeof saved, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    const FragRec* live = h->live[h->cur];
+    const FragRec* live = h->live;
     k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, 0);
     k_find_cuts<<<dim3((h->nf + 255) / 256, 1), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc);
-    k_build_desc<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc);
     // test_copy_struct only re-runs get_bounds for op >= 12 (CL:2121-2126): restore the list otherwise
     CK(cudaMemcpyAsync(h->sc->valid, saved, sizeof saved, cudaMemcpyHostToDevice, h->stream));
     if (apply_and_post(h, 0, op)) return -2;
@@ -1204,7 +1337,7 @@ extern "C" int ig_full_likelihood(ig_handle* h, const float p8[8], int32_t use_s
     k_exz_table<<<std::min(1024, (h->ns + 256) / 256), 256, 0, h->stream>>>(h->exz_test, h->ns + 1, h->sc, mbar, 1);
     const int write = (use_stale_coords && h->coords_ever) ? 0 : 1;
     if (write) { h->coords_ever = true; h->coords_fresh = true; }
-    k_coords<<<h->n_part_zc, IG_THREADS, 0, h->stream>>>(h->live[h->cur], h->sub, h->coord, h->clen, h->ns, h->sc, mbar, 1,
+    k_coords<<<h->n_part_zc, IG_THREADS, 0, h->stream>>>(h->live, h->sub, h->coord, h->clen, h->ns, h->sc, mbar, 1,
                                                         h->part_zc, h->part_nc, write);
     k_reduce<<<1, 256, 0, h->stream>>>(h->part_zc, h->n_part_zc, &h->sc->full_out[1], h->part_nc, &h->sc->full_nintra);
     k_full_lnz<<<h->n_part_full, IG_THREADS, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->ns, h->sc, mbar, 1,
@@ -1246,7 +1379,7 @@ extern "C" int ig_set_sym_diag(ig_handle* h, const int32_t* diag) {
 extern "C" int ig_device_state_ptr(ig_handle* h, void** dev_ptr, int64_t* n_bytes) {
     if (use(h)) return -1;
     CK(cudaStreamSynchronize(h->stream));
-    *dev_ptr = h->live[h->cur];
+    *dev_ptr = h->live;
     *n_bytes = (int64_t)sizeof(FragRec) * h->nf;
     return 0;
 }
