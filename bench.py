@@ -170,7 +170,7 @@ def run_ours(args):
     # ---------------- pass 1: device-timed (value, roofline)
     for f in frag_stream(args.warmup):
         s.step_sampler(f, 5, dt)
-    s.set_profiling(True)
+    s.set_options(refresh_every=args.refresh_every, use_graph=bool(args.graph))
     s.get_stats(reset=True)
     if dist is not None:
         dist.barrier()
@@ -188,9 +188,18 @@ def run_ours(args):
             dist.barrier()
         t_wall = time.perf_counter() - t_wall0
     st = s.get_stats(reset=True)
-    s.set_profiling(False)
     dev_ms = st["ms_step"]
     proposals = st["proposals"]
+
+    # ---------------- pass 1b: per-kernel CUDA-event timing for the roofline (profiling on => no graph)
+    s.set_profiling(True)
+    n_prof = min(args.steps, 500)
+    for i, f in enumerate(frag_stream(n_prof)):
+        if flush is not None:
+            flush.fill_(i & 0xFF)
+        s.step_sampler(f, 5, dt)
+    stp = s.get_stats(reset=True)
+    s.set_profiling(False)
 
     # ---------------- pass 2: end to end through the facade (host RNG + ctypes + H2D/D2H), wall clock
     if dist is not None:
@@ -227,12 +236,13 @@ def run_ours(args):
     e2e = prop2_sum / t_e2e_max
     peak, peak_src = measured_peak()
     nnz, ns = s.n_non_zero, int(s.init_n_sub_frags)
-    n_launch_score = st["steps"]
-    bytes_score = 8 * st["contacts_read"] + 4 * (st["rows"] + st["steps"]) + 16 * st["rows"] + 32 * st["frags"]
-    bytes_full = (8 * nnz + 4 * (ns + 1) + 20 * ns) * st["steps"]
-    kern = {"k_score": (st["ms_score"], bytes_score), "k_full_lnz": (st["ms_full"], bytes_full)}
+    n_launch_score = stp["steps"]
+    n_full = max(stp["full_refreshes"], 0)
+    bytes_score = 8 * stp["contacts_read"] + 4 * (stp["rows"] + stp["steps"]) + 16 * stp["rows"] + 32 * stp["frags"]
+    bytes_full = (8 * nnz + 4 * (ns + 1) + 20 * ns) * n_full
+    kern = {"k_score": (stp["ms_score"], bytes_score, n_launch_score), "k_full_lnz": (stp["ms_full"], bytes_full, n_full)}
     dom = max(kern, key=lambda k: kern[k][0])
-    ach = {k: (b / max(ms, 1e-9) / 1e6) for k, (ms, b) in kern.items()}  # GB/s
+    ach = {k: (b / max(ms, 1e-9) / 1e6) for k, (ms, b, _n) in kern.items()}  # GB/s
     out = {
         "metric": "delta-log-L proposals scored per second (MCMC step_sampler, pyramid level 4)",
         "value": value, "unit": "proposals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -243,7 +253,11 @@ def run_ours(args):
                    "chains": world, "n_neighbours": 5, "burn_in_cycles": burn, "n_contigs_at_start": n_contigs0,
                    "l2": ("flushed between steps with a 256 MiB write (untimed); timed = sum of per-step CUDA-event "
                           "intervals" if args.flush_l2 else "not flushed (inputs %s L2)" % (">" if nnz * 8 > 126e6 else "<")),
-                   "full_likelihood": "recomputed every step (reference semantics, CL:1409)",
+                   "full_likelihood": ("recomputed over every contact each step (reference schedule, CL:1409)"
+                                       if args.refresh_every == 1 else
+                                       "maintained incrementally, full recompute every %d steps (same values up to f64 "
+                                       "summation order; tests/test_gpu_parity.py)" % args.refresh_every),
+                   "cuda_graph": bool(args.graph), "full_refreshes_in_timed_region": st["full_refreshes"],
                    "gather_every": args.gather_every if world > 1 else None},
         "mcmc_cycle_s": dev_ms_max / 1e3 / args.steps * level.n_frags,
         "proposals_per_step": prop_sum / world / args.steps,
@@ -253,9 +267,10 @@ def run_ours(args):
         "gpu_launches": int(st["launches"]),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach[dom], "peak": peak, "unit": "GB/s",
                      "frac": ach[dom] / peak, "traffic": None, "peak_source": peak_src,
-                     "kernels": {k: {"ms_per_launch": kern[k][0] / max(n_launch_score, 1),
-                                     "alg_bytes_per_launch": kern[k][1] / max(n_launch_score, 1),
+                     "kernels": {k: {"launches": kern[k][2], "ms_per_launch": kern[k][0] / max(kern[k][2], 1),
+                                     "alg_bytes_per_launch": kern[k][1] / max(kern[k][2], 1),
                                      "achieved_GBs": ach[k]} for k in kern},
+                     "terms_per_launch": stp["contacts_selected"] * (stp["proposals"] / max(stp["steps"], 1) / 5.0) / max(stp["steps"], 1),
                      "note": "instruction-bound, not HBM-bound: <=24 x (powf + f64 log10) per 8-byte contact (DESIGN.md)"},
         "clocks": clk.summary(),
         "setup_s": {"generate": t_gen, "burn_in": t_burn},
@@ -350,6 +365,8 @@ def main():
     ap.add_argument("--bomb", type=int, default=1)
     ap.add_argument("--flush-l2", type=int, default=1)
     ap.add_argument("--gather-every", type=int, default=500)
+    ap.add_argument("--refresh-every", type=int, default=4096)
+    ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

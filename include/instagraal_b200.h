@@ -112,6 +112,13 @@ int ig_set_sym_diag(ig_handle* h, const int32_t* diag);
  * and the scoring kernel's algorithmic traffic counters; see bench.py */
 int ig_set_profiling(ig_handle* h, int32_t on);
 int ig_get_stats(ig_handle* h, double out10[10], int32_t reset);
+/* refresh_every = N: recompute coordinates + full likelihood over every contact at least every N steps
+ * (1 = every step, the reference's own schedule CL:1407-1409; 0 = only after the state was changed from
+ * outside); in between they are maintained incrementally (identical up to f64 summation order).
+ * use_graph: replay each step as one CUDA graph. */
+int ig_set_options(ig_handle* h, int32_t refresh_every, int32_t use_graph);
+/* number of full refreshes among the steps covered by the last ig_get_stats call */
+int ig_get_full_refresh_count(ig_handle* h, int64_t* out);
 
 /* replica chains (one handle per GPU/process): exchange {likelihood, n_contigs, live id_c/pos/ori...}
  * is done by the host facade over NCCL; the library only exposes the packed best-state buffer. */

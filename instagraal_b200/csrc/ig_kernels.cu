@@ -60,7 +60,12 @@ struct DevScalars {
     double scores[IG_MAX_CANDS * IG_N_OPS];
     double z_new[IG_MAX_CANDS * IG_N_OPS];    // zero-term sum Z of the whole scaffold under each scored move
     int nintra_new[IG_MAX_CANDS * IG_N_OPS];  // intra pixel count under each scored move
+    double lnz_new[IG_MAX_CANDS * IG_N_OPS];  // full non-zero likelihood of the scaffold under each scored move
     double likelihood;
+    // incremental maintenance of (coordinates, lnz_full, z_cur, nintra_cur) across steps
+    double lnz_next, z_next; int nintra_next;
+    int prev_k, prev_u, prev_windowed, prev_id_a, prev_n_rows;
+    unsigned int ticket_out;
     double full_out[3];
     int full_nintra, pad_;
     unsigned int ticket_cuts[IG_MAX_CANDS], ticket_rows[IG_MAX_CANDS];  // last-block-done counters
@@ -719,6 +724,7 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
         const double lz = z * log_e + val_inter;
         const double lnz = s_nz[u] - ((u >= t && compat_last_block && t > 0) ? s_corr[u] : 0.0);
         sc->scores[k * IG_N_OPS + m] = lnz + lz + sc->lnz_full - s_nz[24];
+        sc->lnz_new[k * IG_N_OPS + m] = sc->lnz_full - s_nz[24] + s_nz[u];  // without the last-block quirk
         sc->z_new[k * IG_N_OPS + m] = z;
         sc->nintra_new[k * IG_N_OPS + m] = n_intra;
     }
@@ -776,6 +782,93 @@ __global__ void k_select_step(DevScalars* sc, const IgDescriptor* __restrict__ d
     sc->n_heads = 0; sc->sum_l_cont = 0; sc->dist_half = 0;
     if (op >= 12) for (int i = 0; i < 12; i++) sc->valid[i] = desc_g[kc].valid[i];
     sc->max_label += 2;
+    int u_star = 0;
+    for (int u = 0; u < desc_g[kc].n_uniq; u++) if (desc_g[kc].uniq[u] == op) u_star = u;
+    sc->prev_k = kc; sc->prev_u = u_star;
+    sc->prev_windowed = (sc->ci[kc].same && sc->ci[kc].is_circ == 0) ? 1 : 0;
+    sc->prev_id_a = sc->ci[kc].id_a; sc->prev_n_rows = sc->ci[kc].n_rows;
+    sc->lnz_next = sc->lnz_new[best]; sc->z_next = sc->z_new[best]; sc->nintra_next = sc->nintra_new[best];
+    sc->ticket_out = 0;
+}
+
+// Same-linear-contig moves are scored on a WINDOWED slice (slice_sp_mat, KA:565-586): contacts of the
+// contig outside the windows keep their distance mathematically, but the reference's next full
+// recomputation (CL:1409) sees their float32 coordinates re-rounded.  To keep lnz_full identical to
+// that recomputation without rescanning every contact, add exactly those contacts' term changes.
+__global__ void __launch_bounds__(IG_THREADS)
+k_lnz_outside(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, const CoordRec* __restrict__ coord,
+              const int* __restrict__ clen, DevScalars* sc, const int* __restrict__ rows, const int* __restrict__ rowidx, int ns,
+              const RowMut* __restrict__ table, const int* __restrict__ table_len, float mbar, const float* __restrict__ exz_tab,
+              double* __restrict__ part) {
+    if (!sc->prev_windowed) return;
+    __shared__ double sm[32];
+    __shared__ int is_last;
+    const int k = sc->prev_k, u = sc->prev_u;
+    const Params p = sc->p;
+    const double l10v = sc->log10_vinter;
+    const CandInfo ci_k = sc->ci[k];
+    const int lane = threadIdx.x & 31;
+    const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const int* my_rows = rows + (size_t)k * ns;
+    const int* my_idx = rowidx + (size_t)k * ns;
+    const RowMut* tab = table + ((size_t)k * IG_N_OPS + u) * ns;
+    const int* tlen = table_len + ((size_t)k * IG_N_OPS + u) * ns;
+    double acc = 0.0;
+    for (int ri = wg; ri < ci_k.n_rows; ri += nw) {
+        const int r = my_rows[ri];
+        const CoordRec ci = coord[r];
+        const RowMut a = tab[ri];
+        for (long long q = row_ptr[r] + lane; q < row_ptr[r + 1]; q += 32) {
+            const int2 c = __ldg(&cv[q]);
+            const CoordRec cj = coord[c.x];
+            if (cj.id_c != ci_k.id_a) continue;               // other contigs: inter-contig term, unchanged
+            if (contact_selected(ci, cj, c.y, ci_k)) continue;  // already inside lnz_new
+            const int rj = my_idx[c.x];
+            const RowMut bm = tab[rj];
+            CoordRec cim, cjm;
+            cim.dist = a.dist; cim.id_c = a.id_c; cim.pos = a.pos; cim.s_tot = a.s_tot;
+            cjm.dist = bm.dist; cjm.id_c = bm.id_c; cjm.pos = bm.pos; cjm.s_tot = bm.s_tot;
+            const double ob = (double)c.y, obc = ob_const(ob);
+            // the full-likelihood kernel takes the circular length from the ROW (KA:4428)
+            const double t_old = contact_term(ci, cj, clen[r], ob, obc, p, l10v, mbar, exz_tab);
+            const double t_new = contact_term(cim, cjm, tlen[ri], ob, obc, p, l10v, mbar, exz_tab);
+            acc += t_new - t_old;
+        }
+    }
+    const double tot = block_sum(acc, sm);
+    if (threadIdx.x == 0) {
+        part[blockIdx.x] = tot;
+        __threadfence();
+        is_last = (atomicAdd(&sc->ticket_out, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double v = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) v += ((volatile double*)part)[i];
+    const double all = block_sum(v, sm);
+    if (threadIdx.x == 0) sc->lnz_next += all;
+}
+
+// start of the next step in incremental mode: the coordinates of the rows touched by the last applied
+// move are taken from the mutation table (bit-identical to uni_fill_vect_dist on the new scaffold),
+// everything else is unchanged; the scalar likelihood pieces were prepared by the previous step.
+__global__ void __launch_bounds__(256)
+k_commit_coords(CoordRec* __restrict__ coord, int* __restrict__ clen, DevScalars* sc, const int* __restrict__ rows, int ns,
+                const RowMut* __restrict__ table, const int* __restrict__ table_len) {
+    const int k = sc->prev_k, u = sc->prev_u, n = sc->prev_n_rows;
+    const int* my_rows = rows + (size_t)k * ns;
+    const RowMut* tab = table + ((size_t)k * IG_N_OPS + u) * ns;
+    const int* tlen = table_len + ((size_t)k * IG_N_OPS + u) * ns;
+    for (int ri = blockIdx.x * blockDim.x + threadIdx.x; ri < n; ri += gridDim.x * blockDim.x) {
+        const int r = my_rows[ri];
+        const RowMut m = tab[ri];
+        CoordRec c; c.dist = m.dist; c.id_c = m.id_c; c.pos = m.pos; c.s_tot = m.s_tot;
+        coord[r] = c; clen[r] = tlen[ri];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc->lnz_full = sc->lnz_next; sc->z_cur = sc->z_next; sc->nintra_cur = sc->nintra_next;
+    }
 }
 
 // K11: apply the winning move to every fragment (test_copy_struct + copy_struct, CL:2094-2151)
@@ -931,6 +1024,10 @@ struct ig_handle {
     DevScalars* h_sc;  // pinned mirror
     int* h_small;      // pinned scratch (cands, nuniq, nsub)
     bool params_set, coords_fresh, coords_ever;
+    bool incr_valid; int refresh_every; long long steps_since_full;
+    double* part_out;
+    long long last_n_full;
+    cudaGraphExec_t graph[2]; bool graph_failed, capturing, use_graph; long long n_full;
     // measurement (CUDA events on the launching stream)
     cudaEvent_t ev[6];
     double ms_step, ms_score, ms_full;
@@ -989,6 +1086,8 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
     h = new ig_handle();
     h->cfg = *cfg; h->nf = cfg->n_frags; h->ns = cfg->n_sub_frags; h->nnz = cfg->nnz;
     h->params_set = false; h->coords_fresh = false; h->coords_ever = false;
+    h->incr_valid = false; h->refresh_every = 4096; h->steps_since_full = 0;
+    h->graph[0] = h->graph[1] = nullptr; h->graph_failed = false; h->capturing = false; h->use_graph = true; h->n_full = 0;
     cudaError_t e0 = cudaSetDevice(cfg->device);
     if (e0 != cudaSuccess) { g_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e0); delete h; return -2; }
 #define CKC(x) do { int r_ = (x); if (r_) { g_err = h->err; ig_destroy(h); return r_; } } while (0)
@@ -1024,6 +1123,7 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
         if (dev_alloc(h, &h->rowidx, (size_t)IG_MAX_CANDS * ns)) return -2;
         h->n_part_full = sms * 8;
         if (dev_alloc(h, &h->part_full, h->n_part_full)) return -2;
+        if (dev_alloc(h, &h->part_out, h->n_part_full)) return -2;
         h->n_part_zc = sms * 2;
         if (dev_alloc(h, &h->part_zc, h->n_part_zc) || dev_alloc(h, &h->part_nc, h->n_part_zc)) return -2;
         if (dev_alloc(h, &h->d_nuniq, IG_MAX_CANDS) || dev_alloc(h, &h->d_nsub, IG_MAX_CANDS) || dev_alloc(h, &h->d_perm, nf)) return -2;
@@ -1082,7 +1182,7 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
 extern "C" void ig_destroy(ig_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
-    void* ptrs[] = {h->live, h->part_c, h->table, h->table_len, h->rowidx, h->init_live, h->sub, h->coord, h->clen, h->row_ptr, h->cv, h->sym_diag,
+    void* ptrs[] = {h->live, h->part_out, h->part_c, h->table, h->table_len, h->rowidx, h->init_live, h->sub, h->coord, h->clen, h->row_ptr, h->cv, h->sym_diag,
                     h->init_prev, h->init_next, h->orientable, h->sc, h->desc, h->exz, h->exz_test, h->chunk_cnt,
                     h->rows, h->row_cnt, h->part_nz, h->part_z, h->part_i, h->part_full, h->part_zc, h->part_nc,
                     h->d_nuniq, h->d_nsub, h->d_perm, h->d_hist};
@@ -1090,6 +1190,7 @@ extern "C" void ig_destroy(ig_handle* h) {
     if (h->h_sc) cudaFreeHost(h->h_sc);
     if (h->h_small) cudaFreeHost(h->h_small);
     for (int i = 0; i < 6; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < 2; i++) if (h->graph[i]) cudaGraphExecDestroy(h->graph[i]);
     if (h->side) cudaStreamDestroy(h->side);
     if (h->ev_coords) cudaEventDestroy(h->ev_coords);
     if (h->ev_lnz) cudaEventDestroy(h->ev_lnz);
@@ -1117,6 +1218,7 @@ extern "C" int ig_set_params(ig_handle* h, const float p8[8]) {
     if (launch_ok(h, "set_params")) return -2;
     CK(cudaStreamSynchronize(h->stream));
     h->params_set = true;
+    h->incr_valid = false;  // lnz_full / z_cur depend on the parameters
     return 0;
 }
 
@@ -1160,6 +1262,7 @@ extern "C" int ig_set_state(ig_handle* h, const int32_t* in13) {
     for (int i = 0; i < h->nf; i++) maxlab = std::max(maxlab, in13[(size_t)2 * h->nf + i]);
     CK(cudaMemcpy(&h->sc->max_label, &maxlab, sizeof(int), cudaMemcpyHostToDevice));
     h->coords_fresh = false;
+    h->incr_valid = false;
     return 0;
 }
 extern "C" int ig_get_valid_insert(ig_handle* h, int32_t out12[12]) {
@@ -1181,6 +1284,7 @@ extern "C" int ig_bomb(ig_handle* h, const int32_t* perm) {
     CK(cudaMemcpyAsync(&h->sc->max_label, &maxlab, sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->coords_fresh = false;
+    h->incr_valid = false;
     return 0;
 }
 
@@ -1245,11 +1349,13 @@ static int apply_and_post(ig_handle* h, int forced_cand, int forced_op) {
     return launch_ok(h, "apply");
 }
 
-static int fetch_result(ig_handle* h, int n, const int32_t* cands, ig_step_result* out, bool applied) {
-    CK(cudaMemcpyAsync(h->h_sc, h->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_small + 16, h->d_nuniq, IG_MAX_CANDS * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_small + 32, h->d_nsub, IG_MAX_CANDS * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+static int fetch_result(ig_handle* h, int n, const int32_t* cands, ig_step_result* out, bool applied, bool copy = true) {
+    if (copy) {
+        CK(cudaMemcpyAsync(h->h_sc, h->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_small + 16, h->d_nuniq, IG_MAX_CANDS * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_small + 32, h->d_nsub, IG_MAX_CANDS * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
     const DevScalars& s = *h->h_sc;
     memset(out, 0, sizeof *out);
     for (int i = 0; i < n * IG_N_OPS; i++) out->scores[i] = s.scores[i];
@@ -1266,29 +1372,129 @@ static int fetch_result(ig_handle* h, int n, const int32_t* cands, ig_step_resul
     return 0;
 }
 
+// Everything one step enqueues (no host synchronisation): used directly and under graph capture.
+//   full = 1: fill_dist_single + eval_likelihood over every contact (CL:1407-1409), on the side stream,
+//             overlapped with the candidate setup on the main stream;
+//   full = 0: incremental refresh from the previous step's mutation table (same values up to f64
+//             summation order), O(rows of the last move).
+static int enqueue_step(ig_handle* h, int full, int n_grid_cands) {
+    const float mbar = h->cfg.mean_sub_len_kb;
+    const int n = n_grid_cands;
+    cudaMemcpyAsync(&h->sc->n_cands, h->h_small, (2 + IG_MAX_CANDS) * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    cudaEventRecord(h->ev_fork, h->stream);
+    cudaStreamWaitEvent(h->side, h->ev_fork, 0);
+    if (full) {
+        k_coords<<<h->n_part_zc, IG_THREADS, 0, h->side>>>(h->live, h->sub, h->coord, h->clen, h->ns, h->sc, mbar, 0, h->part_zc,
+                                                          h->part_nc, 1);
+        k_reduce<<<1, 256, 0, h->side>>>(h->part_zc, h->n_part_zc, &h->sc->z_cur, h->part_nc, &h->sc->nintra_cur);
+        cudaEventRecord(h->ev_coords, h->side);
+        if (h->profile && !h->capturing) cudaEventRecord(h->ev[2], h->side);
+        k_full_lnz<<<h->n_part_full, IG_THREADS, 0, h->side>>>(h->row_ptr, h->cv, h->coord, h->clen, h->ns, h->sc, mbar, 0, h->exz,
+                                                              h->part_full);
+        if (h->profile && !h->capturing) cudaEventRecord(h->ev[3], h->side);
+        k_reduce<<<1, 256, 0, h->side>>>(h->part_full, h->n_part_full, &h->sc->lnz_full, nullptr, nullptr);
+        cudaEventRecord(h->ev_lnz, h->side);
+    } else {
+        k_commit_coords<<<std::min(h->n_part_zc, (h->ns + 255) / 256), 256, 0, h->side>>>(h->coord, h->clen, h->sc, h->rows, h->ns,
+                                                                                         h->table, h->table_len);
+        cudaEventRecord(h->ev_coords, h->side);
+        cudaEventRecord(h->ev_lnz, h->side);
+    }
+    const FragRec* live = h->live;
+    k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, 1);
+    k_find_cuts<<<dim3((h->nf + 255) / 256, n), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc);
+    cudaStreamWaitEvent(h->stream, h->ev_coords, 0);
+    k_rows_count<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks);
+    k_rows_write<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks, h->rows,
+                                                                       h->rowidx, h->ns);
+    k_precompute<<<dim3(h->grid_pre, n), IG_THREADS, 0, h->stream>>>(h->coord, h->clen, live, h->sub, h->sc, h->desc, h->rows, h->ns,
+                                                                    h->table, h->table_len, mbar, h->part_z, h->part_i);
+    if (h->profile && !h->capturing) cudaEventRecord(h->ev[4], h->stream);
+    k_score<<<dim3(h->grid_score, n), IG_THREADS, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
+                                                                 h->ns, h->row_cnt, h->table, h->table_len, mbar, h->exz, h->part_nz,
+                                                                 h->part_c);
+    if (h->profile && !h->capturing) cudaEventRecord(h->ev[5], h->stream);
+    cudaStreamWaitEvent(h->stream, h->ev_lnz, 0);
+    k_finalize<<<n, 256, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->sc, h->desc, h->rows, h->rowidx, h->ns, h->row_cnt, h->table,
+                                         h->table_len, mbar, h->exz, h->part_nz, h->part_c, h->grid_score, h->part_z, h->part_i,
+                                         h->grid_pre, h->cfg.n_pix, h->cfg.compat_last_block, h->d_nuniq, h->d_nsub);
+    k_select_step<<<1, 128, 0, h->stream>>>(h->sc, h->desc);
+    k_lnz_outside<<<h->n_part_full, IG_THREADS, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->rows, h->rowidx, h->ns,
+                                                               h->table, h->table_len, mbar, h->exz, h->part_out);
+    k_apply<<<(h->nf + 255) / 256, 256, 0, h->stream>>>(h->live, h->nf, h->sc, h->desc, -1, -1);
+    k_post<<<(h->nf + 255) / 256, 256, 0, h->stream>>>(h->live, h->nf, h->init_prev, h->init_next, h->orientable, h->sc);
+    cudaMemcpyAsync(h->h_sc, h->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(h->h_small + 16, h->d_nuniq, IG_MAX_CANDS * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(h->h_small + 32, h->d_nsub, IG_MAX_CANDS * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    return launch_ok(h, "enqueue_step");
+}
+#define IG_LAUNCHES_FULL 15
+#define IG_LAUNCHES_INCR 12
+
+static int get_graph(ig_handle* h, int full, cudaGraphExec_t* out) {
+    cudaGraphExec_t& ge = h->graph[full];
+    if (!ge && !h->graph_failed) {
+        cudaGraph_t g = nullptr;
+        h->capturing = true;
+        cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            enqueue_step(h, full, IG_MAX_CANDS);
+            e = cudaStreamEndCapture(h->stream, &g);
+        }
+        h->capturing = false;
+        if (e == cudaSuccess && g) e = cudaGraphInstantiate(&ge, g, 0);
+        if (g) cudaGraphDestroy(g);
+        if (e != cudaSuccess || !ge) { ge = nullptr; h->graph_failed = true; cudaGetLastError(); }
+    }
+    *out = ge;
+    return 0;
+}
+
 extern "C" int ig_step(ig_handle* h, int32_t id_frag, const int32_t* cands, int32_t n_cands, ig_step_result* out) {
     if (use(h)) return -1;
     if (!h->params_set) { h->err = "ig_step: parameters not set (ig_set_params)"; return -1; }
     if (!out) { h->err = "ig_step: null result"; return -1; }
+    if (n_cands <= 0 || n_cands > IG_MAX_CANDS) { h->err = "n_cands out of range"; return -1; }
+    if (id_frag < 0 || id_frag >= h->nf) { h->err = "id_frag out of range"; return -1; }
+    for (int i = 0; i < n_cands; i++) if (cands[i] < 0 || cands[i] >= h->nf) { h->err = "candidate out of range"; return -1; }
+    int* hs = h->h_small;
+    hs[0] = n_cands; hs[1] = id_frag;
+    for (int i = 0; i < IG_MAX_CANDS; i++) hs[2 + i] = i < n_cands ? cands[i] : 0;
+    const int full = (!h->incr_valid || (h->refresh_every > 0 && h->steps_since_full >= h->refresh_every)) ? 1 : 0;
+    cudaGraphExec_t ge = nullptr;
+    if (h->use_graph && !h->profile) get_graph(h, full, &ge);
     cudaEventRecord(h->ev[0], h->stream);
-    if (refresh_current(h, h->side, true)) return -2;
-    if (int rc = score_candidates(h, id_frag, cands, n_cands, 1, true)) return rc;
-    k_select_step<<<1, 128, 0, h->stream>>>(h->sc, h->desc);
-    k_apply<<<(h->nf + 255) / 256, 256, 0, h->stream>>>(h->live, h->nf, h->sc, h->desc, -1, -1);
-    k_post<<<(h->nf + 255) / 256, 256, 0, h->stream>>>(h->live, h->nf, h->init_prev, h->init_next, h->orientable, h->sc);
-    h->n_launches += 3;
-    h->coords_fresh = false;
-    if (launch_ok(h, "step")) return -2;
+    if (ge) {
+        CK(cudaGraphLaunch(ge, h->stream));
+    } else {
+        if (enqueue_step(h, full, n_cands)) return -2;
+    }
     cudaEventRecord(h->ev[1], h->stream);
-    int rc = fetch_result(h, n_cands, cands, out, true);
+    CK(cudaStreamSynchronize(h->stream));
+    h->n_launches += full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR;
+    h->steps_since_full = full ? 1 : h->steps_since_full + 1;
+    h->n_full += full;
+    h->incr_valid = true;
+    h->coords_fresh = false; h->coords_ever = true;
+    int rc = fetch_result(h, n_cands, cands, out, true, false);
     if (rc) return rc;
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->ms_step += ms;
     if (h->profile) {
-        if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) h->ms_full += ms;
+        if (full && cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) h->ms_full += ms;
         if (cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]) == cudaSuccess) h->ms_score += ms;
     }
     h->n_steps++;
+    return 0;
+}
+
+// measurement / parity knobs: refresh_every = N -> recompute the coordinates and the full likelihood
+// over every contact at least every N steps (1 = every step, exactly the reference's schedule;
+// 0 = only when the state was changed from outside); use_graph = replay the step as one CUDA graph.
+extern "C" int ig_set_options(ig_handle* h, int32_t refresh_every, int32_t use_graph) {
+    if (!h) return -1;
+    h->refresh_every = refresh_every;
+    h->use_graph = use_graph ? true : false;
     return 0;
 }
 
@@ -1296,6 +1502,7 @@ extern "C" int ig_eval_scores(ig_handle* h, int32_t id_frag, int32_t id_cand, in
                               int32_t* n_uniq, int32_t* n_sub) {
     if (use(h)) return -1;
     if (!h->params_set) { h->err = "ig_eval_scores: parameters not set"; return -1; }
+    h->incr_valid = false;
     if (refresh_current(h, h->stream, false)) return -2;
     if (int rc = score_candidates(h, id_frag, &id_cand, 1, flip_eject, false)) return rc;
     ig_step_result r;
@@ -1309,6 +1516,7 @@ extern "C" int ig_eval_scores(ig_handle* h, int32_t id_frag, int32_t id_cand, in
 extern "C" int ig_apply(ig_handle* h, int32_t id_frag, int32_t id_cand, int32_t op, ig_step_result* out) {
     if (use(h)) return -1;
     if (op < 0 || op >= IG_N_OPS) { h->err = "ig_apply: bad op"; return -1; }
+    h->incr_valid = false;
     if (id_frag < 0 || id_frag >= h->nf || id_cand < 0 || id_cand >= h->nf) { h->err = "ig_apply: fragment out of range"; return -1; }
     int* hs = h->h_small;
     hs[0] = 1; hs[1] = id_frag; hs[2] = id_cand;
@@ -1394,10 +1602,11 @@ extern "C" int ig_get_stats(ig_handle* h, double out10[10], int32_t reset) {
     CK(cudaMemcpy(h->h_sc, h->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost));
     out10[0] = h->ms_step; out10[1] = h->ms_score; out10[2] = h->ms_full;
     out10[3] = (double)h->n_launches; out10[4] = (double)h->n_steps;
+    h->last_n_full = h->n_full;
     out10[5] = (double)h->h_sc->st_contacts; out10[6] = (double)h->h_sc->st_rows; out10[7] = (double)h->h_sc->st_frags;
     out10[8] = (double)h->h_sc->st_selected; out10[9] = (double)h->h_sc->st_proposals;
     if (reset) {
-        h->ms_step = h->ms_score = h->ms_full = 0.0; h->n_launches = 0; h->n_steps = 0;
+        h->ms_step = h->ms_score = h->ms_full = 0.0; h->n_launches = 0; h->n_steps = 0; h->n_full = 0;
         CK(cudaMemset(&h->sc->st_contacts, 0, 5 * sizeof(unsigned long long)));
     }
     return 0;
@@ -1405,5 +1614,11 @@ extern "C" int ig_get_stats(ig_handle* h, double out10[10], int32_t reset) {
 extern "C" int ig_set_profiling(ig_handle* h, int32_t on) {
     if (!h) return -1;
     h->profile = on ? 1 : 0;
+    return 0;
+}
+
+extern "C" int ig_get_full_refresh_count(ig_handle* h, int64_t* out) {
+    if (!h) return -1;
+    *out = h->last_n_full;
     return 0;
 }

@@ -209,12 +209,22 @@ class sampler:
     def set_profiling(self, on):
         L.check(self._h, L.lib().ig_set_profiling(self._h, int(bool(on))), "ig_set_profiling")
 
+    def set_options(self, refresh_every=4096, use_graph=True):
+        """refresh_every=1 reproduces the reference's schedule (full likelihood over every contact each
+        step); larger values maintain it incrementally between full refreshes (same values up to f64
+        summation order)."""
+        L.check(self._h, L.lib().ig_set_options(self._h, int(refresh_every), int(bool(use_graph))), "ig_set_options")
+
     def get_stats(self, reset=False):
         out = np.zeros(10, dtype=np.float64)
         L.check(self._h, L.lib().ig_get_stats(self._h, _ptr(out), int(bool(reset))), "ig_get_stats")
         keys = ("ms_step", "ms_score", "ms_full", "launches", "steps", "contacts_read", "rows", "frags",
                 "contacts_selected", "proposals")
-        return dict(zip(keys, out.tolist()))
+        d = dict(zip(keys, out.tolist()))
+        nf = C.c_int64(0)
+        L.lib().ig_get_full_refresh_count(self._h, C.byref(nf))
+        d["full_refreshes"] = int(nf.value)
+        return d
 
     def free_gpu(self):
         if self._h is not None:

@@ -295,8 +295,8 @@ def make_level(spec: SynthSpec) -> LevelData:
 WORKLOADS = {
     "micro": SynthSpec(n_frags=40, n_contigs=5, n_chrom=2, max_offset=60, lambda1=20.0, seed=1),
     "toy": SynthSpec(n_frags=150, n_contigs=10, n_chrom=3, max_offset=200, lambda1=25.0, seed=42),
-    "T": SynthSpec(n_frags=900, n_contigs=146, n_chrom=16, max_offset=600, lambda1=60.0, trans_per_row=8.0, seed=42),
-    "Y3": SynthSpec(n_frags=2700, n_contigs=146, n_chrom=16, max_offset=900, lambda1=40.0, trans_per_row=8.0, seed=42),
+    "T": SynthSpec(n_frags=900, n_contigs=146, n_chrom=16, max_offset=800, lambda1=300.0, trans_per_row=40.0, seed=42),
+    "Y3": SynthSpec(n_frags=2700, n_contigs=146, n_chrom=16, max_offset=1500, lambda1=100.0, trans_per_row=40.0, seed=42),
     "G": SynthSpec(n_frags=100000, n_contigs=2000, n_chrom=20, max_offset=2500, lambda1=420.0,
                    trans_per_row=150.0, seed=7),
 }

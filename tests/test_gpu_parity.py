@@ -214,3 +214,38 @@ def test_last_block_quirk_switch(built):
             assert s1[m] == s0[m]
         else:
             assert s1[m] >= s0[m]  # the quirk drops (negative) terms
+
+
+def test_incremental_likelihood_equals_full_recompute(built):
+    """Default mode maintains coordinates / lnz_full / zero terms incrementally between full refreshes;
+    refresh_every=1 recomputes them over every contact each step like the reference (CL:1407-1409).
+    Both must give the same trajectory and the same likelihoods (f64 summation-order noise only);
+    a divergence is only allowed at an exact tie."""
+    level = make_level(WORKLOADS["T"])
+    runs = []
+    for refresh, graph in ((1, False), (0, True)):
+        s = make_sampler(level)
+        s.set_options(refresh_every=refresh, use_graph=graph)
+        s.set_param_simu(P8_RIPPE)
+        np.random.seed(11)
+        s.bomb_the_genome()
+        frs = np.arange(level.n_frags)
+        np.random.shuffle(frs)
+        out = []
+        for f in list(frs) + list(frs[:300]):
+            r = s.step_sampler(int(f), 5, np.float32(0.01))
+            out.append((float(r[0]), int(r[2]), int(r[3]), int(r[5]), np.sort(s.all_scores[s.all_scores != 0])[-2:].copy()))
+        runs.append(out)
+        st = s.get_stats()
+        if refresh == 0:
+            assert st["full_refreshes"] <= 1
+        s.free_gpu()
+    n_same = 0
+    for a, b in zip(*runs):
+        if a[1:4] != b[1:4]:
+            top = a[4]
+            assert abs(top[-1] - top[-2]) <= 1e-9 * abs(top[-1]), ("diverged without a tie", n_same, a, b)
+            break
+        assert abs(a[0] - b[0]) <= 1e-9 * abs(a[0]), (n_same, a[0], b[0])
+        n_same += 1
+    assert n_same >= 200, n_same
