@@ -199,6 +199,7 @@ def run_ours(args):
             flush.fill_(i & 0xFF)
         s.step_sampler(f, 5, dt)
     stp = s.get_stats(reset=True)
+    ktimes = s.get_kernel_times(reset=True)
     s.set_profiling(False)
 
     # ---------------- pass 2: end to end through the facade (host RNG + ctypes + H2D/D2H), wall clock
@@ -272,6 +273,7 @@ def run_ours(args):
                                      "achieved_GBs": ach[k]} for k in kern},
                      "terms_per_launch": stp["contacts_selected"] * (stp["proposals"] / max(stp["steps"], 1) / 5.0) / max(stp["steps"], 1),
                      "note": "instruction-bound, not HBM-bound: <=24 x (powf + f64 log10) per 8-byte contact (DESIGN.md)"},
+        "kernel_us_per_step": {k: v / max(n_launch_score, 1) * 1e3 for k, v in ktimes.items()},
         "clocks": clk.summary(),
         "setup_s": {"generate": t_gen, "burn_in": t_burn},
     }

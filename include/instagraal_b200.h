@@ -112,6 +112,8 @@ int ig_set_sym_diag(ig_handle* h, const int32_t* diag);
  * and the scoring kernel's algorithmic traffic counters; see bench.py */
 int ig_set_profiling(ig_handle* h, int32_t on);
 int ig_get_stats(ig_handle* h, double out10[10], int32_t reset);
+/* profiling mode only: accumulated ms between consecutive main-stream launches of a step */
+int ig_get_kernel_times(ig_handle* h, double out11[11], int32_t reset);
 /* refresh_every = N: recompute coordinates + full likelihood over every contact at least every N steps
  * (1 = every step, the reference's own schedule CL:1407-1409; 0 = only after the state was changed from
  * outside); in between they are maintained incrementally (identical up to f64 summation order).

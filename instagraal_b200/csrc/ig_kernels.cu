@@ -282,21 +282,25 @@ __global__ void k_set_params(DevScalars* sc, Params p, int test) {
 //     of candidate k reads the list_valid_insert left by get_bounds of candidate k-1 (quirk Q3).
 __global__ void k_cand_setup(const FragRec* __restrict__ live, DevScalars* sc, IgDescriptor* desc, int n_bounds,
                              int first_flip_eject) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    // one lane per candidate: pivots and get_bounds in parallel; only the uniq lists chain through the
+    // previous candidate's validity list (quirk Q3), which goes through shared memory
+    __shared__ int sv[IG_MAX_CANDS + 1][12];
+    const int k = threadIdx.x;
+    const int n = sc->n_cands;
     const int a = sc->a;
     const Frag A = live[a].f;
-    int prev_valid[12];
-    for (int i = 0; i < 12; i++) prev_valid[i] = sc->valid[i];
-    for (int k = 0; k < sc->n_cands; k++) {
+    if (k < 12) sv[0][k] = sc->valid[k];
+    Frag B = A;
+    int b = a;
+    if (k < n) {
+        b = sc->cands[k];
+        B = live[b].f;
         IgDescriptor& d = desc[k];
-        const int b = sc->cands[k];
-        const Frag B = live[b].f;
         d.a = a; d.b = b; d.max_id = sc->max_label;
         d.A = A; d.B = B;
-        d.n_uniq = ig_uniq_mutations(A, B, prev_valid, (k == 0) ? first_flip_eject : 0, d.uniq);
         ig_get_bounds_positions(A, B, d.valid, d.cut_pos_up, d.cut_pos_down);
+        for (int i = 0; i < 12; i++) sv[k + 1][i] = d.valid[i];
         for (int i = 0; i < IG_N_CUT; i++) { d.f_up[i] = -1; d.f_down[i] = -1; }
-        for (int i = 0; i < 12; i++) prev_valid[i] = d.valid[i];
         // slice windows, KA:526-551 (sub-fragment units of the live scaffold)
         CandInfo& c = sc->ci[k];
         int pfa = A.sub_pos * (A.ori == 1) + (A.sub_pos - A.sub_len) * (A.ori == -1); if (pfa < 0) pfa = 0;
@@ -307,7 +311,12 @@ __global__ void k_cand_setup(const FragRec* __restrict__ live, DevScalars* sc, I
         c.n_rows = 0; c.n_sub = 0; c.row_hi = -1;
         sc->ticket_cuts[k] = 0; sc->ticket_rows[k] = 0;
     }
-    for (int i = 0; i < 12; i++) sc->valid[i] = prev_valid[i];  // state after the last candidate (CL:1854-1870)
+    __syncthreads();
+    if (k < n) {
+        IgDescriptor& d = desc[k];
+        d.n_uniq = ig_uniq_mutations(A, B, sv[k], (k == 0) ? first_flip_eject : 0, d.uniq);
+    }
+    if (k < 12) sc->valid[k] = sv[n][k];  // state after the last candidate's get_bounds (CL:1854-1870)
 }
 // K3: cut fragments of get_bounds (KA:2255-2269), all candidates at once; the LAST block to finish a
 //     candidate then evaluates every pivot of its descriptor (one thread).
@@ -332,9 +341,9 @@ k_find_cuts(const FragRec* __restrict__ live, int nf, DevScalars* sc, IgDescript
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(&sc->ticket_cuts[k], 1u) == gridDim.x - 1);
     __syncthreads();
-    if (is_last && threadIdx.x == 0) {
+    if (is_last && threadIdx.x < 32) {
         __threadfence();
-        ig_build_descriptor(desc[k], [&](int j) { return live[j].f; });
+        ig_build_descriptor_part(desc[k], [&](int j) { return live[j].f; }, threadIdx.x);
     }
 }
 
@@ -633,7 +642,8 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
     __shared__ double t_val[IG_N_OPS][64];
     __shared__ int2 t_cv[64];
     __shared__ int t_ri[64];
-    __shared__ int t_cnt;
+    __shared__ int t_cnt, t_need, t_ri_cur;
+    __shared__ int t_wsum[8];
     const IgDescriptor& d = desc_g[k];
     const Params p = sc->p;
     const double l10v = sc->log10_vinter;
@@ -672,21 +682,51 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
     const int* tlen = table_len + (size_t)k * IG_N_OPS * ns;
     // ---- last-block quirk: uniq slots u >= t lose the final (n_sub % 64) contacts of the row-sorted slice
     if (compat_last_block && t > 0 && t < n_uniq) {
-        if (threadIdx.x == 0) {  // serial, hence deterministic, collection of the last t selected contacts
-            int need = t, n = 0;
-            for (int ri = ci_k.n_rows - 1; ri >= 0 && need > 0; ri--) {
-                if (row_cnt[(size_t)k * ns + ri] == 0) continue;
-                const int r = rows[(size_t)k * ns + ri];
-                const CoordRec ci = coord[r];
-                for (long long q = row_ptr[r + 1] - 1; q >= row_ptr[r] && need > 0; q--) {
-                    const int2 c = cv[q];
-                    const CoordRec cj = coord[c.x];
-                    if (!(cj.id_c == ci_k.id_a || cj.id_c == ci_k.id_b)) continue;
-                    if (!contact_selected(ci, cj, c.y, ci_k)) continue;
-                    t_cv[n] = c; t_ri[n] = ri; n++; need--;
-                }
+        // ordered (hence deterministic) collection of the last t selected contacts of the row-sorted slice:
+        // rows from the last one backwards, the whole block scans a row's contacts with a block-wide
+        // exclusive scan of the selection flags, keeping the row's last `take` selected contacts in order
+        if (threadIdx.x == 0) { t_cnt = 0; t_need = t; t_ri_cur = ci_k.n_rows - 1; }
+        __syncthreads();
+        while (true) {
+            // advance to the next row (backwards) that has selected contacts
+            if (threadIdx.x == 0) {
+                int ri = t_ri_cur;
+                while (ri >= 0 && row_cnt[(size_t)k * ns + ri] == 0) ri--;
+                t_ri_cur = ri;
             }
-            t_cnt = n;
+            __syncthreads();
+            const int ri = t_ri_cur, need = t_need;
+            if (ri < 0 || need <= 0) break;
+            const int rc = row_cnt[(size_t)k * ns + ri];
+            const int take = min(rc, need);
+            const int skip = rc - take;  // selected contacts of this row that stay outside the tail
+            const int r = rows[(size_t)k * ns + ri];
+            const CoordRec ci = coord[r];
+            const long long b0 = row_ptr[r], e0 = row_ptr[r + 1];
+            const int base_slot = t_cnt;
+            int running = 0;  // selected contacts of this row seen so far (uniform across the block)
+            for (long long q0 = b0; q0 < e0; q0 += blockDim.x) {
+                const long long q = q0 + threadIdx.x;
+                int2 c = make_int2(0, 0);
+                bool sel = false;
+                if (q < e0) {
+                    c = cv[q];
+                    const CoordRec cj = coord[c.x];
+                    sel = (cj.id_c == ci_k.id_a || cj.id_c == ci_k.id_b) && contact_selected(ci, cj, c.y, ci_k);
+                }
+                // block-wide exclusive scan of sel
+                const unsigned bal = __ballot_sync(0xffffffffu, sel);
+                if (lane == 0) t_wsum[w] = __popc(bal);
+                __syncthreads();
+                int before = 0, total = 0;
+                for (int ww = 0; ww < nwarp; ww++) { const int x = t_wsum[ww]; if (ww < w) before += x; total += x; }
+                const int idx = running + before + __popc(bal & ((1u << lane) - 1));
+                if (sel && idx >= skip) { const int slot = base_slot + (idx - skip); t_cv[slot] = c; t_ri[slot] = ri; }
+                running += total;
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) { t_cnt = base_slot + take; t_need = need - take; t_ri_cur = ri - 1; }
+            __syncthreads();
         }
         __syncthreads();
         const int n_items = t_cnt * (n_uniq - t);
@@ -764,27 +804,32 @@ __global__ void k_select(DevScalars* sc) {
 // step path: selection + the bookkeeping of k_post_scalars in one launch (k_apply reads the label base
 // from the descriptor, not from sc->max_label, so bumping it here cannot race)
 __global__ void k_select_step(DevScalars* sc, const IgDescriptor* __restrict__ desc_g) {
-    __shared__ double sm[IG_MAX_CANDS * IG_N_OPS];
     const int n = sc->n_cands * IG_N_OPS;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = sc->scores[i];
-    __syncthreads();
-    if (threadIdx.x != 0) return;
+    const int lane = threadIdx.x;  // one warp
+    // first index of the maximum among the scored (non-zero) proposals (CL:1435-1446)
     int best = -1;
     double bv = 0.0;
-    for (int i = 0; i < n; i++) {
-        const double v = sm[i];
+    for (int i = lane; i < n; i += 32) {
+        const double v = sc->scores[i];
         if (v == 0.0) continue;
         if (best < 0 || v > bv) { best = i; bv = v; }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int ob = __shfl_down_sync(0xffffffffu, best, o);
+        const double ov = __shfl_down_sync(0xffffffffu, bv, o);
+        if (ob >= 0 && (best < 0 || ov > bv || (ov == bv && ob < best))) { best = ob; bv = ov; }
+    }
+    best = __shfl_sync(0xffffffffu, best, 0);
     if (best < 0) best = 0;
     const int kc = best / IG_N_OPS, op = best % IG_N_OPS;
-    sc->win_cand = kc; sc->win_op = op; sc->likelihood = sm[best];
+    const unsigned hit = __ballot_sync(0xffffffffu, lane < desc_g[kc].n_uniq && desc_g[kc].uniq[lane] == op);
+    if (lane < 12 && op >= 12) sc->valid[lane] = desc_g[kc].valid[lane];
+    if (lane != 0) return;
+    sc->win_cand = kc; sc->win_op = op; sc->likelihood = sc->scores[best];
     sc->n_heads = 0; sc->sum_l_cont = 0; sc->dist_half = 0;
-    if (op >= 12) for (int i = 0; i < 12; i++) sc->valid[i] = desc_g[kc].valid[i];
     sc->max_label += 2;
-    int u_star = 0;
-    for (int u = 0; u < desc_g[kc].n_uniq; u++) if (desc_g[kc].uniq[u] == op) u_star = u;
-    sc->prev_k = kc; sc->prev_u = u_star;
+    sc->prev_k = kc; sc->prev_u = hit ? (__ffs(hit) - 1) : 0;
     sc->prev_windowed = (sc->ci[kc].same && sc->ci[kc].is_circ == 0) ? 1 : 0;
     sc->prev_id_a = sc->ci[kc].id_a; sc->prev_n_rows = sc->ci[kc].n_rows;
     sc->lnz_next = sc->lnz_new[best]; sc->z_next = sc->z_new[best]; sc->nintra_next = sc->nintra_new[best];
@@ -1000,7 +1045,7 @@ struct ig_handle {
     int nf, ns;
     long long nnz;
     cudaStream_t stream, side;
-    cudaEvent_t ev_coords, ev_lnz, ev_fork;
+    cudaEvent_t ev_coords, ev_lnz, ev_fork, ev_sel, ev_out;
     FragRec *live, *init_live;
     SubRec* sub;
     CoordRec* coord;
@@ -1030,6 +1075,7 @@ struct ig_handle {
     cudaGraphExec_t graph[2]; bool graph_failed, capturing, use_graph; long long n_full;
     // measurement (CUDA events on the launching stream)
     cudaEvent_t ev[6];
+    cudaEvent_t evk[16]; double ms_k[16];  // per-kernel event timing of the main stream (profiling mode)
     double ms_step, ms_score, ms_full;
     long long n_launches, n_steps;
     int profile;
@@ -1097,7 +1143,10 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
         CK(cudaEventCreateWithFlags(&h->ev_coords, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_lnz, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_sel, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
         for (int i = 0; i < 6; i++) CK(cudaEventCreate(&h->ev[i]));
+        for (int i = 0; i < 16; i++) { CK(cudaEventCreate(&h->evk[i])); h->ms_k[i] = 0.0; }
         h->ms_step = h->ms_score = h->ms_full = 0.0; h->n_launches = 0; h->n_steps = 0; h->profile = 0;
         const int nf = h->nf, ns = h->ns;
         if (dev_alloc(h, &h->live, nf) || dev_alloc(h, &h->init_live, nf)) return -2;
@@ -1190,11 +1239,14 @@ extern "C" void ig_destroy(ig_handle* h) {
     if (h->h_sc) cudaFreeHost(h->h_sc);
     if (h->h_small) cudaFreeHost(h->h_small);
     for (int i = 0; i < 6; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < 16; i++) if (h->evk[i]) cudaEventDestroy(h->evk[i]);
     for (int i = 0; i < 2; i++) if (h->graph[i]) cudaGraphExecDestroy(h->graph[i]);
     if (h->side) cudaStreamDestroy(h->side);
     if (h->ev_coords) cudaEventDestroy(h->ev_coords);
     if (h->ev_lnz) cudaEventDestroy(h->ev_lnz);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_sel) cudaEventDestroy(h->ev_sel);
+    if (h->ev_out) cudaEventDestroy(h->ev_out);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -1401,28 +1453,46 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands) {
         cudaEventRecord(h->ev_lnz, h->side);
     }
     const FragRec* live = h->live;
+#define IG_MARK(i) do { if (h->profile && !h->capturing) cudaEventRecord(h->evk[i], h->stream); } while (0)
+    IG_MARK(0);
     k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, 1);
+    IG_MARK(1);
     k_find_cuts<<<dim3((h->nf + 255) / 256, n), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc);
     cudaStreamWaitEvent(h->stream, h->ev_coords, 0);
+    IG_MARK(2);
     k_rows_count<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks);
+    IG_MARK(3);
     k_rows_write<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks, h->rows,
                                                                        h->rowidx, h->ns);
+    IG_MARK(4);
     k_precompute<<<dim3(h->grid_pre, n), IG_THREADS, 0, h->stream>>>(h->coord, h->clen, live, h->sub, h->sc, h->desc, h->rows, h->ns,
                                                                     h->table, h->table_len, mbar, h->part_z, h->part_i);
     if (h->profile && !h->capturing) cudaEventRecord(h->ev[4], h->stream);
+    IG_MARK(5);
     k_score<<<dim3(h->grid_score, n), IG_THREADS, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
                                                                  h->ns, h->row_cnt, h->table, h->table_len, mbar, h->exz, h->part_nz,
                                                                  h->part_c);
     if (h->profile && !h->capturing) cudaEventRecord(h->ev[5], h->stream);
     cudaStreamWaitEvent(h->stream, h->ev_lnz, 0);
+    IG_MARK(6);
     k_finalize<<<n, 256, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->sc, h->desc, h->rows, h->rowidx, h->ns, h->row_cnt, h->table,
                                          h->table_len, mbar, h->exz, h->part_nz, h->part_c, h->grid_score, h->part_z, h->part_i,
                                          h->grid_pre, h->cfg.n_pix, h->cfg.compat_last_block, h->d_nuniq, h->d_nsub);
-    k_select_step<<<1, 128, 0, h->stream>>>(h->sc, h->desc);
-    k_lnz_outside<<<h->n_part_full, IG_THREADS, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->rows, h->rowidx, h->ns,
-                                                               h->table, h->table_len, mbar, h->exz, h->part_out);
+    IG_MARK(7);
+    k_select_step<<<1, 32, 0, h->stream>>>(h->sc, h->desc);
+    IG_MARK(8);
+    // independent of apply/post: runs beside them on the side stream, joined before the result copy
+    cudaEventRecord(h->ev_sel, h->stream);
+    cudaStreamWaitEvent(h->side, h->ev_sel, 0);
+    k_lnz_outside<<<h->grid_score, IG_THREADS, 0, h->side>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->rows, h->rowidx, h->ns,
+                                                             h->table, h->table_len, mbar, h->exz, h->part_out);
+    cudaEventRecord(h->ev_out, h->side);
+    IG_MARK(9);
     k_apply<<<(h->nf + 255) / 256, 256, 0, h->stream>>>(h->live, h->nf, h->sc, h->desc, -1, -1);
+    IG_MARK(10);
     k_post<<<(h->nf + 255) / 256, 256, 0, h->stream>>>(h->live, h->nf, h->init_prev, h->init_next, h->orientable, h->sc);
+    IG_MARK(11);
+    cudaStreamWaitEvent(h->stream, h->ev_out, 0);
     cudaMemcpyAsync(h->h_sc, h->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, h->stream);
     cudaMemcpyAsync(h->h_small + 16, h->d_nuniq, IG_MAX_CANDS * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
     cudaMemcpyAsync(h->h_small + 32, h->d_nsub, IG_MAX_CANDS * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
@@ -1483,6 +1553,8 @@ extern "C" int ig_step(ig_handle* h, int32_t id_frag, const int32_t* cands, int3
     if (h->profile) {
         if (full && cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) h->ms_full += ms;
         if (cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]) == cudaSuccess) h->ms_score += ms;
+        for (int i = 0; i < 11; i++)
+            if (cudaEventElapsedTime(&ms, h->evk[i], h->evk[i + 1]) == cudaSuccess) h->ms_k[i] += ms;
     }
     h->n_steps++;
     return 0;
@@ -1620,5 +1692,14 @@ extern "C" int ig_set_profiling(ig_handle* h, int32_t on) {
 extern "C" int ig_get_full_refresh_count(ig_handle* h, int64_t* out) {
     if (!h) return -1;
     *out = h->last_n_full;
+    return 0;
+}
+
+// profiling mode only: accumulated ms between consecutive main-stream launches of a step, in order:
+// cand_setup, find_cuts(+wait coords), rows_count, rows_write, precompute, score(+wait lnz), finalize,
+// select, lnz_outside, apply, post
+extern "C" int ig_get_kernel_times(ig_handle* h, double out11[11], int32_t reset) {
+    if (!h) return -1;
+    for (int i = 0; i < 11; i++) { out11[i] = h->ms_k[i]; if (reset) h->ms_k[i] = 0.0; }
     return 0;
 }

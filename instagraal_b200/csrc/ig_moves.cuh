@@ -473,6 +473,36 @@ IG_HD void ig_build_descriptor(IgDescriptor& d, const Loader& load) {
         }
 }
 
+// Same as ig_build_descriptor, split over the lanes of one warp (lane 0..11: block ops; 12: pop
+// pivots; 13, 14: the two translocation families).  Lanes >= 15 do nothing.
+template <class Loader>
+IG_HD void ig_build_descriptor_part(IgDescriptor& d, const Loader& load, int lane) {
+    const int a = d.a, b = d.b, max_id = d.max_id;
+    if (lane < 12) {
+        const int k = lane, i = k >> 1, up = (k & 1) == 0 ? 1 : 0;
+        IgBlockOp& o = d.blk[k];
+        o.cut = up ? d.f_up[i] : d.f_down[i];
+        o.valid = d.valid[k];
+        o.C = o.cut >= 0 ? load(o.cut) : d.A;
+        o.EA = ig_extract_block(d.A, a, d.A, o.C, o.cut, up, max_id);
+        o.EB = ig_extract_block(d.B, b, d.A, o.C, o.cut, up, max_id);
+    } else if (lane == 12) {
+        d.PA = ig_pop_out(d.A, a, d.A, a, max_id);
+        d.PB = ig_pop_out(d.B, b, d.A, a, max_id);
+        d.max_id2 = max_id + (d.A.l_cont >= 2 ? 1 : 0);
+    } else if (lane < 15) {
+        const int ua = lane - 13;
+        const Frag t1a = ig_split(d.A, a, d.A, ua, max_id);
+        const Frag t1b = ig_split(d.B, b, d.A, ua, max_id);
+        const int m1 = max_id + ig_split_new_label(d.A, ua);
+        d.T1A[ua] = t1a; d.T1B[ua] = t1b; d.max_id1[ua] = m1;
+        for (int ub = 0; ub < 2; ub++) {
+            d.T2A[ua][ub] = ig_split(t1a, a, t1b, ub, m1);
+            d.T2B[ua][ub] = ig_split(t1b, b, t1b, ub, m1);
+        }
+    }
+}
+
 // Fields of fragment i (live fields f) under op `op` of the candidate described by d.
 IG_HD Frag ig_eval_op(const IgDescriptor& d, int op, const Frag& f, int i) {
     if (op == 1) { Frag o = f; if (i == d.a) o.ori = -f.ori; return o; }      // KA:612-670

@@ -209,6 +209,14 @@ class sampler:
     def set_profiling(self, on):
         L.check(self._h, L.lib().ig_set_profiling(self._h, int(bool(on))), "ig_set_profiling")
 
+    KERNEL_ORDER = ("k_cand_setup", "k_find_cuts", "k_rows_count", "k_rows_write", "k_precompute", "k_score",
+                    "k_finalize", "k_select_step", "k_lnz_outside", "k_apply", "k_post")
+
+    def get_kernel_times(self, reset=False):
+        out = np.zeros(11, dtype=np.float64)
+        L.check(self._h, L.lib().ig_get_kernel_times(self._h, _ptr(out), int(bool(reset))), "ig_get_kernel_times")
+        return dict(zip(self.KERNEL_ORDER, out.tolist()))
+
     def set_options(self, refresh_every=4096, use_graph=True):
         """refresh_every=1 reproduces the reference's schedule (full likelihood over every contact each
         step); larger values maintain it incrementally between full refreshes (same values up to f64
