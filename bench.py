@@ -279,6 +279,13 @@ def run_ours(args):
     }
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline(level, p8, st_burn, args.cpu_budget_s)
+    if not args.no_ref_gpu and world == 1:
+        try:
+            s.free_gpu()
+            out["ref_gpu_baseline"] = ref_gpu_baseline(level, p8, st_burn, args.ref_gpu_budget_s, local)
+            out["ref_gpu_baseline"]["speedup_e2e_vs_ref_gpu"] = e2e / out["ref_gpu_baseline"]["value"]
+        except Exception as ex:  # the baseline must never break the bench line
+            out["ref_gpu_baseline"] = {"unavailable": repr(ex)[:200]}
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
@@ -310,6 +317,39 @@ def cpu_baseline(level, p8, state13, budget_s):
     return {"value": n_prop / dt, "unit": "proposals/s", "cores": 1, "kind": "port",
             "sample": "%d step_sampler calls (%d proposals) of the same workload from the same burnt-in scaffold, %.1f s"
                       % (n_steps, n_prop, dt)}
+
+
+def ref_gpu_baseline(level, p8, state13, budget_s, device=0):
+    """B-ref (GPU): the reference's own kernels (oracle/_ref/ref_kernels.cubin) driven in the reference's
+    launch order with its per-launch synchronisation, NumPy 'thrust' round trips, 17-array D2H copies
+    and Python dist loop (oracle/ref_replay.py, validated against the golden vectors on the CPU backend)."""
+    cubin = os.path.join(ROOT, "oracle", "_ref", "ref_kernels.cubin")
+    if not os.path.exists(cubin):
+        return {"unavailable": "oracle/_ref/ref_kernels.cubin not built"}
+    from oracle.ref_replay import RefReplaySampler
+    from oracle.sampler_oracle import return_neighbours, setup_distri_frags
+    r = RefReplaySampler(level, p8, backend="gpu", device=device)
+    if state13 is not None:
+        r.set_state(state13)
+    distri = setup_distri_frags(level.sub_sampled_sparse_matrix, level.n_frags)
+    np.random.seed(3)
+    frs = np.arange(level.n_frags)
+    np.random.shuffle(frs)
+    r.step_sampler(int(frs[0]), return_neighbours(distri, level.n_frags, int(frs[0]), 5))  # warm-up (module load, caches)
+    l0 = r.be.n_launch
+    t0 = time.perf_counter()
+    n_prop = n_steps = 0
+    for f in frs[1:]:
+        r.step_sampler(int(f), return_neighbours(distri, level.n_frags, int(f), 5))
+        n_prop += int(sum(r.n_uniq_list))
+        n_steps += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": n_prop / dt, "unit": "proposals/s", "ms_per_step": dt / n_steps * 1e3, "steps": n_steps,
+            "kernel_launches_per_step": (r.be.n_launch - l0) / n_steps,
+            "kind": "reference kernels (cubin built from /root/reference) + restated reference host sequence (route ii)",
+            "sample": "%d step_sampler calls from the same burnt-in scaffold, %.1f s" % (n_steps, dt)}
 
 
 def _ref_worker(a):
@@ -371,6 +411,8 @@ def main():
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true")
+    ap.add_argument("--ref-gpu-budget-s", type=float, default=10.0)
     args = ap.parse_args()
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     if args.impl == "reference":

@@ -36,7 +36,7 @@ def score_tol(s_ref):
     return 1e-5 * np.abs(s_ref - best) + 2e-8 * np.abs(s_ref) + 1e-9
 
 
-def replay(golden, impl, max_steps=None, check_state=True):
+def replay(golden, impl, max_steps=None, check_state=True, check_nuis=True):
     """``impl`` must provide: set_state(int32[13,NF]), set_valid(int32[12]), set_params(f32[8]),
     eval_nuisance(f32[8]) -> float (full likelihood under test params on the stale coordinates),
     step(A, cands:list[int]) -> dict(scores f64[24*n], op, B, o, dist, mean_len, n_contigs),
@@ -94,7 +94,7 @@ def replay(golden, impl, max_steps=None, check_state=True):
             else:
                 res.errors.append((t, "different move chosen", gid, gid_ref, float(gap)))
         # nuisance-parameter likelihood (evaluated on the coordinates of THIS step's start, quirk Q5)
-        if "step_nuis_step" in g and t in nuis_at and gid == gid_ref:
+        if check_nuis and "step_nuis_step" in g and t in nuis_at and gid == gid_ref:
             k = nuis_at[t]
             want = float(g["step_nuis"][k][7])
             got = float(impl.eval_nuisance(g["step_params"][k]))
