@@ -53,7 +53,7 @@ class CpuBackend:
         ctypes.memmove(arr.ctypes.data, ptr, arr.nbytes)
 
     def launch(self, name, grid, block, args):
-        ints = [int(v) & 0xFFFFFFFFFFFFFFFF for k, v in args if k != "f"]
+        ints = [int(v) & 0xFFFFFFFFFFFFFFFF for k, v in args if k not in ("f", "x")]
         fps = [int(np.float32(v).view(np.uint32)) for k, v in args if k == "f"]
         ia = (ctypes.c_uint64 * max(len(ints), 1))(*ints)
         fa = (ctypes.c_uint32 * max(len(fps), 1))(*fps)
@@ -111,6 +111,8 @@ class GpuBackend:
                 vals.append(float(v)); types.append(ctypes.c_float)
             elif k == "q":
                 vals.append(int(v)); types.append(ctypes.c_ulonglong)
+            elif k == "x":  # unused float2 parameter of flip_frag (KA:612-613): the driver checks the count
+                vals.append(0.0); types.append(ctypes.c_double)
             else:
                 vals.append(int(v)); types.append(ctypes.c_int)
         self._ck(self.drv.cuLaunchKernel(f, int(grid), 1, 1, int(block), 1, 1, 0, 0, (tuple(vals), tuple(types)), 0))
@@ -289,7 +291,7 @@ class RefReplaySampler:
         if mode == 0:
             self._L("simple_copy", nf, 1024, [("p", self.cand[0].ptr), ("p", self.pop.ptr), ("i", nf)])
         elif mode == 1:
-            self._L("flip_frag", nf, 1024, [("p", self.cand[1].ptr), ("p", self.live.ptr), ("i", a), ("i", nf)])
+            self._L("flip_frag", nf, 1024, [("p", self.cand[1].ptr), ("p", self.live.ptr), ("i", a), ("i", nf), ("x", 0)])
         else:
             kern = ("pop_in_frag_1", "pop_in_frag_1", "pop_in_frag_2", "pop_in_frag_2", "pop_in_frag_3", "pop_in_frag_3")[mode - 2]
             self._L(kern, nf, 1024, [("p", self.cand[mode].ptr), ("p", self.pop.ptr), ("i", a), ("i", b), ("i", max_id2),
