@@ -142,7 +142,11 @@ def run_ours(args):
     s.set_param_simu(p8)
     burn = args.burn_cycles if args.burn_cycles >= 0 else (2 if level.n_frags <= 5000 else 0)
     t0 = time.time()
-    if burn > 0:
+    if args.start == "true":  # fully assembled regime without burn-in: one contig per true chromosome
+        burn = 0
+        np.random.seed(1000 + rank)
+        s._set_state(level.true_state())
+    elif burn > 0:
         burn_in(s, level, burn, 1000 + rank)
     else:
         np.random.seed(1000 + rank)
@@ -251,7 +255,7 @@ def run_ours(args):
         "dtype": "f32 expected contacts / f64 log-likelihood accumulation / int32 scaffold",
         "data": "synthetic", "impl": "ours",
         "config": {"workload": args.workload, "n_frags": level.n_frags, "n_sub_frags": ns, "nnz": nnz,
-                   "chains": world, "n_neighbours": 5, "burn_in_cycles": burn, "n_contigs_at_start": n_contigs0,
+                   "chains": world, "n_neighbours": 5, "start": args.start, "burn_in_cycles": burn, "n_contigs_at_start": n_contigs0,
                    "l2": ("flushed between steps with a 256 MiB write (untimed); timed = sum of per-step CUDA-event "
                           "intervals" if args.flush_l2 else "not flushed (inputs %s L2)" % (">" if nnz * 8 > 126e6 else "<")),
                    "full_likelihood": ("recomputed over every contact each step (reference schedule, CL:1409)"
@@ -405,6 +409,7 @@ def main():
     ap.add_argument("--workload", default="T")
     ap.add_argument("--burn-cycles", type=int, default=-1)
     ap.add_argument("--bomb", type=int, default=1)
+    ap.add_argument("--start", default="bomb", choices=["bomb", "true"])
     ap.add_argument("--flush-l2", type=int, default=1)
     ap.add_argument("--gather-every", type=int, default=500)
     ap.add_argument("--refresh-every", type=int, default=4096)

@@ -507,79 +507,11 @@ k_precompute(const CoordRec* __restrict__ coord, const int* __restrict__ clen, c
 //      of rows) so small assemblies still fill the 148 SMs.  Mutated coordinates of both endpoints
 //      come from the table written by k_precompute (row side: warp-uniform broadcast loads; column
 //      side: rowidx gather, contiguous across neighbouring contacts).
-template <int GS>
-__device__ __forceinline__ void score_items(
-    const long long* __restrict__ row_ptr, const int2* __restrict__ cv, const CoordRec* __restrict__ coord,
-    const int* __restrict__ clen, const int* __restrict__ my_rows, const int* __restrict__ my_idx, int ns,
-    int* __restrict__ my_row_cnt, const RowMut* __restrict__ tab, const int* __restrict__ tlen, float mbar,
-    const float* __restrict__ exz_tab, const Params& p, double l10v, const CandInfo& ci_k, int n_uniq,
-    double* __restrict__ wred /* [25] this warp's slot sums */, int* __restrict__ wredi /* [2] */) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int wg = blockIdx.x * IG_WARPS_PER_BLOCK + w, nw = gridDim.x * IG_WARPS_PER_BLOCK;
-    constexpr int NG = IG_N_OPS / GS;
-    const int n_items = ci_k.n_rows * NG;
-    for (int it = wg; it < n_items; it += nw) {
-        const int ri = it / NG, g = it - ri * NG;
-        const int u0 = g * GS;
-        if (u0 >= n_uniq && g != 0) continue;
-        const int r = my_rows[ri];
-        const CoordRec ci = coord[r];
-        const long long b = row_ptr[r], e = row_ptr[r + 1];
-        double acc[GS];
-#pragma unroll
-        for (int j = 0; j < GS; j++) acc[j] = 0.0;
-        double acc_cur = 0.0;
-        int row_sel = 0;
-        for (long long q = b + lane; q < e; q += 32) {
-            const int2 c = __ldg(&cv[q]);
-            const CoordRec cj = coord[c.x];
-            if (!(cj.id_c == ci_k.id_a || cj.id_c == ci_k.id_b)) continue;
-            if (!contact_selected(ci, cj, c.y, ci_k)) continue;
-            row_sel++;
-            const double ob = (double)c.y, obc = ob_const(ob);
-            const double t_cur = contact_term(ci, cj, clen[c.x], ob, obc, p, l10v, mbar, exz_tab);
-            acc_cur += t_cur;
-            const int rj = my_idx[c.x];
-            const bool cur_same = ci.id_c == cj.id_c;
-            const float cur_s = fabsf(ci.dist - cj.dist);
-            const int cur_dp = abs(ci.pos - cj.pos);
-#pragma unroll
-            for (int j = 0; j < GS; j++) {
-                const int u = u0 + j;
-                if (u < n_uniq) {
-                    const RowMut a = tab[(size_t)u * ns + ri];
-                    const RowMut bm = tab[(size_t)u * ns + rj];
-                    CoordRec cim, cjm;
-                    cim.dist = a.dist; cim.id_c = a.id_c; cim.pos = a.pos; cim.s_tot = a.s_tot;
-                    cjm.dist = bm.dist; cjm.id_c = bm.id_c; cjm.pos = bm.pos; cjm.s_tot = bm.s_tot;
-                    const bool m_same = cim.id_c == cjm.id_c;
-                    double t;
-                    if (m_same == cur_same && cim.s_tot == ci.s_tot &&
-                        (!m_same || (cim.s_tot == 0 && fabsf(cim.dist - cjm.dist) == cur_s && abs(cim.pos - cjm.pos) == cur_dp))) {
-                        t = t_cur;  // bit-exact shortcut: identical inputs give the identical term
-                    } else {
-                        const int len_j = (m_same && cim.s_tot != 0) ? tlen[(size_t)u * ns + rj] : 0;
-                        t = contact_term(cim, cjm, len_j, ob, obc, p, l10v, mbar, exz_tab);
-                    }
-                    acc[j] += t;
-                }
-            }
-        }
-        // fixed-order accumulation into this warp's slot sums (work items are visited in a fixed order)
-#pragma unroll
-        for (int j = 0; j < GS; j++) {
-            const double v = warp_sum(acc[j]);
-            if (lane == 0 && u0 + j < n_uniq) wred[u0 + j] += v;
-        }
-        if (g == 0) {
-            const double v = warp_sum(acc_cur);
-            row_sel = __reduce_add_sync(0xffffffffu, row_sel);
-            if (lane == 0) { wred[24] += v; my_row_cnt[ri] = row_sel; wredi[0] += row_sel; wredi[1] += (int)(e - b); }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(IG_THREADS, 2)
+// The mutation loop is deliberately NOT unrolled and contact_term is instantiated only twice: an
+// unrolled 24-way body (x4 group sizes) measured 35 warps stalled on instruction fetch per issue
+// (ncu "no_instruction", profiles/r1_ncu_k_score_G_v1.txt) -- the kernel has to fit the I-cache.
+// Per-thread per-slot accumulators therefore live in shared memory ([slot][thread], conflict-free).
+__global__ void __launch_bounds__(IG_THREADS, 3)
 k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, const CoordRec* __restrict__ coord,
         const int* __restrict__ clen, const DevScalars* __restrict__ sc, const IgDescriptor* __restrict__ desc_g,
         const int* __restrict__ rows, const int* __restrict__ rowidx, int ns, int* __restrict__ row_cnt,
@@ -589,6 +521,7 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
 {
     const int k = blockIdx.y;
     if (k >= sc->n_cands) return;
+    extern __shared__ double acc_s[];                 // [IG_N_OPS][IG_THREADS]
     __shared__ double red[IG_WARPS_PER_BLOCK][25];
     __shared__ int redi[IG_WARPS_PER_BLOCK][2];
     const Params p = sc->p;
@@ -604,14 +537,67 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
     int* my_cnt = row_cnt + (size_t)k * ns;
     const RowMut* tab = table + (size_t)k * IG_N_OPS * ns;
     const int* tlen = table_len + (size_t)k * IG_N_OPS * ns;
-    const int nw = gridDim.x * IG_WARPS_PER_BLOCK;
-#define IG_SCORE(GS) score_items<GS>(row_ptr, cv, coord, clen, my_rows, my_idx, ns, my_cnt, tab, tlen, mbar, exz_tab, p, l10v, \
-                                     ci_k, n_uniq, red[w], redi[w])
-    if (ci_k.n_rows >= nw) IG_SCORE(24);
-    else if (ci_k.n_rows * 4 >= nw) IG_SCORE(6);
-    else if (ci_k.n_rows * 8 >= nw) IG_SCORE(3);
-    else IG_SCORE(1);
-#undef IG_SCORE
+    const int wg = blockIdx.x * IG_WARPS_PER_BLOCK + w, nw = gridDim.x * IG_WARPS_PER_BLOCK;
+    // group size: all slots per item when there are more rows than warps, fewer when a candidate has few rows
+    int gs = IG_N_OPS;
+    if (ci_k.n_rows < nw) gs = (ci_k.n_rows * 4 >= nw) ? 6 : ((ci_k.n_rows * 8 >= nw) ? 3 : 1);
+    const int ng = IG_N_OPS / gs;
+    const int n_items = ci_k.n_rows * ng;
+    double* my_acc = acc_s + threadIdx.x;
+    for (int it = wg; it < n_items; it += nw) {
+        const int ri = it / ng, g = it - ri * ng;
+        const int u0 = g * gs;
+        if (u0 >= n_uniq && g != 0) continue;
+        const int u1 = min(u0 + gs, n_uniq);
+        const int r = my_rows[ri];
+        const CoordRec ci = coord[r];
+        const long long b = row_ptr[r], e = row_ptr[r + 1];
+        for (int u = u0; u < u1; u++) my_acc[(u - u0) * IG_THREADS] = 0.0;
+        double acc_cur = 0.0;
+        int row_sel = 0;
+        for (long long q = b + lane; q < e; q += 32) {
+            const int2 c = __ldg(&cv[q]);
+            const CoordRec cj = coord[c.x];
+            if (!(cj.id_c == ci_k.id_a || cj.id_c == ci_k.id_b)) continue;
+            if (!contact_selected(ci, cj, c.y, ci_k)) continue;
+            row_sel++;
+            const double ob = (double)c.y, obc = ob_const(ob);
+            const double t_cur = contact_term(ci, cj, clen[c.x], ob, obc, p, l10v, mbar, exz_tab);
+            acc_cur += t_cur;
+            const int rj = my_idx[c.x];
+            const bool cur_same = ci.id_c == cj.id_c;
+            const float cur_s = fabsf(ci.dist - cj.dist);
+            const int cur_dp = abs(ci.pos - cj.pos);
+            const RowMut* ta = tab + (size_t)u0 * ns + ri;
+            const RowMut* tb = tab + (size_t)u0 * ns + rj;
+#pragma unroll 1
+            for (int u = u0; u < u1; u++, ta += ns, tb += ns) {
+                const RowMut a = *ta;
+                const RowMut bm = *tb;
+                CoordRec cim, cjm;
+                cim.dist = a.dist; cim.id_c = a.id_c; cim.pos = a.pos; cim.s_tot = a.s_tot;
+                cjm.dist = bm.dist; cjm.id_c = bm.id_c; cjm.pos = bm.pos; cjm.s_tot = bm.s_tot;
+                const bool m_same = cim.id_c == cjm.id_c;
+                double t = t_cur;  // bit-exact shortcut: identical inputs give the identical term
+                if (!(m_same == cur_same && cim.s_tot == ci.s_tot &&
+                      (!m_same || (cim.s_tot == 0 && fabsf(cim.dist - cjm.dist) == cur_s && abs(cim.pos - cjm.pos) == cur_dp)))) {
+                    const int len_j = (m_same && cim.s_tot != 0) ? tlen[(size_t)u * ns + rj] : 0;
+                    t = contact_term(cim, cjm, len_j, ob, obc, p, l10v, mbar, exz_tab);
+                }
+                my_acc[(u - u0) * IG_THREADS] += t;
+            }
+        }
+        // fixed-order accumulation into this warp's slot sums (work items are visited in a fixed order)
+        for (int u = u0; u < u1; u++) {
+            const double v = warp_sum(my_acc[(u - u0) * IG_THREADS]);
+            if (lane == 0) red[w][u] += v;
+        }
+        if (g == 0) {
+            const double v = warp_sum(acc_cur);
+            row_sel = __reduce_add_sync(0xffffffffu, row_sel);
+            if (lane == 0) { red[w][24] += v; my_cnt[ri] = row_sel; redi[w][0] += row_sel; redi[w][1] += (int)(e - b); }
+        }
+    }
     __syncthreads();
     if (threadIdx.x < 25) {
         double v = 0.0;
@@ -624,6 +610,7 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
         part_c[PART_IDX(k, 2, threadIdx.x, gridDim.x, blockIdx.x)] = iv;
     }
 }
+#define IG_SCORE_SMEM (IG_N_OPS * IG_THREADS * sizeof(double))
 
 // K9: per-candidate finalisation: fixed-order parallel reduction of the block partials, the
 //     reference's last-block quirk (KA:4362), zero terms (eval_all_likelihood_on_zero_2nd
@@ -988,8 +975,16 @@ k_post(const FragRec* __restrict__ live, int nf, const int* __restrict__ init_pr
             if (n1 == n0 || n1 == p0) half += 2;
         }
     }
-    if (heads) { atomicAdd(&s_heads, 1); atomicAdd((unsigned long long*)&s_len, (unsigned long long)len); }
-    if (half) atomicAdd((unsigned long long*)&s_half, (unsigned long long)half);
+    // warp-level reductions first: one shared atomic per warp instead of one per thread
+    const int w_heads = __reduce_add_sync(0xffffffffu, heads);
+    const int w_half = __reduce_add_sync(0xffffffffu, half);
+    long long w_len = len;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w_len += __shfl_down_sync(0xffffffffu, w_len, o);
+    if ((threadIdx.x & 31) == 0) {
+        if (w_heads) { atomicAdd(&s_heads, w_heads); atomicAdd((unsigned long long*)&s_len, (unsigned long long)w_len); }
+        if (w_half) atomicAdd((unsigned long long*)&s_half, (unsigned long long)w_half);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         if (s_heads) atomicAdd(&sc->n_heads, s_heads);
@@ -1161,8 +1156,9 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, cfg->device));
         const int sms = prop.multiProcessorCount;
-        h->grid_score = sms * 2;  // 2 resident CTAs of 8 warps per SM (launch bounds)
-        h->grid_pre = sms;
+        h->grid_score = sms * 3;  // 3 resident CTAs of 8 warps per SM (launch bounds, 48 KB dynamic smem each)
+        CK(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IG_SCORE_SMEM));
+        h->grid_pre = sms * 4;
         if (dev_alloc(h, &h->part_nz, (size_t)IG_MAX_CANDS * h->grid_score * 25)) return -2;
         if (dev_alloc(h, &h->part_c, (size_t)IG_MAX_CANDS * h->grid_score * 2)) return -2;
         if (dev_alloc(h, &h->part_z, (size_t)IG_MAX_CANDS * h->grid_pre * 25)) return -2;
@@ -1379,7 +1375,7 @@ static int score_candidates(ig_handle* h, int a, const int32_t* cands, int n, in
     k_precompute<<<dim3(h->grid_pre, n), IG_THREADS, 0, h->stream>>>(h->coord, h->clen, live, h->sub, h->sc, h->desc, h->rows, h->ns,
                                                                     h->table, h->table_len, mbar, h->part_z, h->part_i);
     if (h->profile) cudaEventRecord(h->ev[4], h->stream);
-    k_score<<<dim3(h->grid_score, n), IG_THREADS, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
+    k_score<<<dim3(h->grid_score, n), IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
                                                                  h->ns, h->row_cnt, h->table, h->table_len, mbar, h->exz, h->part_nz,
                                                                  h->part_c);
     if (h->profile) cudaEventRecord(h->ev[5], h->stream);
@@ -1469,7 +1465,7 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands) {
                                                                     h->table, h->table_len, mbar, h->part_z, h->part_i);
     if (h->profile && !h->capturing) cudaEventRecord(h->ev[4], h->stream);
     IG_MARK(5);
-    k_score<<<dim3(h->grid_score, n), IG_THREADS, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
+    k_score<<<dim3(h->grid_score, n), IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
                                                                  h->ns, h->row_cnt, h->table, h->table_len, mbar, h->exz, h->part_nz,
                                                                  h->part_c);
     if (h->profile && !h->capturing) cudaEventRecord(h->ev[5], h->stream);

@@ -62,6 +62,34 @@ class LevelData:
     sub_sampled_sparse_matrix: sp.csr_matrix  # level L, upper incl. diagonal, int32
     mean_value_trans: float
     true_order: np.ndarray = field(default=None)  # sub-frag ids along the true genome
+    true_chrom: np.ndarray = field(default=None)  # chromosome of each entry of true_order
+
+    def true_state(self):
+        """int32[13, NF] scaffold of the TRUE assembly (one contig per chromosome, fragments in true
+        order, reversed initial contigs carried as ori = -1): the fully assembled regime."""
+        parent = self.np_sub_frags_2_frags["x"].astype(np.int64)
+        fr = parent[self.true_order]
+        keep = np.r_[True, fr[1:] != fr[:-1]]
+        frags = fr[keep]                      # fragments in true order
+        chrom = self.true_chrom[keep]
+        sub_first = self.true_order[keep]     # first sub-fragment met for each fragment
+        j_first = self.np_sub_frags_2_frags["w"].astype(np.int64)[sub_first]
+        ori = np.where(j_first == 0, 1, -1)
+        soa = self.S_o_A_frags
+        sub_len = np.asarray(soa["sub_len"])[frags]
+        ori = np.where(sub_len == 1, 1, ori)
+        len_bp = np.asarray(soa["len_bp"])[frags]
+        st = _soa(chrom + 1, len_bp, sub_len)
+        out = np.zeros((13, self.n_frags), dtype=np.int32)
+        names = ("pos", "sub_pos", "id_c", "start_bp", "len_bp", "sub_len", "circ", "prev", "next", "l_cont",
+                 "sub_l_cont", "l_cont_bp")
+        for i, k in enumerate(names):
+            v = st[k]
+            if k in ("prev", "next"):
+                v = np.where(v >= 0, frags[np.clip(v, 0, None)], -1)
+            out[i, frags] = v
+        out[12, frags] = ori
+        return out
 
     def sampler_args(self):
         """The 29 positional constructor arguments of the reference ``sampler``."""
@@ -286,7 +314,7 @@ def make_level(spec: SynthSpec) -> LevelData:
         spec=spec, n_frags=nf, n_sub_frags=ns, S_o_A_frags=soa, S_o_A_sub_frags=sub_soa,
         np_sub_frags_2_frags=s2f, np_sub_frags_id=ids4, np_sub_frags_len_bp=len3, np_sub_frags_accu=accu3,
         np_rep_sub_frags_id=rep4, sparse_matrix=mat, sub_sampled_sparse_matrix=sub_mat,
-        mean_value_trans=float(mvt), true_order=true_ids,
+        mean_value_trans=float(mvt), true_order=true_ids, true_chrom=true_chrom,
     )
 
 
