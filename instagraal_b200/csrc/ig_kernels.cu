@@ -396,7 +396,7 @@ k_rows_count(const CoordRec* __restrict__ coord, int ns, DevScalars* sc, int* __
 }
 __global__ void __launch_bounds__(IG_ROW_CHUNK)
 k_rows_write(const CoordRec* __restrict__ coord, int ns, const DevScalars* __restrict__ sc, const int* __restrict__ chunk_off,
-             int n_chunks, int* __restrict__ rows, int* __restrict__ rowidx, int rows_stride) {
+             int n_chunks, int* __restrict__ rows, int* __restrict__ rowidx, int* __restrict__ row_cnt, int rows_stride) {
     const int k = blockIdx.y;
     if (k >= sc->n_cands) return;
     __shared__ int wsum[32];
@@ -417,6 +417,7 @@ k_rows_write(const CoordRec* __restrict__ coord, int ns, const DevScalars* __res
         const int off = chunk_off[k * n_chunks + blockIdx.x] + (w ? wsum[w - 1] : 0) + __popc(b & ((1u << lane) - 1));
         rows[(size_t)k * rows_stride + off] = r;
         rowidx[(size_t)k * rows_stride + r] = off;
+        row_cnt[(size_t)k * rows_stride + off] = 0;  // k_score (block mode) accumulates into it
     }
 }
 
@@ -507,28 +508,54 @@ k_precompute(const CoordRec* __restrict__ coord, const int* __restrict__ clen, c
 //      of rows) so small assemblies still fill the 148 SMs.  Mutated coordinates of both endpoints
 //      come from the table written by k_precompute (row side: warp-uniform broadcast loads; column
 //      side: rowidx gather, contiguous across neighbouring contacts).
-// The mutation loop is deliberately NOT unrolled and contact_term is instantiated only twice: an
+// The mutation loop is deliberately NOT unrolled and the expensive math is instantiated once: an
 // unrolled 24-way body (x4 group sizes) measured 35 warps stalled on instruction fetch per issue
-// (ncu "no_instruction", profiles/r1_ncu_k_score_G_v1.txt) -- the kernel has to fit the I-cache.
-// Per-thread per-slot accumulators therefore live in shared memory ([slot][thread], conflict-free).
+// (ncu "no_instruction", profiles/r1_ncu_k_score_G.txt) -- the kernel has to fit the I-cache.
+// Per-thread per-slot accumulators live in shared memory ([slot][thread], conflict-free).
+//
+// Divergence: for most (contact, mutation) pairs the term is cheap -- bit-identical to the current
+// state's term, or the constant inter-contig / out-of-range floor -- and only a few lanes of a warp
+// need powf + f64 log10 (ncu: 11 of 32 lanes active on average).  Those evaluations are therefore
+// QUEUED per warp in shared memory and executed 32 at a time with all lanes busy; the result is
+// added to the executing lane's accumulator (only the sum over lanes matters; the order is fixed,
+// hence deterministic).
+struct __align__(8) QEnt { float s; int dp; int slot; int pad; double ob; double obc; };  // 32 B
+#define IG_QCAP 64
+
+__device__ __forceinline__ void eval_queue(const QEnt* __restrict__ q, int n, double* __restrict__ my_acc, const Params& p,
+                                           double l10v, const float* __restrict__ exz_tab) {
+    const int lane = threadIdx.x & 31;
+    if (lane < n) {
+        const QEnt e = q[lane];
+        const float exf = fmaxf((p.d == 2.0f) ? (p.c1 * powf(e.s, p.slope)) * p.fact
+                                              : (p.c1 * powf(e.s, p.slope) * expf((p.d - 2) / (powf(e.s * p.lm / p.kuhn, 2.0f) + p.d))) * p.fact,
+                                p.v_inter);  // rippe_contacts for 0 < s < d_max (KA:153-163)
+        const double t = pxl_term(exf, e.ob, e.obc, l10v, p.v_inter) + (double)exz_tab[e.dp] * LOG10E_F;
+        my_acc[e.slot * IG_THREADS] += t;
+    }
+}
+
 __global__ void __launch_bounds__(IG_THREADS, 3)
 k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, const CoordRec* __restrict__ coord,
         const int* __restrict__ clen, const DevScalars* __restrict__ sc, const IgDescriptor* __restrict__ desc_g,
         const int* __restrict__ rows, const int* __restrict__ rowidx, int ns, int* __restrict__ row_cnt,
         const RowMut* __restrict__ table, const int* __restrict__ table_len, float mbar, const float* __restrict__ exz_tab,
         double* __restrict__ part_nz,   // [cand][25][gridDim.x]  (24 uniq slots + current)
-        int* __restrict__ part_c)       // [cand][2][gridDim.x]   (contacts selected, contacts read)
+        int* __restrict__ part_c,       // [cand][2][gridDim.x]   (contacts selected, contacts read)
+        int gs_div)                     // work-splitting knob: split a row into slot groups while rows*groups < warps/gs_div
 {
     const int k = blockIdx.y;
     if (k >= sc->n_cands) return;
     extern __shared__ double acc_s[];                 // [IG_N_OPS][IG_THREADS]
     __shared__ double red[IG_WARPS_PER_BLOCK][25];
     __shared__ int redi[IG_WARPS_PER_BLOCK][2];
+    __shared__ QEnt queue[IG_WARPS_PER_BLOCK][IG_QCAP];
     const Params p = sc->p;
     const double l10v = sc->log10_vinter;
     const CandInfo ci_k = sc->ci[k];
     const int n_uniq = desc_g[k].n_uniq;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1;
     if (lane < 25) red[w][lane] = 0.0;
     if (lane < 2) redi[w][lane] = 0;
     __syncwarp();
@@ -539,12 +566,32 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
     const int* tlen = table_len + (size_t)k * IG_N_OPS * ns;
     const int wg = blockIdx.x * IG_WARPS_PER_BLOCK + w, nw = gridDim.x * IG_WARPS_PER_BLOCK;
     // group size: all slots per item when there are more rows than warps, fewer when a candidate has few rows
+    // Work distribution.  Mode W (many rows): one warp per (row, slot group), gs = 24.  Mode B (few rows,
+    // e.g. a yeast-scale assembly): one BLOCK per (row, slot group), its 8 warps striding the row's
+    // contacts, so that the longest row no longer sets the kernel's critical path; rows are split into
+    // slot groups only as far as needed to occupy the grid (each extra group repeats the per-contact
+    // selection + current-state term).
+    // (block mode is kept for experiments, IG_BLOCK_MODE=1: at yeast scale it measured slower than
+    //  splitting rows into slot groups -- 79 us vs 64 us -- because only 3 of 8 warps find contacts)
+    const bool block_mode = (gs_div < 0) && ci_k.n_rows < nw / (-gs_div);
+    const int div = gs_div < 0 ? -gs_div : gs_div;
     int gs = IG_N_OPS;
-    if (ci_k.n_rows < nw) gs = (ci_k.n_rows * 4 >= nw) ? 6 : ((ci_k.n_rows * 8 >= nw) ? 3 : 1);
+    if (block_mode) {
+        const int want = (int)gridDim.x / 2;
+        gs = (ci_k.n_rows >= want) ? 24 : ((ci_k.n_rows * 4 >= want) ? 6 : ((ci_k.n_rows * 8 >= want) ? 3 : 1));
+    } else {
+        const int want = nw / div;
+        if (ci_k.n_rows < want) gs = (ci_k.n_rows * 4 >= want) ? 6 : ((ci_k.n_rows * 8 >= want) ? 3 : 1);
+    }
     const int ng = IG_N_OPS / gs;
     const int n_items = ci_k.n_rows * ng;
     double* my_acc = acc_s + threadIdx.x;
-    for (int it = wg; it < n_items; it += nw) {
+    QEnt* myq = queue[w];
+    // constant term of a contact whose endpoints lie in different contigs (KA:4348-4352) minus the ob part
+    const double inter_const = (double)p.v_inter * LOG10E_F;
+    const int it0 = block_mode ? (int)blockIdx.x : wg, it_step = block_mode ? (int)gridDim.x : nw;
+    const int q_off = block_mode ? 32 * w : 0, q_step = block_mode ? 32 * IG_WARPS_PER_BLOCK : 32;
+    for (int it = it0; it < n_items; it += it_step) {
         const int ri = it / ng, g = it - ri * ng;
         const int u0 = g * gs;
         if (u0 >= n_uniq && g != 0) continue;
@@ -555,38 +602,84 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
         for (int u = u0; u < u1; u++) my_acc[(u - u0) * IG_THREADS] = 0.0;
         double acc_cur = 0.0;
         int row_sel = 0;
-        for (long long q = b + lane; q < e; q += 32) {
-            const int2 c = __ldg(&cv[q]);
-            const CoordRec cj = coord[c.x];
-            if (!(cj.id_c == ci_k.id_a || cj.id_c == ci_k.id_b)) continue;
-            if (!contact_selected(ci, cj, c.y, ci_k)) continue;
-            row_sel++;
-            const double ob = (double)c.y, obc = ob_const(ob);
-            const double t_cur = contact_term(ci, cj, clen[c.x], ob, obc, p, l10v, mbar, exz_tab);
-            acc_cur += t_cur;
-            const int rj = my_idx[c.x];
-            const bool cur_same = ci.id_c == cj.id_c;
-            const float cur_s = fabsf(ci.dist - cj.dist);
-            const int cur_dp = abs(ci.pos - cj.pos);
+        int qn = 0;  // warp-uniform queue fill
+        for (long long q0 = b + q_off; q0 < e; q0 += q_step) {
+            const long long q = q0 + lane;
+            bool active = false;
+            int2 c = make_int2(0, 0);
+            CoordRec cj = ci;
+            if (q < e) {
+                c = __ldg(&cv[q]);
+                cj = coord[c.x];
+                active = (cj.id_c == ci_k.id_a || cj.id_c == ci_k.id_b) && contact_selected(ci, cj, c.y, ci_k);
+            }
+            if (!__any_sync(0xffffffffu, active)) continue;
+            double ob = 0.0, obc = 0.0, t_cur = 0.0, t_inter = 0.0;
+            int rj = 0, cur_dp = 0;
+            float cur_s = 0.f;
+            bool cur_same = false;
+            if (active) {
+                row_sel++;
+                ob = (double)c.y; obc = ob_const(ob);
+                t_cur = contact_term(ci, cj, clen[c.x], ob, obc, p, l10v, mbar, exz_tab);
+                acc_cur += t_cur;
+                t_inter = pxl_term(p.v_inter, ob, obc, l10v, p.v_inter) + inter_const;
+                rj = my_idx[c.x];
+                cur_same = ci.id_c == cj.id_c;
+                cur_s = fabsf(ci.dist - cj.dist);
+                cur_dp = abs(ci.pos - cj.pos);
+            }
             const RowMut* ta = tab + (size_t)u0 * ns + ri;
             const RowMut* tb = tab + (size_t)u0 * ns + rj;
 #pragma unroll 1
             for (int u = u0; u < u1; u++, ta += ns, tb += ns) {
-                const RowMut a = *ta;
-                const RowMut bm = *tb;
-                CoordRec cim, cjm;
-                cim.dist = a.dist; cim.id_c = a.id_c; cim.pos = a.pos; cim.s_tot = a.s_tot;
-                cjm.dist = bm.dist; cjm.id_c = bm.id_c; cjm.pos = bm.pos; cjm.s_tot = bm.s_tot;
-                const bool m_same = cim.id_c == cjm.id_c;
-                double t = t_cur;  // bit-exact shortcut: identical inputs give the identical term
-                if (!(m_same == cur_same && cim.s_tot == ci.s_tot &&
-                      (!m_same || (cim.s_tot == 0 && fabsf(cim.dist - cjm.dist) == cur_s && abs(cim.pos - cjm.pos) == cur_dp)))) {
-                    const int len_j = (m_same && cim.s_tot != 0) ? tlen[(size_t)u * ns + rj] : 0;
-                    t = contact_term(cim, cjm, len_j, ob, obc, p, l10v, mbar, exz_tab);
+                bool push = false;
+                float s_m = 0.f;
+                int dp_m = 0;
+                if (active) {
+                    const RowMut a = *ta;
+                    const RowMut bm = *tb;
+                    const bool m_same = a.id_c == bm.id_c;
+                    s_m = fabsf(a.dist - bm.dist);
+                    dp_m = abs(a.pos - bm.pos);
+                    double t;
+                    if (m_same == cur_same && a.s_tot == ci.s_tot && (!m_same || (a.s_tot == 0 && s_m == cur_s && dp_m == cur_dp))) {
+                        t = t_cur;            // bit-exact shortcut: identical inputs give the identical term
+                    } else if (!m_same) {
+                        t = t_inter;          // different contigs: both expectations are v_inter
+                    } else if (a.s_tot != 0) {  // circular contig (rare): evaluate in place
+                        CoordRec cim, cjm;
+                        cim.dist = a.dist; cim.id_c = a.id_c; cim.pos = a.pos; cim.s_tot = a.s_tot;
+                        cjm.dist = bm.dist; cjm.id_c = bm.id_c; cjm.pos = bm.pos; cjm.s_tot = bm.s_tot;
+                        t = contact_term(cim, cjm, tlen[(size_t)u * ns + rj], ob, obc, p, l10v, mbar, exz_tab);
+                    } else if (!((s_m > 0.0f) && (s_m < p.d_max))) {
+                        // linear, outside (0, d_max): rippe_contacts returns max(0, v_inter) = v_inter
+                        t = pxl_term(p.v_inter, ob, obc, l10v, p.v_inter) + (double)exz_tab[dp_m] * LOG10E_F;
+                    } else {
+                        push = true; t = 0.0;  // needs powf + log10: queue it
+                    }
+                    if (!push) my_acc[(u - u0) * IG_THREADS] += t;
                 }
-                my_acc[(u - u0) * IG_THREADS] += t;
+                const unsigned pm = __ballot_sync(0xffffffffu, push);
+                if (pm) {
+                    if (push) {
+                        QEnt en; en.s = s_m; en.dp = dp_m; en.slot = u - u0; en.pad = 0; en.ob = ob; en.obc = obc;
+                        myq[qn + __popc(pm & lt_mask)] = en;
+                    }
+                    qn += __popc(pm);
+                    __syncwarp();
+                    if (qn >= 32) {
+                        eval_queue(myq, 32, my_acc, p, l10v, exz_tab);
+                        __syncwarp();
+                        if (lane < qn - 32) { const QEnt mv = myq[32 + lane]; myq[lane] = mv; }
+                        qn -= 32;
+                        __syncwarp();
+                    }
+                }
             }
         }
+        if (qn > 0) { eval_queue(myq, qn, my_acc, p, l10v, exz_tab); }
+        __syncwarp();
         // fixed-order accumulation into this warp's slot sums (work items are visited in a fixed order)
         for (int u = u0; u < u1; u++) {
             const double v = warp_sum(my_acc[(u - u0) * IG_THREADS]);
@@ -595,7 +688,11 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
         if (g == 0) {
             const double v = warp_sum(acc_cur);
             row_sel = __reduce_add_sync(0xffffffffu, row_sel);
-            if (lane == 0) { red[w][24] += v; my_cnt[ri] = row_sel; redi[w][0] += row_sel; redi[w][1] += (int)(e - b); }
+            if (lane == 0) {
+                red[w][24] += v; redi[w][0] += row_sel;
+                if (block_mode) { if (row_sel) atomicAdd(&my_cnt[ri], row_sel); if (w == 0) redi[w][1] += (int)(e - b); }
+                else { my_cnt[ri] = row_sel; redi[w][1] += (int)(e - b); }
+            }
         }
     }
     __syncthreads();
@@ -1066,6 +1163,7 @@ struct ig_handle {
     bool params_set, coords_fresh, coords_ever;
     bool incr_valid; int refresh_every; long long steps_since_full;
     double* part_out;
+    int gs_div;
     long long last_n_full;
     cudaGraphExec_t graph[2]; bool graph_failed, capturing, use_graph; long long n_full;
     // measurement (CUDA events on the launching stream)
@@ -1128,6 +1226,9 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
     h->cfg = *cfg; h->nf = cfg->n_frags; h->ns = cfg->n_sub_frags; h->nnz = cfg->nnz;
     h->params_set = false; h->coords_fresh = false; h->coords_ever = false;
     h->incr_valid = false; h->refresh_every = 4096; h->steps_since_full = 0;
+    h->gs_div = 4;
+    if (const char* e = getenv("IG_GS_DIV")) h->gs_div = std::max(1, atoi(e));
+    if (const char* e = getenv("IG_BLOCK_MODE")) if (atoi(e)) h->gs_div = -h->gs_div;
     h->graph[0] = h->graph[1] = nullptr; h->graph_failed = false; h->capturing = false; h->use_graph = true; h->n_full = 0;
     cudaError_t e0 = cudaSetDevice(cfg->device);
     if (e0 != cudaSuccess) { g_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e0); delete h; return -2; }
@@ -1371,13 +1472,13 @@ static int score_candidates(ig_handle* h, int a, const int32_t* cands, int n, in
     if (overlap) cudaStreamWaitEvent(h->stream, h->ev_coords, 0);
     k_rows_count<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks);
     k_rows_write<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks, h->rows,
-                                                                       h->rowidx, h->ns);
+                                                                       h->rowidx, h->row_cnt, h->ns);
     k_precompute<<<dim3(h->grid_pre, n), IG_THREADS, 0, h->stream>>>(h->coord, h->clen, live, h->sub, h->sc, h->desc, h->rows, h->ns,
                                                                     h->table, h->table_len, mbar, h->part_z, h->part_i);
     if (h->profile) cudaEventRecord(h->ev[4], h->stream);
     k_score<<<dim3(h->grid_score, n), IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
                                                                  h->ns, h->row_cnt, h->table, h->table_len, mbar, h->exz, h->part_nz,
-                                                                 h->part_c);
+                                                                 h->part_c, h->gs_div);
     if (h->profile) cudaEventRecord(h->ev[5], h->stream);
     h->n_launches += 7;
     if (overlap) cudaStreamWaitEvent(h->stream, h->ev_lnz, 0);
@@ -1459,7 +1560,7 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands) {
     k_rows_count<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks);
     IG_MARK(3);
     k_rows_write<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks, h->rows,
-                                                                       h->rowidx, h->ns);
+                                                                       h->rowidx, h->row_cnt, h->ns);
     IG_MARK(4);
     k_precompute<<<dim3(h->grid_pre, n), IG_THREADS, 0, h->stream>>>(h->coord, h->clen, live, h->sub, h->sc, h->desc, h->rows, h->ns,
                                                                     h->table, h->table_len, mbar, h->part_z, h->part_i);
@@ -1467,7 +1568,7 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands) {
     IG_MARK(5);
     k_score<<<dim3(h->grid_score, n), IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
                                                                  h->ns, h->row_cnt, h->table, h->table_len, mbar, h->exz, h->part_nz,
-                                                                 h->part_c);
+                                                                 h->part_c, h->gs_div);
     if (h->profile && !h->capturing) cudaEventRecord(h->ev[5], h->stream);
     cudaStreamWaitEvent(h->stream, h->ev_lnz, 0);
     IG_MARK(6);
