@@ -100,6 +100,14 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(workload, kernel):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the
+    committed `ncu --set full` capture of the same workload (profiles/r1_ncu_*.txt), or None."""
+    table = {("T", "k_score"): 1.118208e6 + 0.0, ("G", "k_score"): 118.486784e6 + 4.7104e6,
+             ("G", "k_full_lnz"): 679.342336e6 + 4.3264e6}
+    return table.get((workload, kernel))
+
+
 def build_level(name):
     from instagraal_b200.synth import WORKLOADS, make_level
     t0 = time.time()
@@ -271,7 +279,7 @@ def run_ours(args):
                 "ms_per_step": t_e2e_max / n_e2e * 1e3},
         "gpu_launches": int(st["launches"]),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach[dom], "peak": peak, "unit": "GB/s",
-                     "frac": ach[dom] / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": ach[dom] / peak, "traffic": measured_traffic(args.workload, dom), "peak_source": peak_src,
                      "kernels": {k: {"launches": kern[k][2], "ms_per_launch": kern[k][0] / max(kern[k][2], 1),
                                      "alg_bytes_per_launch": kern[k][1] / max(kern[k][2], 1),
                                      "achieved_GBs": ach[k]} for k in kern},
@@ -403,8 +411,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3000)
-    ap.add_argument("--warmup", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=8000)
+    ap.add_argument("--warmup", type=int, default=500)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="T")
     ap.add_argument("--burn-cycles", type=int, default=-1)

@@ -712,7 +712,7 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
 // K9: per-candidate finalisation: fixed-order parallel reduction of the block partials, the
 //     reference's last-block quirk (KA:4362), zero terms (eval_all_likelihood_on_zero_2nd
 //     KA:4005-4027) and score assembly (eval_all_scores KA:4029-4046).  One block per candidate.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, const CoordRec* __restrict__ coord,
            DevScalars* sc, const IgDescriptor* __restrict__ desc_g, const int* __restrict__ rows, const int* __restrict__ rowidx,
            int ns, const int* __restrict__ row_cnt, const RowMut* __restrict__ table, const int* __restrict__ table_len,
@@ -727,7 +727,7 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
     __shared__ int2 t_cv[64];
     __shared__ int t_ri[64];
     __shared__ int t_cnt, t_need, t_ri_cur;
-    __shared__ int t_wsum[8];
+    __shared__ int t_wsum[32];
     const IgDescriptor& d = desc_g[k];
     const Params p = sc->p;
     const double l10v = sc->log10_vinter;
@@ -735,27 +735,35 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
     const int n_uniq = d.n_uniq;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     // 25 + 25 + 25 + 2 slots, one warp per slot, lanes stride the partial blocks, fixed shuffle tree
+    // 32 warps, one slot each per round; every lane first issues all of its loads (independent, in
+    // flight together), then adds them in index order; fixed shuffle tree => deterministic
     for (int slot = w; slot < 77; slot += nwarp) {
-        if (slot < 25) {
+        if (slot < 50) {
+            const double* src = slot < 25 ? &part_nz[PART_IDX(k, 25, slot, n_part, 0)] : &part_z[PART_IDX(k, 25, slot - 25, n_part_z, 0)];
+            const int n = slot < 25 ? n_part : n_part_z;
             double v = 0.0;
-            for (int i = lane; i < n_part; i += 32) v += part_nz[PART_IDX(k, 25, slot, n_part, i)];
+            for (int i0 = 0; i0 < n; i0 += 32 * 8) {
+                double x[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) { const int i = i0 + j * 32 + lane; x[j] = i < n ? src[i] : 0.0; }
+#pragma unroll
+                for (int j = 0; j < 8; j++) v += x[j];
+            }
             v = warp_sum(v);
-            if (lane == 0) s_nz[slot] = v;
-        } else if (slot < 50) {
-            double v = 0.0;
-            for (int i = lane; i < n_part_z; i += 32) v += part_z[PART_IDX(k, 25, slot - 25, n_part_z, i)];
-            v = warp_sum(v);
-            if (lane == 0) s_z[slot - 25] = v;
-        } else if (slot < 75) {
-            int v = 0;
-            for (int i = lane; i < n_part_z; i += 32) v += part_i[PART_IDX(k, 25, slot - 50, n_part_z, i)];
-            v = __reduce_add_sync(0xffffffffu, v);
-            if (lane == 0) s_i[slot - 50] = v;
+            if (lane == 0) { if (slot < 25) s_nz[slot] = v; else s_z[slot - 25] = v; }
         } else {
+            const int* src = slot < 75 ? &part_i[PART_IDX(k, 25, slot - 50, n_part_z, 0)] : &part_c[PART_IDX(k, 2, slot - 75, n_part, 0)];
+            const int n = slot < 75 ? n_part_z : n_part;
             int v = 0;
-            for (int i = lane; i < n_part; i += 32) v += part_c[PART_IDX(k, 2, slot - 75, n_part, i)];
+            for (int i0 = 0; i0 < n; i0 += 32 * 8) {
+                int x[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) { const int i = i0 + j * 32 + lane; x[j] = i < n ? src[i] : 0; }
+#pragma unroll
+                for (int j = 0; j < 8; j++) v += x[j];
+            }
             v = __reduce_add_sync(0xffffffffu, v);
-            if (lane == 0) s_c[slot - 75] = v;
+            if (lane == 0) { if (slot < 75) s_i[slot - 50] = v; else s_c[slot - 75] = v; }
         }
     }
     if (threadIdx.x < IG_N_OPS) s_corr[threadIdx.x] = 0.0;
@@ -1482,7 +1490,7 @@ static int score_candidates(ig_handle* h, int a, const int32_t* cands, int n, in
     if (h->profile) cudaEventRecord(h->ev[5], h->stream);
     h->n_launches += 7;
     if (overlap) cudaStreamWaitEvent(h->stream, h->ev_lnz, 0);
-    k_finalize<<<n, 256, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->sc, h->desc, h->rows, h->rowidx, h->ns, h->row_cnt, h->table,
+    k_finalize<<<n, 1024, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->sc, h->desc, h->rows, h->rowidx, h->ns, h->row_cnt, h->table,
                                          h->table_len, mbar, h->exz, h->part_nz, h->part_c, h->grid_score, h->part_z, h->part_i,
                                          h->grid_pre, h->cfg.n_pix, h->cfg.compat_last_block, h->d_nuniq, h->d_nsub);
     return launch_ok(h, "score_candidates");
@@ -1572,7 +1580,7 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands) {
     if (h->profile && !h->capturing) cudaEventRecord(h->ev[5], h->stream);
     cudaStreamWaitEvent(h->stream, h->ev_lnz, 0);
     IG_MARK(6);
-    k_finalize<<<n, 256, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->sc, h->desc, h->rows, h->rowidx, h->ns, h->row_cnt, h->table,
+    k_finalize<<<n, 1024, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->sc, h->desc, h->rows, h->rowidx, h->ns, h->row_cnt, h->table,
                                          h->table_len, mbar, h->exz, h->part_nz, h->part_c, h->grid_score, h->part_z, h->part_i,
                                          h->grid_pre, h->cfg.n_pix, h->cfg.compat_last_block, h->d_nuniq, h->d_nsub);
     IG_MARK(7);

@@ -174,6 +174,16 @@ class sampler:
             "pop out insert @ right or -1", "transloc_1", "transloc_2", "transloc_3", "transloc_4",
             "local_scramble d1", "local_scramble d2", "local_scramble d3", "local_scramble d4"]
         self.setup_distri_frags()
+        # one result record per handle, read through NumPy views (no per-step ctypes -> list conversions)
+        self._res = L.ig_step_result()
+        self._res_scores = np.frombuffer(self._res, dtype=np.float64, count=L.IG_MAX_CANDS * L.IG_N_OPS,
+                                         offset=L.ig_step_result.scores.offset)
+        self._res_nuniq = np.frombuffer(self._res, dtype=np.int32, count=L.IG_MAX_CANDS, offset=L.ig_step_result.n_uniq.offset)
+        self._res_nsub = np.frombuffer(self._res, dtype=np.int32, count=L.IG_MAX_CANDS, offset=L.ig_step_result.n_sub.offset)
+        self._cand_buf = np.zeros(L.IG_MAX_CANDS, dtype=np.int32)
+        self._cand_ptr = _ptr(self._cand_buf)
+        self._res_ref = C.byref(self._res)
+        self._ig_step = L.lib().ig_step
 
     # ------------------------------------------------------------------ state plumbing
     def _get_state(self):
@@ -290,14 +300,16 @@ class sampler:
         self.candidates = list(candidates)
         self.candidates.sort()
         n = len(self.candidates)
-        cands = np.ascontiguousarray(self.candidates, dtype=np.int32)
-        res = L.ig_step_result()
-        L.check(self._h, L.lib().ig_step(self._h, int(id_frag), _ptr(cands), n, C.byref(res)), "ig_step")
-        self.all_scores = np.array(res.scores[:self.n_tmp_struct * n], dtype=np.float64)
-        self.n_uniq = list(res.n_uniq[:n])
-        self.n_sub_vals = list(res.n_sub[:n])
-        self.n_proposals_scored += int(sum(self.n_uniq))
-        self.q4_hits = int(res.q4_hits)
+        self._cand_buf[:n] = self.candidates
+        res = self._res
+        rc = self._ig_step(self._h, int(id_frag), self._cand_ptr, n, self._res_ref)
+        if rc != 0:
+            L.check(self._h, rc, "ig_step")
+        self.all_scores = self._res_scores[:self.n_tmp_struct * n].copy()
+        self.n_uniq = self._res_nuniq[:n].tolist()
+        self.n_sub_vals = self._res_nsub[:n].tolist()
+        self.n_proposals_scored += sum(self.n_uniq)
+        self.q4_hits = res.q4_hits
         global_id = np.int64(res.cand_index * self.n_tmp_struct + res.op_sampled)
         id_f_sampled = self.candidates[int(global_id / self.n_tmp_struct)]
         op_sampled = global_id % self.n_tmp_struct
