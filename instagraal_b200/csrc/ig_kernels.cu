@@ -68,7 +68,7 @@ struct DevScalars {
     unsigned int ticket_out;
     double full_out[3];
     int full_nintra, pad_;
-    unsigned int ticket_cuts[IG_MAX_CANDS], ticket_rows[IG_MAX_CANDS];  // last-block-done counters
+    unsigned int ticket_cuts[IG_MAX_CANDS], ticket_rows[IG_MAX_CANDS], ticket_fin;  // last-block-done counters
     // measurement: algorithmic traffic of the scoring kernel, accumulated over steps
     unsigned long long st_contacts, st_rows, st_frags, st_selected, st_proposals;
 };
@@ -317,6 +317,7 @@ __global__ void k_cand_setup(const FragRec* __restrict__ live, DevScalars* sc, I
         d.n_uniq = ig_uniq_mutations(A, B, sv[k], (k == 0) ? first_flip_eject : 0, d.uniq);
     }
     if (k < 12) sc->valid[k] = sv[n][k];  // state after the last candidate's get_bounds (CL:1854-1870)
+    if (k == 0) sc->ticket_fin = 0;
 }
 // K3: cut fragments of get_bounds (KA:2255-2269), all candidates at once; the LAST block to finish a
 //     candidate then evaluates every pivot of its descriptor (one thread).
@@ -709,6 +710,8 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
 }
 #define IG_SCORE_SMEM (IG_N_OPS * IG_THREADS * sizeof(double))
 
+__device__ void select_step(DevScalars* sc, const IgDescriptor* __restrict__ desc_g);
+
 // K9: per-candidate finalisation: fixed-order parallel reduction of the block partials, the
 //     reference's last-block quirk (KA:4362), zero terms (eval_all_likelihood_on_zero_2nd
 //     KA:4005-4027) and score assembly (eval_all_scores KA:4029-4046).  One block per candidate.
@@ -718,7 +721,7 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
            int ns, const int* __restrict__ row_cnt, const RowMut* __restrict__ table, const int* __restrict__ table_len,
            float mbar, const float* __restrict__ exz_tab, const double* __restrict__ part_nz, const int* __restrict__ part_c,
            int n_part, const double* __restrict__ part_z, const int* __restrict__ part_i, int n_part_z, double n_pix,
-           int compat_last_block, int* __restrict__ n_uniq_out, int* __restrict__ n_sub_out) {
+           int compat_last_block, int* __restrict__ n_uniq_out, int* __restrict__ n_sub_out, int do_select) {
     const int k = blockIdx.x;
     if (k >= sc->n_cands) return;
     __shared__ double s_nz[25], s_z[25], s_corr[IG_N_OPS];
@@ -871,6 +874,16 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
         atomicAdd(&sc->st_selected, (unsigned long long)n_sub);
         atomicAdd(&sc->st_proposals, (unsigned long long)n_uniq);
     }
+    if (!do_select) return;
+    // move selection by the LAST candidate block to finish (saves a dependent launch)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) t_cnt = (atomicAdd(&sc->ticket_fin, 1u) == (unsigned)sc->n_cands - 1) ? 1 : 0;
+    __syncthreads();
+    if (t_cnt && threadIdx.x < 32) {
+        __threadfence();
+        select_step(sc, desc_g);
+    }
 }
 
 // K10: move selection (CL:1435-1446): scores==0 -> -inf; first index of the maximum.
@@ -895,14 +908,14 @@ __global__ void k_select(DevScalars* sc) {
 }
 // step path: selection + the bookkeeping of k_post_scalars in one launch (k_apply reads the label base
 // from the descriptor, not from sc->max_label, so bumping it here cannot race)
-__global__ void k_select_step(DevScalars* sc, const IgDescriptor* __restrict__ desc_g) {
+__device__ void select_step(DevScalars* sc, const IgDescriptor* __restrict__ desc_g) {
     const int n = sc->n_cands * IG_N_OPS;
-    const int lane = threadIdx.x;  // one warp
+    const int lane = threadIdx.x & 31;  // executed by one full warp
     // first index of the maximum among the scored (non-zero) proposals (CL:1435-1446)
     int best = -1;
     double bv = 0.0;
     for (int i = lane; i < n; i += 32) {
-        const double v = sc->scores[i];
+        const double v = __ldcg(&sc->scores[i]);
         if (v == 0.0) continue;
         if (best < 0 || v > bv) { best = i; bv = v; }
     }
@@ -918,15 +931,16 @@ __global__ void k_select_step(DevScalars* sc, const IgDescriptor* __restrict__ d
     const unsigned hit = __ballot_sync(0xffffffffu, lane < desc_g[kc].n_uniq && desc_g[kc].uniq[lane] == op);
     if (lane < 12 && op >= 12) sc->valid[lane] = desc_g[kc].valid[lane];
     if (lane != 0) return;
-    sc->win_cand = kc; sc->win_op = op; sc->likelihood = sc->scores[best];
+    sc->win_cand = kc; sc->win_op = op; sc->likelihood = __ldcg(&sc->scores[best]);
     sc->n_heads = 0; sc->sum_l_cont = 0; sc->dist_half = 0;
     sc->max_label += 2;
     sc->prev_k = kc; sc->prev_u = hit ? (__ffs(hit) - 1) : 0;
     sc->prev_windowed = (sc->ci[kc].same && sc->ci[kc].is_circ == 0) ? 1 : 0;
     sc->prev_id_a = sc->ci[kc].id_a; sc->prev_n_rows = sc->ci[kc].n_rows;
-    sc->lnz_next = sc->lnz_new[best]; sc->z_next = sc->z_new[best]; sc->nintra_next = sc->nintra_new[best];
+    sc->lnz_next = __ldcg(&sc->lnz_new[best]); sc->z_next = __ldcg(&sc->z_new[best]); sc->nintra_next = __ldcg(&sc->nintra_new[best]);
     sc->ticket_out = 0;
 }
+__global__ void k_select_step(DevScalars* sc, const IgDescriptor* __restrict__ desc_g) { select_step(sc, desc_g); }
 
 // Same-linear-contig moves are scored on a WINDOWED slice (slice_sp_mat, KA:565-586): contacts of the
 // contig outside the windows keep their distance mathematically, but the reference's next full
@@ -1492,7 +1506,7 @@ static int score_candidates(ig_handle* h, int a, const int32_t* cands, int n, in
     if (overlap) cudaStreamWaitEvent(h->stream, h->ev_lnz, 0);
     k_finalize<<<n, 1024, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->sc, h->desc, h->rows, h->rowidx, h->ns, h->row_cnt, h->table,
                                          h->table_len, mbar, h->exz, h->part_nz, h->part_c, h->grid_score, h->part_z, h->part_i,
-                                         h->grid_pre, h->cfg.n_pix, h->cfg.compat_last_block, h->d_nuniq, h->d_nsub);
+                                         h->grid_pre, h->cfg.n_pix, h->cfg.compat_last_block, h->d_nuniq, h->d_nsub, 0);
     return launch_ok(h, "score_candidates");
 }
 
@@ -1582,9 +1596,8 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands) {
     IG_MARK(6);
     k_finalize<<<n, 1024, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->sc, h->desc, h->rows, h->rowidx, h->ns, h->row_cnt, h->table,
                                          h->table_len, mbar, h->exz, h->part_nz, h->part_c, h->grid_score, h->part_z, h->part_i,
-                                         h->grid_pre, h->cfg.n_pix, h->cfg.compat_last_block, h->d_nuniq, h->d_nsub);
+                                         h->grid_pre, h->cfg.n_pix, h->cfg.compat_last_block, h->d_nuniq, h->d_nsub, 1);
     IG_MARK(7);
-    k_select_step<<<1, 32, 0, h->stream>>>(h->sc, h->desc);
     IG_MARK(8);
     // independent of apply/post: runs beside them on the side stream, joined before the result copy
     cudaEventRecord(h->ev_sel, h->stream);
@@ -1603,8 +1616,8 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands) {
     cudaMemcpyAsync(h->h_small + 32, h->d_nsub, IG_MAX_CANDS * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
     return launch_ok(h, "enqueue_step");
 }
-#define IG_LAUNCHES_FULL 15
-#define IG_LAUNCHES_INCR 12
+#define IG_LAUNCHES_FULL 14
+#define IG_LAUNCHES_INCR 11
 
 static int get_graph(ig_handle* h, int full, cudaGraphExec_t* out) {
     cudaGraphExec_t& ge = h->graph[full];
