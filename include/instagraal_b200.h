@@ -66,6 +66,16 @@ typedef struct ig_step_result {
     int32_t reserved;
 } ig_step_result;
 
+typedef struct ig_cycle_step {   /* compact per-step record of ig_run_cycle (what IG.full_em collects, IG:221-241) */
+    double likelihood;       /* o */
+    double lnz_full;
+    double dist;
+    int64_t sum_l_cont;
+    int32_t n_contigs, op_sampled, id_f_sampled, cand_index;
+    int32_t n_proposals;     /* proposals scored in this step (sum of n_uniq) */
+    int32_t q4_hits;
+} ig_cycle_step;
+
 /* sampler.__init__ device part (CL:92-319: sparse_data_2_gpu, setup_all_gpu_struct, loadProgram) */
 int ig_create(const ig_config* cfg, const ig_level_data* data, ig_handle** out);
 /* sampler.free_gpu (CL:3167-3177) */
@@ -88,6 +98,10 @@ int ig_bomb(ig_handle* h, const int32_t* perm);
 
 /* step_sampler (CL:1401-1465) after the host drew + sorted the candidates (CL:1403-1404) */
 int ig_step(ig_handle* h, int32_t id_frag, const int32_t* cands, int32_t n_cands, ig_step_result* out);
+/* n_steps consecutive step_sampler calls (the inner loop of full_em, IG:217-241) enqueued without any host
+ * synchronisation in between; cands8 = [n_steps][IG_MAX_CANDS] sorted candidates, n_cands = [n_steps]. */
+int ig_run_cycle(ig_handle* h, int32_t n_steps, const int32_t* frags, const int32_t* cands8, const int32_t* n_cands,
+                 ig_cycle_step* out);
 /* eval = score every mutation of one (A,B) pair without applying: extract_uniq_mutations +
  * perform_mutations + slice_sparse_mat + extract_current_sub_likelihood + eval_all_sub_likelihood
  * (CL:1417-1431).  Refreshes the coordinates / full likelihood like the head of step_sampler. */

@@ -21,7 +21,7 @@ EXPORTS = (
     "ig_create", "ig_destroy", "ig_last_error", "ig_device_count", "ig_set_params", "ig_get_state",
     "ig_set_state", "ig_get_valid_insert", "ig_set_valid_insert", "ig_bomb", "ig_step", "ig_eval_scores",
     "ig_apply", "ig_full_likelihood", "ig_distance_histogram", "ig_set_sym_diag", "ig_device_state_ptr",
-    "ig_set_profiling", "ig_get_stats", "ig_set_options", "ig_get_full_refresh_count", "ig_get_kernel_times",
+    "ig_set_profiling", "ig_get_stats", "ig_set_options", "ig_get_full_refresh_count", "ig_get_kernel_times", "ig_run_cycle",
 )
 
 
@@ -43,6 +43,15 @@ class ig_step_result(C.Structure):
                 ("n_uniq", C.c_int32 * IG_MAX_CANDS), ("n_sub", C.c_int32 * IG_MAX_CANDS), ("q4_hits", C.c_int32),
                 ("reserved", C.c_int32)]
 
+
+class ig_cycle_step(C.Structure):
+    _fields_ = [("likelihood", C.c_double), ("lnz_full", C.c_double), ("dist", C.c_double), ("sum_l_cont", C.c_int64),
+                ("n_contigs", C.c_int32), ("op_sampled", C.c_int32), ("id_f_sampled", C.c_int32), ("cand_index", C.c_int32),
+                ("n_proposals", C.c_int32), ("q4_hits", C.c_int32)]
+
+
+CYCLE_DTYPE = [("likelihood", "<f8"), ("lnz_full", "<f8"), ("dist", "<f8"), ("sum_l_cont", "<i8"), ("n_contigs", "<i4"),
+               ("op_sampled", "<i4"), ("id_f_sampled", "<i4"), ("cand_index", "<i4"), ("n_proposals", "<i4"), ("q4_hits", "<i4")]
 
 _lib = None
 
@@ -79,6 +88,7 @@ def lib():
         L.ig_get_stats.argtypes = [vp, vp, i32]
         L.ig_set_options.argtypes = [vp, i32, i32]
         L.ig_get_kernel_times.argtypes = [vp, vp, i32]
+        L.ig_run_cycle.argtypes = [vp, i32, vp, vp, vp, vp]
         L.ig_get_full_refresh_count.argtypes = [vp, C.POINTER(i64)]
         for name in EXPORTS:
             if name not in ("ig_destroy", "ig_last_error"):

@@ -65,12 +65,21 @@ struct DevScalars {
     // incremental maintenance of (coordinates, lnz_full, z_cur, nintra_cur) across steps
     double lnz_next, z_next; int nintra_next;
     int prev_k, prev_u, prev_windowed, prev_id_a, prev_n_rows;
-    unsigned int ticket_out;
+    unsigned int ticket_out, ticket_post;
+    int step_idx;
     double full_out[3];
     int full_nintra, pad_;
     unsigned int ticket_cuts[IG_MAX_CANDS], ticket_rows[IG_MAX_CANDS], ticket_fin;  // last-block-done counters
     // measurement: algorithmic traffic of the scoring kernel, accumulated over steps
     unsigned long long st_contacts, st_rows, st_frags, st_selected, st_proposals;
+};
+
+struct CycleOut {  // compact per-step record of ig_run_cycle (128 B)
+    double likelihood, lnz_full;
+    long long dist_half, sum_l_cont;
+    int n_heads, win_cand, win_op, q4_hits;
+    int n_uniq[IG_MAX_CANDS], n_sub[IG_MAX_CANDS];
+    int pad[8];
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -281,7 +290,12 @@ __global__ void k_set_params(DevScalars* sc, Params p, int test) {
 // K2: per-candidate setup.  Thread 0 walks the candidates IN ORDER because extract_uniq_mutations
 //     of candidate k reads the list_valid_insert left by get_bounds of candidate k-1 (quirk Q3).
 __global__ void k_cand_setup(const FragRec* __restrict__ live, DevScalars* sc, IgDescriptor* desc, int n_bounds,
-                             int first_flip_eject) {
+                             int first_flip_eject, const int* __restrict__ cyc_in) {
+    if (cyc_in) {  // cycle mode: this step's {n_cands, fragment, candidates} come from the uploaded cycle plan
+        const int* src = cyc_in + (size_t)sc->step_idx * (2 + IG_MAX_CANDS);
+        if (threadIdx.x < 2 + IG_MAX_CANDS) (&sc->n_cands)[threadIdx.x] = src[threadIdx.x];
+        __syncthreads();
+    }
     // one lane per candidate: pivots and get_bounds in parallel; only the uniq lists chain through the
     // previous candidate's validity list (quirk Q3), which goes through shared memory
     __shared__ int sv[IG_MAX_CANDS + 1][12];
@@ -317,7 +331,7 @@ __global__ void k_cand_setup(const FragRec* __restrict__ live, DevScalars* sc, I
         d.n_uniq = ig_uniq_mutations(A, B, sv[k], (k == 0) ? first_flip_eject : 0, d.uniq);
     }
     if (k < 12) sc->valid[k] = sv[n][k];  // state after the last candidate's get_bounds (CL:1854-1870)
-    if (k == 0) sc->ticket_fin = 0;
+    if (k == 0) { sc->ticket_fin = 0; sc->ticket_post = 0; }
 }
 // K3: cut fragments of get_bounds (KA:2255-2269), all candidates at once; the LAST block to finish a
 //     candidate then evaluates every pivot of its descriptor (one thread).
@@ -1064,7 +1078,8 @@ __global__ void k_post_scalars(DevScalars* sc, const IgDescriptor* __restrict__ 
 }
 __global__ void __launch_bounds__(256)
 k_post(const FragRec* __restrict__ live, int nf, const int* __restrict__ init_prev, const int* __restrict__ init_next,
-       const int* __restrict__ orientable, DevScalars* sc) {
+       const int* __restrict__ orientable, DevScalars* sc, CycleOut* __restrict__ cyc_out, const int* __restrict__ d_nuniq,
+       const int* __restrict__ d_nsub) {
     __shared__ int s_heads;
     __shared__ long long s_len, s_half;
     if (threadIdx.x == 0) { s_heads = 0; s_len = 0; s_half = 0; }
@@ -1109,6 +1124,19 @@ k_post(const FragRec* __restrict__ live, int nf, const int* __restrict__ init_pr
         if (s_heads) atomicAdd(&sc->n_heads, s_heads);
         if (s_len) atomicAdd((unsigned long long*)&sc->sum_l_cont, (unsigned long long)s_len);
         if (s_half) atomicAdd((unsigned long long*)&sc->dist_half, (unsigned long long)s_half);
+        if (cyc_out) {  // cycle mode: the last block to finish publishes this step's record and advances the plan
+            __threadfence();
+            if (atomicAdd(&sc->ticket_post, 1u) == gridDim.x - 1) {
+                __threadfence();
+                CycleOut o;
+                o.likelihood = sc->likelihood; o.lnz_full = sc->lnz_full;
+                o.dist_half = *(volatile long long*)&sc->dist_half; o.sum_l_cont = *(volatile long long*)&sc->sum_l_cont;
+                o.n_heads = *(volatile int*)&sc->n_heads; o.win_cand = sc->win_cand; o.win_op = sc->win_op; o.q4_hits = sc->q4_hits;
+                for (int i = 0; i < IG_MAX_CANDS; i++) { o.n_uniq[i] = d_nuniq[i]; o.n_sub[i] = d_nsub[i]; o.pad[i] = 0; }
+                cyc_out[sc->step_idx] = o;
+                sc->step_idx += 1;
+            }
+        }
     }
 }
 __global__ void k_explode(FragRec* live, int nf, const int* __restrict__ perm) {  // KA:409-426
@@ -1187,7 +1215,8 @@ struct ig_handle {
     double* part_out;
     int gs_div;
     long long last_n_full;
-    cudaGraphExec_t graph[2]; bool graph_failed, capturing, use_graph; long long n_full;
+    cudaGraphExec_t graph[4];
+    int* cyc_in; CycleOut* cyc_out; int cyc_cap; bool graph_failed, capturing, use_graph; long long n_full;
     // measurement (CUDA events on the launching stream)
     cudaEvent_t ev[6];
     cudaEvent_t evk[16]; double ms_k[16];  // per-kernel event timing of the main stream (profiling mode)
@@ -1251,7 +1280,7 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
     h->gs_div = 4;
     if (const char* e = getenv("IG_GS_DIV")) h->gs_div = std::max(1, atoi(e));
     if (const char* e = getenv("IG_BLOCK_MODE")) if (atoi(e)) h->gs_div = -h->gs_div;
-    h->graph[0] = h->graph[1] = nullptr; h->graph_failed = false; h->capturing = false; h->use_graph = true; h->n_full = 0;
+    h->graph[0] = h->graph[1] = h->graph[2] = h->graph[3] = nullptr; h->cyc_in = nullptr; h->cyc_out = nullptr; h->cyc_cap = 0; h->graph_failed = false; h->capturing = false; h->use_graph = true; h->n_full = 0;
     cudaError_t e0 = cudaSetDevice(cfg->device);
     if (e0 != cudaSuccess) { g_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e0); delete h; return -2; }
 #define CKC(x) do { int r_ = (x); if (r_) { g_err = h->err; ig_destroy(h); return r_; } } while (0)
@@ -1359,7 +1388,9 @@ extern "C" void ig_destroy(ig_handle* h) {
     if (h->h_small) cudaFreeHost(h->h_small);
     for (int i = 0; i < 6; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 16; i++) if (h->evk[i]) cudaEventDestroy(h->evk[i]);
-    for (int i = 0; i < 2; i++) if (h->graph[i]) cudaGraphExecDestroy(h->graph[i]);
+    for (int i = 0; i < 4; i++) if (h->graph[i]) cudaGraphExecDestroy(h->graph[i]);
+    if (h->cyc_in) cudaFree(h->cyc_in);
+    if (h->cyc_out) cudaFree(h->cyc_out);
     if (h->side) cudaStreamDestroy(h->side);
     if (h->ev_coords) cudaEventDestroy(h->ev_coords);
     if (h->ev_lnz) cudaEventDestroy(h->ev_lnz);
@@ -1489,7 +1520,7 @@ static int score_candidates(ig_handle* h, int a, const int32_t* cands, int n, in
     for (int i = 0; i < IG_MAX_CANDS; i++) hs[2 + i] = i < n ? cands[i] : 0;
     CK(cudaMemcpyAsync(&h->sc->n_cands, hs, (2 + IG_MAX_CANDS) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     const FragRec* live = h->live;
-    k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, first_flip_eject);
+    k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, first_flip_eject, nullptr);
     k_find_cuts<<<dim3((h->nf + 255) / 256, n), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc);
     if (overlap) cudaStreamWaitEvent(h->stream, h->ev_coords, 0);
     k_rows_count<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks);
@@ -1514,7 +1545,7 @@ static int apply_and_post(ig_handle* h, int forced_cand, int forced_op) {
     const int nf = h->nf;
     k_apply<<<(nf + 255) / 256, 256, 0, h->stream>>>(h->live, nf, h->sc, h->desc, forced_cand, forced_op);
     k_post_scalars<<<1, 1, 0, h->stream>>>(h->sc, h->desc, forced_cand, forced_op);
-    k_post<<<(nf + 255) / 256, 256, 0, h->stream>>>(h->live, nf, h->init_prev, h->init_next, h->orientable, h->sc);
+    k_post<<<(nf + 255) / 256, 256, 0, h->stream>>>(h->live, nf, h->init_prev, h->init_next, h->orientable, h->sc, nullptr, nullptr, nullptr);
     h->coords_fresh = false;
     h->n_launches += 3;
     return launch_ok(h, "apply");
@@ -1548,10 +1579,10 @@ static int fetch_result(ig_handle* h, int n, const int32_t* cands, ig_step_resul
 //             overlapped with the candidate setup on the main stream;
 //   full = 0: incremental refresh from the previous step's mutation table (same values up to f64
 //             summation order), O(rows of the last move).
-static int enqueue_step(ig_handle* h, int full, int n_grid_cands) {
+static int enqueue_step(ig_handle* h, int full, int n_grid_cands, int cycle = 0) {
     const float mbar = h->cfg.mean_sub_len_kb;
     const int n = n_grid_cands;
-    cudaMemcpyAsync(&h->sc->n_cands, h->h_small, (2 + IG_MAX_CANDS) * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    if (!cycle) cudaMemcpyAsync(&h->sc->n_cands, h->h_small, (2 + IG_MAX_CANDS) * sizeof(int), cudaMemcpyHostToDevice, h->stream);
     cudaEventRecord(h->ev_fork, h->stream);
     cudaStreamWaitEvent(h->side, h->ev_fork, 0);
     if (full) {
@@ -1574,7 +1605,7 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands) {
     const FragRec* live = h->live;
 #define IG_MARK(i) do { if (h->profile && !h->capturing) cudaEventRecord(h->evk[i], h->stream); } while (0)
     IG_MARK(0);
-    k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, 1);
+    k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, 1, cycle ? h->cyc_in : nullptr);
     IG_MARK(1);
     k_find_cuts<<<dim3((h->nf + 255) / 256, n), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc);
     cudaStreamWaitEvent(h->stream, h->ev_coords, 0);
@@ -1608,25 +1639,28 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands) {
     IG_MARK(9);
     k_apply<<<(h->nf + 255) / 256, 256, 0, h->stream>>>(h->live, h->nf, h->sc, h->desc, -1, -1);
     IG_MARK(10);
-    k_post<<<(h->nf + 255) / 256, 256, 0, h->stream>>>(h->live, h->nf, h->init_prev, h->init_next, h->orientable, h->sc);
+    k_post<<<(h->nf + 255) / 256, 256, 0, h->stream>>>(h->live, h->nf, h->init_prev, h->init_next, h->orientable, h->sc,
+                                                       cycle ? h->cyc_out : nullptr, h->d_nuniq, h->d_nsub);
     IG_MARK(11);
     cudaStreamWaitEvent(h->stream, h->ev_out, 0);
-    cudaMemcpyAsync(h->h_sc, h->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, h->stream);
-    cudaMemcpyAsync(h->h_small + 16, h->d_nuniq, IG_MAX_CANDS * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
-    cudaMemcpyAsync(h->h_small + 32, h->d_nsub, IG_MAX_CANDS * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (!cycle) {
+        cudaMemcpyAsync(h->h_sc, h->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, h->stream);
+        cudaMemcpyAsync(h->h_small + 16, h->d_nuniq, IG_MAX_CANDS * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+        cudaMemcpyAsync(h->h_small + 32, h->d_nsub, IG_MAX_CANDS * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    }
     return launch_ok(h, "enqueue_step");
 }
 #define IG_LAUNCHES_FULL 14
 #define IG_LAUNCHES_INCR 11
 
-static int get_graph(ig_handle* h, int full, cudaGraphExec_t* out) {
-    cudaGraphExec_t& ge = h->graph[full];
+static int get_graph(ig_handle* h, int full, cudaGraphExec_t* out, int cycle = 0) {
+    cudaGraphExec_t& ge = h->graph[full + 2 * cycle];
     if (!ge && !h->graph_failed) {
         cudaGraph_t g = nullptr;
         h->capturing = true;
         cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
         if (e == cudaSuccess) {
-            enqueue_step(h, full, IG_MAX_CANDS);
+            enqueue_step(h, full, IG_MAX_CANDS, cycle);
             e = cudaStreamEndCapture(h->stream, &g);
         }
         h->capturing = false;
@@ -1678,6 +1712,71 @@ extern "C" int ig_step(ig_handle* h, int32_t id_frag, const int32_t* cands, int3
     return 0;
 }
 
+// A whole MCMC cycle (or any run of steps) enqueued without a single host synchronisation in between:
+// the host uploads the plan {fragment, sorted candidates} of every step (drawn with the reference's own
+// RNG calls, which do not depend on the chain state), every step is one CUDA-graph replay that reads its
+// plan entry and writes a compact record on the device, and the host synchronises once at the end.
+// Semantically identical to n_steps calls of ig_step (IG.full_em inner loop, instagraal.py:217-241).
+extern "C" int ig_run_cycle(ig_handle* h, int32_t n_steps, const int32_t* frags, const int32_t* cands8, const int32_t* n_cands,
+                            ig_cycle_step* out) {
+    if (use(h)) return -1;
+    if (!h->params_set) { h->err = "ig_run_cycle: parameters not set"; return -1; }
+    if (n_steps <= 0) return 0;
+    std::vector<int> plan((size_t)n_steps * (2 + IG_MAX_CANDS), 0);
+    for (int t = 0; t < n_steps; t++) {
+        const int n = n_cands[t];
+        if (n <= 0 || n > IG_MAX_CANDS || frags[t] < 0 || frags[t] >= h->nf) { h->err = "ig_run_cycle: bad plan entry"; return -1; }
+        int* p = &plan[(size_t)t * (2 + IG_MAX_CANDS)];
+        p[0] = n; p[1] = frags[t];
+        for (int i = 0; i < n; i++) {
+            const int c = cands8[(size_t)t * IG_MAX_CANDS + i];
+            if (c < 0 || c >= h->nf) { h->err = "ig_run_cycle: candidate out of range"; return -1; }
+            p[2 + i] = c;
+        }
+    }
+    if (n_steps > h->cyc_cap) {
+        if (h->cyc_in) cudaFree(h->cyc_in);
+        if (h->cyc_out) cudaFree(h->cyc_out);
+        h->cyc_in = nullptr; h->cyc_out = nullptr; h->cyc_cap = 0;
+        for (int i = 2; i < 4; i++) if (h->graph[i]) { cudaGraphExecDestroy(h->graph[i]); h->graph[i] = nullptr; }  // pointers are baked in
+        if (dev_alloc(h, &h->cyc_in, (size_t)n_steps * (2 + IG_MAX_CANDS)) || dev_alloc(h, &h->cyc_out, (size_t)n_steps)) return -2;
+        h->cyc_cap = n_steps;
+    }
+    CK(cudaMemcpyAsync(h->cyc_in, plan.data(), plan.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(&h->sc->step_idx, 0, sizeof(int), h->stream));
+    cudaEventRecord(h->ev[0], h->stream);
+    for (int t = 0; t < n_steps; t++) {
+        const int full = (!h->incr_valid || (h->refresh_every > 0 && h->steps_since_full >= h->refresh_every)) ? 1 : 0;
+        cudaGraphExec_t ge = nullptr;
+        if (h->use_graph) get_graph(h, full, &ge, 1);
+        if (ge) { CK(cudaGraphLaunch(ge, h->stream)); }
+        else if (enqueue_step(h, full, IG_MAX_CANDS, 1)) return -2;
+        h->steps_since_full = full ? 1 : h->steps_since_full + 1;
+        h->n_full += full;
+        h->incr_valid = true;
+        h->n_launches += full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR;
+    }
+    cudaEventRecord(h->ev[1], h->stream);
+    std::vector<CycleOut> res(n_steps);
+    CK(cudaMemcpyAsync(res.data(), h->cyc_out, sizeof(CycleOut) * n_steps, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->coords_fresh = false; h->coords_ever = true;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->ms_step += ms;
+    h->n_steps += n_steps;
+    for (int t = 0; t < n_steps; t++) {
+        const CycleOut& r = res[t];
+        ig_cycle_step& o = out[t];
+        o.likelihood = r.likelihood; o.lnz_full = r.lnz_full;
+        o.dist = (3.0 * h->nf - 0.5 * (double)r.dist_half) / (3.0 * h->nf);
+        o.sum_l_cont = r.sum_l_cont; o.n_contigs = r.n_heads; o.op_sampled = r.win_op; o.cand_index = r.win_cand;
+        o.id_f_sampled = cands8[(size_t)t * IG_MAX_CANDS + r.win_cand];
+        o.q4_hits = r.q4_hits; o.n_proposals = 0;
+        for (int i = 0; i < n_cands[t]; i++) o.n_proposals += r.n_uniq[i];
+    }
+    return 0;
+}
+
 // measurement / parity knobs: refresh_every = N -> recompute the coordinates and the full likelihood
 // over every contact at least every N steps (1 = every step, exactly the reference's schedule;
 // 0 = only when the state was changed from outside); use_graph = replay the step as one CUDA graph.
@@ -1715,7 +1814,7 @@ extern "C" int ig_apply(ig_handle* h, int32_t id_frag, int32_t id_cand, int32_t 
     CK(cudaMemcpyAsync(saved, h->sc->valid, sizeof saved, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     const FragRec* live = h->live;
-    k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, 0);
+    k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, 0, nullptr);
     k_find_cuts<<<dim3((h->nf + 255) / 256, 1), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc);
     // test_copy_struct only re-runs get_bounds for op >= 12 (CL:2121-2126): restore the list otherwise
     CK(cudaMemcpyAsync(h->sc->valid, saved, sizeof saved, cudaMemcpyHostToDevice, h->stream));

@@ -321,6 +321,33 @@ class sampler:
         self.curr_likelihood_on_nz = res.lnz_full
         return (o, res.dist, op_sampled, id_f_sampled, self.mean_length_contigs, self.n_contigs)
 
+    def run_cycle(self, list_frags, n_neighbours=5, candidates=None):
+        """The inner loop of full_em (IG:217-241) for the fragments in ``list_frags`` as ONE library call:
+        candidates are drawn here with the reference's own RNG calls in the reference's order (they do not
+        depend on the chain state), the whole run is enqueued on the GPU without host synchronisation, and
+        the per-step tuples of step_sampler come back as a structured array
+        (likelihood, dist, op_sampled, id_f_sampled, sum_l_cont, n_contigs, n_proposals)."""
+        n = len(list_frags)
+        frags = np.ascontiguousarray(list_frags, dtype=np.int32)
+        c8 = np.zeros((n, L.IG_MAX_CANDS), dtype=np.int32)
+        nc = np.zeros(n, dtype=np.int32)
+        for t in range(n):
+            cs = candidates[t] if candidates is not None else self.return_neighbours(int(frags[t]), n_neighbours)
+            cs = sorted(int(c) for c in cs)
+            nc[t] = len(cs)
+            c8[t, :len(cs)] = cs
+        out = np.zeros(n, dtype=L.CYCLE_DTYPE)
+        assert out.dtype.itemsize == C.sizeof(L.ig_cycle_step)
+        L.check(self._h, L.lib().ig_run_cycle(self._h, n, _ptr(frags), _ptr(c8), _ptr(nc), _ptr(out)), "ig_run_cycle")
+        if n:
+            last = out[-1]
+            self.n_contigs = np.int32(last["n_contigs"])
+            self.mean_length_contigs = np.float32(last["sum_l_cont"]) / np.float32(last["n_contigs"])
+            self.likelihood_t = self.o = np.float64(last["likelihood"])
+            self.n_proposals_scored += int(out["n_proposals"].sum())
+            self.candidates = c8[-1, :nc[-1]].tolist()
+        return out
+
     def eval_likelihood(self):
         """CL:1245-1294: refresh the coordinates and the full non-zero likelihood of the live scaffold."""
         out = np.zeros(3, dtype=np.float64)

@@ -249,3 +249,33 @@ def test_incremental_likelihood_equals_full_recompute(built):
         assert abs(a[0] - b[0]) <= 1e-9 * abs(a[0]), (n_same, a[0], b[0])
         n_same += 1
     assert n_same >= 200, n_same
+
+
+def test_run_cycle_equals_stepwise(built):
+    """ig_run_cycle (whole run enqueued without host synchronisation) == the same steps through ig_step."""
+    from oracle.sampler_oracle import return_neighbours, setup_distri_frags
+    level = make_level(WORKLOADS["toy"])
+    distri = setup_distri_frags(level.sub_sampled_sparse_matrix, level.n_frags)
+    np.random.seed(21)
+    perm = np.random.permutation(level.n_frags).astype(np.int32)
+    frs = np.concatenate([np.random.permutation(level.n_frags) for _ in range(3)])
+    cands = [sorted(return_neighbours(distri, level.n_frags, int(f), 5)) for f in frs]
+    res = []
+    for mode in ("step", "cycle"):
+        s = make_sampler(level)
+        s.set_param_simu(P8)
+        import ctypes as C
+        from instagraal_b200 import _lib as L
+        L.check(s._h, L.lib().ig_bomb(s._h, perm.ctypes.data_as(C.c_void_p)), "ig_bomb")
+        if mode == "step":
+            out = [s.step_sampler(int(f), 5, np.float32(0.01), candidates=c) for f, c in zip(frs, cands)]
+            rec = [(float(o[0]), float(o[1]), int(o[2]), int(o[3]), int(o[5])) for o in out]
+        else:
+            out = s.run_cycle(frs, 5, candidates=cands)
+            rec = [(float(r["likelihood"]), float(r["dist"]), int(r["op_sampled"]), int(r["id_f_sampled"]), int(r["n_contigs"]))
+                   for r in out]
+        res.append((rec, s._get_state(), s.get_valid_insert()))
+        s.free_gpu()
+    assert res[0][0] == res[1][0]
+    assert np.array_equal(res[0][1], res[1][1])
+    assert np.array_equal(res[0][2], res[1][2])
