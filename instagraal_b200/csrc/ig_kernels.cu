@@ -1679,6 +1679,7 @@ extern "C" int ig_step(ig_handle* h, int32_t id_frag, const int32_t* cands, int3
     if (n_cands <= 0 || n_cands > IG_MAX_CANDS) { h->err = "n_cands out of range"; return -1; }
     if (id_frag < 0 || id_frag >= h->nf) { h->err = "id_frag out of range"; return -1; }
     for (int i = 0; i < n_cands; i++) if (cands[i] < 0 || cands[i] >= h->nf) { h->err = "candidate out of range"; return -1; }
+    for (int i = 0; i < n_cands; i++) if (cands[i] == id_frag) { h->err = "candidate equals the visited fragment (reference quirk Q4; see DESIGN.md D1)"; return -1; }
     int* hs = h->h_small;
     hs[0] = n_cands; hs[1] = id_frag;
     for (int i = 0; i < IG_MAX_CANDS; i++) hs[2 + i] = i < n_cands ? cands[i] : 0;
@@ -1730,7 +1731,7 @@ extern "C" int ig_run_cycle(ig_handle* h, int32_t n_steps, const int32_t* frags,
         p[0] = n; p[1] = frags[t];
         for (int i = 0; i < n; i++) {
             const int c = cands8[(size_t)t * IG_MAX_CANDS + i];
-            if (c < 0 || c >= h->nf) { h->err = "ig_run_cycle: candidate out of range"; return -1; }
+            if (c < 0 || c >= h->nf || c == frags[t]) { h->err = "ig_run_cycle: candidate out of range or equal to the visited fragment"; return -1; }
             p[2 + i] = c;
         }
     }

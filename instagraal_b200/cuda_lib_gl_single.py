@@ -297,7 +297,11 @@ class sampler:
         """CL:1401-1465.  ``candidates`` (optional) bypasses the host RNG draw (replay / parity)."""
         if candidates is None:
             candidates = self.return_neighbours(id_frag, n_neighbours)
-        self.candidates = list(candidates)
+        # Deviation D1 (DESIGN.md): a fragment without level-L neighbours gets a uniform draw over ALL
+        # fragments (CL:3124), which can contain the fragment itself; for B == A the reference's
+        # paste_contigs writes nothing (quirk Q4) and stale candidate structs get scored and possibly
+        # applied.  The draw is made as in the reference (same RNG consumption) but B == A is dropped.
+        self.candidates = [c for c in candidates if int(c) != int(id_frag)]
         self.candidates.sort()
         n = len(self.candidates)
         self._cand_buf[:n] = self.candidates
@@ -333,7 +337,7 @@ class sampler:
         nc = np.zeros(n, dtype=np.int32)
         for t in range(n):
             cs = candidates[t] if candidates is not None else self.return_neighbours(int(frags[t]), n_neighbours)
-            cs = sorted(int(c) for c in cs)
+            cs = sorted(int(c) for c in cs if int(c) != int(frags[t]))  # deviation D1, see step_sampler
             nc[t] = len(cs)
             c8[t, :len(cs)] = cs
         out = np.zeros(n, dtype=L.CYCLE_DTYPE)

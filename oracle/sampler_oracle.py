@@ -184,7 +184,7 @@ class OracleSampler:
     def step_sampler(self, id_frag, n_neighbours=5, candidates=None):
         if candidates is None:
             candidates = return_neighbours(self.distri, self.nf, id_frag, n_neighbours)
-        candidates = sorted(candidates)
+        candidates = sorted(c for c in candidates if int(c) != int(id_frag))  # B == A dropped
         self.candidates = candidates
         self.v_cur = sc.fill_vect_dist(self.live, self.sub)
         lnz_full = sc.full_likelihood_nz(self.v_cur, self.coo, self.params, self.mbar)

@@ -279,3 +279,72 @@ def test_run_cycle_equals_stepwise(built):
     assert res[0][0] == res[1][0]
     assert np.array_equal(res[0][1], res[1][1])
     assert np.array_equal(res[0][2], res[1][2])
+
+
+def _lockstep(level, p8, n_steps, seed, bomb=False, n_neigh=5):
+    """product and oracle advance together; after every step the oracle is resynchronised to the
+    product's state (so an exact tie broken differently cannot cascade)."""
+    import oracle.score as sc
+    s = make_sampler(level)
+    s.set_param_simu(p8)
+    o = _oracle(level, p8)
+    np.random.seed(seed)
+    if bomb:
+        s.bomb_the_genome()
+    o.live = {k: s._get_state()[i].copy() for i, k in enumerate(FIELDS13)}
+    o.valid = [int(x) for x in s.get_valid_insert()]
+    frs = np.concatenate([np.random.permutation(level.n_frags) for _ in range(1 + n_steps // level.n_frags)])[:n_steps]
+    ties = 0
+    for f in frs:
+        cands = sorted(int(c) for c in s.return_neighbours(int(f), n_neigh) if int(c) != int(f))
+        if not cands:
+            continue
+        r = s.step_sampler(int(f), n_neigh, np.float32(0.01), candidates=cands)
+        ro = o.step_sampler(int(f), n_neigh, candidates=cands)
+        want, got = o.all_scores, s.all_scores
+        assert np.array_equal(want != 0, got != 0), (f, cands)
+        nz = want != 0
+        tol = 1e-5 * np.abs(want[nz] - want[nz].max()) + 2e-8 * np.abs(want[nz]) + 1e-9
+        assert np.all(np.abs(got[nz] - want[nz]) <= tol), (f, cands, float(np.max(np.abs(got[nz] - want[nz]))))
+        st = s._get_state()
+        if (int(r[2]), int(r[3])) == (int(ro[2]), int(ro[3])):
+            for i, k in enumerate(FIELDS13):
+                assert np.array_equal(st[i], o.live[k]), (f, k)
+            assert float(r[1]) == float(ro[1]) and int(r[5]) == int(ro[5])
+        else:
+            gid_s = cands.index(int(r[3])) * 24 + int(r[2])
+            gid_o = cands.index(int(ro[3])) * 24 + int(ro[2])
+            assert abs(want[gid_s] - want[gid_o]) <= 2e-8 * abs(want[gid_o]) + 1e-9, "diverged without a tie"
+            ties += 1
+            o.live = {k: st[i].copy() for i, k in enumerate(FIELDS13)}
+        o.valid = [int(x) for x in s.get_valid_insert()]
+    s.free_gpu()
+    return ties
+
+
+def test_edge_tiny_level_down_to_one_contig(built):
+    """12 fragments / 34 sub-fragments: ragged sub-fragment counts, windowed same-contig slices, slices
+    shorter than one 64-contact block, everything merging into a single contig."""
+    level = make_level(SynthSpec(n_frags=12, n_contigs=3, n_chrom=1, max_offset=10, lambda1=5.0, trans_per_row=0.5, seed=3))
+    ties = _lockstep(level, P8, 60, seed=0)
+    assert ties <= 30
+
+
+def test_edge_isolated_fragments_and_single_candidate(built):
+    """fragments without any contact (empty CSR rows, no level-L neighbour => uniform candidate draw) and
+    steps with a single candidate."""
+    import scipy.sparse as sp
+    level = make_level(SynthSpec(n_frags=30, n_contigs=4, n_chrom=2, max_offset=30, lambda1=8.0, trans_per_row=1.0, seed=9))
+    # wipe every contact of fragments 0 and 7 (their sub-fragment rows and columns)
+    parent = level.np_sub_frags_2_frags["x"].astype(np.int64)
+    kill = np.isin(parent, [0, 7])
+    m = level.sparse_matrix.tocoo()
+    keep = ~(kill[m.row] | kill[m.col])
+    level.sparse_matrix = sp.csr_matrix((m.data[keep], (m.row[keep], m.col[keep])), shape=m.shape, dtype=np.int32)
+    mm = level.sub_sampled_sparse_matrix.tocoo()
+    keep2 = ~(np.isin(mm.row, [0, 7]) | np.isin(mm.col, [0, 7]))
+    level.sub_sampled_sparse_matrix = sp.csr_matrix((mm.data[keep2], (mm.row[keep2], mm.col[keep2])), shape=mm.shape, dtype=np.int32)
+    ties = _lockstep(level, P8, 70, seed=4, bomb=True)
+    assert ties <= 35
+    ties = _lockstep(level, P8, 40, seed=5, n_neigh=1)
+    assert ties <= 20
