@@ -119,6 +119,10 @@ int ig_full_likelihood(ig_handle* h, const float p[8], int32_t use_stale_coords,
 int ig_distance_histogram(ig_handle* h, double bin_kb, double max_kb, int32_t n_rows, int32_t n_bins,
                           int64_t* hist, int64_t* rows_used);
 
+/* display_current_matrix (CL:2555-2606) without densifying NS x NS on the host: K x K binned contact counts
+ * in the displayed order given by sub_rank[NS] */
+int ig_contact_thumbnail(ig_handle* h, const int32_t* sub_rank, int32_t K, uint32_t* out);
+
 /* diagonal of (M + M^T) at level L-1 (self contacts): only the p(s) histogram sees it (CL:2257-2288) */
 int ig_set_sym_diag(ig_handle* h, const int32_t* diag);
 

@@ -1180,6 +1180,24 @@ k_histogram(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, 
     }
 }
 
+// N1: K x K thumbnail of the contact map in the CURRENT scaffold order, binned on the
+// device (the reference densifies NS x NS on the host, CL:2598-2599).  Integer counts => exact.
+__global__ void __launch_bounds__(IG_THREADS)
+k_thumbnail(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, const int* __restrict__ sub_rank, int ns, int K,
+            unsigned int* __restrict__ img) {
+    const int lane = threadIdx.x & 31;
+    const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int r = wg; r < ns; r += nw) {
+        const int pi = (int)(((long long)sub_rank[r] * K) / ns);
+        for (long long q = row_ptr[r] + lane; q < row_ptr[r + 1]; q += 32) {
+            const int2 c = cv[q];
+            const int pj = (int)(((long long)sub_rank[c.x] * K) / ns);
+            atomicAdd(&img[(size_t)pi * K + pj], (unsigned int)c.y);
+            if (pi != pj) atomicAdd(&img[(size_t)pj * K + pi], (unsigned int)c.y);
+        }
+    }
+}
+
 // ================================================================================================
 // host side
 struct ig_handle {
@@ -1919,5 +1937,23 @@ extern "C" int ig_get_full_refresh_count(ig_handle* h, int64_t* out) {
 extern "C" int ig_get_kernel_times(ig_handle* h, double out11[11], int32_t reset) {
     if (!h) return -1;
     for (int i = 0; i < 11; i++) { out11[i] = h->ms_k[i]; if (reset) h->ms_k[i] = 0.0; }
+    return 0;
+}
+
+// display_current_matrix (CL:2555-2606) without the NS x NS host densification: sub_rank[s] = position of
+// sub-fragment s in the displayed order (computed by the caller from ig_get_state like CL:2563-2585);
+// out = K*K uint32 symmetric binned contact counts of the strict upper triangle.
+extern "C" int ig_contact_thumbnail(ig_handle* h, const int32_t* sub_rank, int32_t K, uint32_t* out) {
+    if (use(h)) return -1;
+    if (K <= 0 || K > 8192) { h->err = "ig_contact_thumbnail: K out of range"; return -1; }
+    int* d_rank = nullptr; unsigned int* d_img = nullptr;
+    if (dev_alloc(h, &d_rank, h->ns) || dev_alloc(h, &d_img, (size_t)K * K)) return -2;
+    CK(cudaMemcpyAsync(d_rank, sub_rank, sizeof(int) * h->ns, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(d_img, 0, sizeof(unsigned int) * (size_t)K * K, h->stream));
+    k_thumbnail<<<h->n_part_full, IG_THREADS, 0, h->stream>>>(h->row_ptr, h->cv, d_rank, h->ns, K, d_img);
+    if (launch_ok(h, "thumbnail")) return -2;
+    CK(cudaMemcpyAsync(out, d_img, sizeof(unsigned int) * (size_t)K * K, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(d_rank); cudaFree(d_img);
     return 0;
 }

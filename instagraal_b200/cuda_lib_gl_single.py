@@ -244,6 +244,39 @@ class sampler:
         d["full_refreshes"] = int(nf.value)
         return d
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def save_checkpoint(self, path):
+        """Everything an MCMC run needs to continue bit-identically: the 13 live scaffold arrays, the
+        carried list_valid_insert (quirk Q3), the parameters, likelihood_t and the host RNG state.  The
+        reference cannot resume a run.  Saving re-synchronises the incremental
+        likelihood state (one full refresh on the next step) so that the continued and the resumed run
+        perform identical arithmetic."""
+        st = self._get_state()
+        valid = self.get_valid_insert()
+        self._set_state(st)
+        self.set_valid_insert(valid)
+        rs = np.random.get_state()
+        np.savez(path, state13=st, valid=valid,
+                 params8=np.array(list(self.param_simu[0]), dtype=np.float32) if self.param_simu is not None else np.zeros(0, np.float32),
+                 likelihood_t=np.float64(self.likelihood_t if self.likelihood_t is not None else np.nan),
+                 mean_value_trans=np.float64(self.mean_value_trans), n_proposals_scored=np.int64(self.n_proposals_scored),
+                 rng_name=np.array(rs[0]), rng_keys=rs[1], rng_pos=np.int64(rs[2]), rng_has_gauss=np.int64(rs[3]),
+                 rng_cached=np.float64(rs[4]))
+
+    def load_checkpoint(self, path):
+        z = np.load(path if str(path).endswith(".npz") else str(path) + ".npz", allow_pickle=False)
+        self._set_state(z["state13"])
+        self.set_valid_insert(z["valid"])
+        if z["params8"].size == 8:
+            self.set_param_simu(z["params8"])
+            self.param_simu_test = self.param_simu
+        lt = float(z["likelihood_t"])
+        self.likelihood_t = None if np.isnan(lt) else np.float64(lt)
+        self.mean_value_trans = float(z["mean_value_trans"])
+        self.n_proposals_scored = int(z["n_proposals_scored"])
+        np.random.set_state((str(z["rng_name"]), z["rng_keys"], int(z["rng_pos"]), int(z["rng_has_gauss"]), float(z["rng_cached"])))
+        self.gpu_vect_frags.copy_from_gpu()
+
     def free_gpu(self):
         if self._h is not None:
             L.lib().ig_destroy(self._h)
@@ -509,6 +542,51 @@ class sampler:
         """CL:665-716 is computed on the device inside every step; this returns it for the live state."""
         raise NotImplementedError("dist is returned by step_sampler / test_copy_struct")
 
-    def display_current_matrix(self, filename):
-        """CL:2555-2606 (densifies NS x NS on the host; SURVEY 'next' row N1 -- not on the hot path)."""
-        raise NotImplementedError("display_current_matrix is outside the accelerated path (SURVEY section 8f, N1)")
+    def display_order(self):
+        """CL:2556-2585: (full_order, dict_contig, full_order_high) -- fragments / sub-fragments in displayed
+        order: contigs by ascending id, fragments by position, sub-fragments reversed when ori == -1."""
+        self.gpu_vect_frags.copy_from_gpu()
+        c = self.gpu_vect_frags
+        order = np.lexsort((c.pos, c.id_c))                       # by contig id, then position
+        full_order = c.id_d[order]
+        dict_contig = {int(k): full_order[c.id_c[order] == k].tolist() for k in np.unique(c.id_c)}
+        ids = self.np_sub_frags_id
+        high = []
+        for i in full_order:
+            v = [int(ids[i]["x"]), int(ids[i]["y"]), int(ids[i]["z"])][: int(ids[i]["w"])]
+            if c.ori[i] == -1:
+                v.reverse()
+            high.extend(v)
+        return full_order.tolist(), dict_contig, high
+
+    def contact_thumbnail(self, size=1024):
+        """K x K binned contact map in the current scaffold order, computed on the GPU."""
+        _fo, _dc, high = self.display_order()
+        rank = np.empty(int(self.init_n_sub_frags), dtype=np.int32)
+        rank[np.asarray(high, dtype=np.int64)] = np.arange(len(high), dtype=np.int32)
+        img = np.zeros((size, size), dtype=np.uint32)
+        L.check(self._h, L.lib().ig_contact_thumbnail(self._h, _ptr(rank), int(size), _ptr(img)), "ig_contact_thumbnail")
+        return img
+
+    def display_current_matrix(self, filename, size=1024):
+        """CL:2555-2606.  The reference densifies the NS x NS matrix on the host (impossible at 1 Gb scale);
+        here a size x size thumbnail is binned on the GPU and written as PNG when matplotlib is available,
+        else as a binary PGM (8-bit, 99th-percentile scaling like the reference's vmax)."""
+        full_order, dict_contig, full_order_high = self.display_order()
+        img = self.contact_thumbnail(size).astype(np.float64)
+        vmax = max(np.percentile(img, 99), 1.0)
+        try:
+            import matplotlib
+            matplotlib.use("Agg")
+            import matplotlib.pyplot as plt
+            fig, ax = plt.subplots(figsize=(14, 14))
+            ax.imshow(img, vmax=vmax, interpolation="nearest")
+            ax.axis("off")
+            fig.savefig(filename, dpi=200, bbox_inches="tight")
+            plt.close(fig)
+        except ImportError:
+            g = np.clip(img / vmax * 255.0, 0, 255).astype(np.uint8)
+            with open(filename, "wb") as fh:
+                fh.write(b"P5\n%d %d\n255\n" % (size, size))
+                fh.write(g.tobytes())
+        return full_order, dict_contig, full_order_high

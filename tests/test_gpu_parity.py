@@ -348,3 +348,67 @@ def test_edge_isolated_fragments_and_single_candidate(built):
     assert ties <= 35
     ties = _lockstep(level, P8, 40, seed=5, n_neigh=1)
     assert ties <= 20
+
+
+def test_checkpoint_resume_is_bit_identical(built, tmp_path):
+    """N3: stop after 150 steps, resume in a NEW sampler, and the next 150 steps (incl. the
+    host RNG draws) equal the uninterrupted run's."""
+    level = make_level(WORKLOADS["toy"])
+
+    def steps(s, n):
+        out = []
+        frs = np.arange(level.n_frags)
+        while len(out) < n:
+            np.random.shuffle(frs)
+            for f in frs:
+                r = s.step_sampler(int(f), 5, np.float32(0.01))
+                out.append((float(r[0]), float(r[1]), int(r[2]), int(r[3]), int(r[5])))
+                if len(out) == n:
+                    break
+        return out
+
+    a = make_sampler(level)
+    a.set_param_simu(P8)
+    np.random.seed(33)
+    a.bomb_the_genome()
+    steps(a, 150)
+    ck = str(tmp_path / "chain.npz")
+    a.save_checkpoint(ck)
+    cont = steps(a, 150)
+    final_a = a._get_state()
+    a.free_gpu()
+    b = make_sampler(level)
+    np.random.seed(999)  # must be overwritten by the checkpoint
+    b.load_checkpoint(ck)
+    res = steps(b, 150)
+    assert res == cont
+    assert np.array_equal(b._get_state(), final_a)
+    b.free_gpu()
+
+
+def test_contact_thumbnail_matches_numpy_binning(built, tmp_path):
+    """N1: GPU-binned K x K contact map in the current scaffold order == NumPy binning."""
+    from oracle.sampler_oracle import upper_coo
+    level = make_level(WORKLOADS["toy"])
+    s = make_sampler(level)
+    s.set_param_simu(P8)
+    np.random.seed(2)
+    s.bomb_the_genome()
+    for f in np.random.permutation(level.n_frags)[:120]:
+        s.step_sampler(int(f), 5, np.float32(0.01))
+    K = 64
+    img = s.contact_thumbnail(K)
+    _fo, _dc, high = s.display_order()
+    assert sorted(high) == list(range(level.n_sub_frags))
+    rank = np.empty(level.n_sub_frags, dtype=np.int64)
+    rank[np.asarray(high)] = np.arange(len(high))
+    rows, cols, dat = upper_coo(level.sparse_matrix)
+    pi, pj = rank[rows] * K // level.n_sub_frags, rank[cols] * K // level.n_sub_frags
+    want = np.zeros((K, K), dtype=np.int64)
+    np.add.at(want, (pi, pj), dat)
+    off = pi != pj
+    np.add.at(want, (pj[off], pi[off]), dat[off])
+    assert np.array_equal(img.astype(np.int64), want)
+    out = s.display_current_matrix(str(tmp_path / "m.pgm"), size=K)
+    assert len(out[0]) == level.n_frags and (tmp_path / "m.pgm").stat().st_size > K * K
+    s.free_gpu()
