@@ -33,7 +33,12 @@ typedef struct ig_config {
     double n_pix;              /* n_pixl_sub_mat, CL:366 (caller reproduces the int32 wrap, quirk Q8) */
     int32_t compat_last_block; /* 1: reproduce the last-64-contact-block quirk of eval_sub_likelihood
                                   (kernel_sparse_adapt.cu:4362); 0: sum every contact */
-    int32_t reserved;
+    int32_t rigid_pruning;     /* 0 (default): every (contact, mutation) whose coordinates are not bit-identical to
+                                  the current state is re-evaluated, reproducing the reference's float32
+                                  re-rounding of shifted coordinates (fill_vect_dist, kernel_sparse_adapt.cu:3751);
+                                  1: contacts whose two ends undergo the same rigid motion are skipped (their
+                                  term cannot change mathematically) -- faster on long contigs, scores differ
+                                  from the reference by that rounding noise */
 } ig_config;
 
 typedef struct ig_level_data {

@@ -28,7 +28,7 @@ EXPORTS = (
 class ig_config(C.Structure):
     _fields_ = [("device", C.c_int32), ("n_frags", C.c_int32), ("n_sub_frags", C.c_int32), ("nnz", C.c_int64),
                 ("max_bounds_insert", C.c_int32), ("mean_sub_len_kb", C.c_float), ("n_pix", C.c_double),
-                ("compat_last_block", C.c_int32), ("reserved", C.c_int32)]
+                ("compat_last_block", C.c_int32), ("rigid_pruning", C.c_int32)]
 
 
 class ig_level_data(C.Structure):

@@ -36,6 +36,8 @@
 struct Params { float kuhn, lm, c1, slope, d, d_max, fact, v_inter; };  // KA:91-100
 struct SubRec { int parent; float watson; float crick; int j; };          // 16 B
 struct CoordRec { float dist; int id_c; int pos; float s_tot; };          // 16 B (uni_fill_vect_dist)
+struct __align__(16) SubX { int start_bp; int len_ori; float watson; float crick; };  // 16 B: what a rigid motion needs to
+                                                                          // recompute a sub-fragment's coordinate (len_ori = len_bp * ori)
 
 struct CandInfo {  // per-candidate slice description (slice_sp_mat prologue, KA:526-551)
     int id_a, id_b, same, is_circ;
@@ -203,7 +205,7 @@ __device__ __forceinline__ double block_sum(double v, double* sm /* >= 32 */) {
 __global__ void __launch_bounds__(IG_THREADS)
 k_coords(const FragRec* __restrict__ live, const SubRec* __restrict__ sub, CoordRec* __restrict__ coord,
          int* __restrict__ clen, int ns, const DevScalars* __restrict__ sc, float mbar, int use_test,
-         double* __restrict__ part_z, int* __restrict__ part_n, int write_coords) {
+         double* __restrict__ part_z, int* __restrict__ part_n, int write_coords, SubX* __restrict__ subx) {
     __shared__ double sm[32];
     __shared__ int sn;
     const Params p = use_test ? sc->p_test : sc->p;
@@ -218,6 +220,8 @@ k_coords(const FragRec* __restrict__ live, const SubRec* __restrict__ sub, Coord
             Frag f = live[s.parent].f;
             c = coords_of(f, s, &len);
             coord[r] = c; clen[r] = len;
+            SubX x; x.start_bp = f.start_bp; x.len_ori = f.len_bp * f.ori; x.watson = s.watson; x.crick = s.crick;
+            subx[r] = x;
         } else { c = coord[r]; len = clen[r]; }
         if (c.pos == 0) nloc += intra_pairs(len);
         z += zero_term(c.pos, len, c.s_tot, p, mbar);
@@ -336,7 +340,7 @@ __global__ void k_cand_setup(const FragRec* __restrict__ live, DevScalars* sc, I
 // K3: cut fragments of get_bounds (KA:2255-2269), all candidates at once; the LAST block to finish a
 //     candidate then evaluates every pivot of its descriptor (one thread).
 __global__ void __launch_bounds__(256)
-k_find_cuts(const FragRec* __restrict__ live, int nf, DevScalars* sc, IgDescriptor* desc) {
+k_find_cuts(const FragRec* __restrict__ live, int nf, DevScalars* sc, IgDescriptor* desc, IgClassTab* __restrict__ clstab) {
     const int k = blockIdx.y;
     if (k >= sc->n_cands) return;
     __shared__ int is_last;
@@ -356,9 +360,74 @@ k_find_cuts(const FragRec* __restrict__ live, int nf, DevScalars* sc, IgDescript
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(&sc->ticket_cuts[k], 1u) == gridDim.x - 1);
     __syncthreads();
-    if (is_last && threadIdx.x < 32) {
+    if (!is_last) return;
+    if (threadIdx.x < 32) {
         __threadfence();
         ig_build_descriptor_part(desc[k], [&](int j) { return live[j].f; }, threadIdx.x);
+    }
+    __syncthreads();
+    // breakpoints of the rigid-motion classes (ig_moves.cuh): k_rows_write classifies the rows with them
+    if (threadIdx.x == 0) {
+        IgClassTab& ct = clstab[k];
+        int bpf[IG_MAX_BP + 2], bps[IG_MAX_BP], bpbs[2];
+        ig_class_breakpoints(d, bpf, bps, bpf + IG_MAX_BP, bpbs);
+        for (int j = 0; j < IG_MAX_BP; j++) ct.bp_sub[j] = bps[j];
+        ct.bp_sub_b[0] = bpbs[0]; ct.bp_sub_b[1] = bpbs[1];
+        ct.distinct_b = d.A.id_c != d.B.id_c; ct.id_b = d.B.id_c;
+    }
+}
+
+// K4: rigid-motion classes of each candidate (ig_moves.cuh): one motion per (class, uniq slot) from a class
+//     representative, then the class-pair bit table read by k_score.  One block per candidate, on the side
+//     stream (only k_score needs the result).
+__global__ void __launch_bounds__(256)
+k_classes(const DevScalars* __restrict__ sc, const IgDescriptor* __restrict__ desc, IgClassTab* __restrict__ clstab, int rigid) {
+    const int k = blockIdx.x;
+    if (k >= sc->n_cands) return;
+    __shared__ IgDescriptor d;
+    __shared__ int s_bpf[IG_MAX_BP + 2], s_have[IG_MAX_CLS];
+    __shared__ IgSig s_sig[IG_MAX_CLS][IG_N_OPS];
+    {
+        const int* src = reinterpret_cast<const int*>(desc + k);
+        int* dst = reinterpret_cast<int*>(&d);
+        for (int i = threadIdx.x; i < (int)(sizeof(IgDescriptor) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    if (threadIdx.x < IG_MAX_CLS) s_have[threadIdx.x] = 0;
+    __syncthreads();
+    IgClassTab& ct = clstab[k];
+    if (threadIdx.x == 0) {
+        int bps[IG_MAX_BP], bpbs[2];
+        ig_class_breakpoints(d, s_bpf, bps, s_bpf + IG_MAX_BP, bpbs);
+    }
+    __syncthreads();
+    const int n_uniq = d.n_uniq;
+    {   // one uniq slot per warp pass (lanes = class representatives): no divergence between ops
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        int on_b = 0;
+        const int pos = lane < IG_MAX_CLS ? ig_class_rep_pos(d, s_bpf, s_bpf + IG_MAX_BP, lane, &on_b) : -1;
+        const int cls = pos < 0 ? -1 : (on_b ? IG_CLS_B0 + ig_class_count(s_bpf + IG_MAX_BP, 2, pos) : ig_class_count(s_bpf, IG_MAX_BP, pos));
+        if (w == 0 && cls >= 0) s_have[cls] = 1;
+        for (int u = w; u < n_uniq; u += (int)(blockDim.x >> 5)) {
+            if (cls < 0) continue;
+            const IgSig g = ig_class_signature(d, on_b, pos, d.uniq[u]);   // representatives of one class agree
+            s_sig[cls][u] = g;
+            IgMotion mo; mo.dbp = g.dbp; mo.dsp = g.dsp; mo.id_c = g.id_c; mo.flip = g.flip;
+            ct.mot[cls * IG_N_OPS + u] = mo;
+        }
+    }
+    __syncthreads();
+    const int circ_a = d.A.circ, circ_b = d.B.circ;
+    for (int t = threadIdx.x; t < IG_MAX_CLS * IG_MAX_CLS; t += blockDim.x) {
+        const int c1 = t / IG_MAX_CLS, c2 = t - c1 * IG_MAX_CLS;
+        unsigned m = 0xffffffu;
+        if (s_have[c1] && s_have[c2]) {
+            m = 0;
+            const int cur_same = (c1 >= IG_CLS_B0) == (c2 >= IG_CLS_B0);
+            const int cur_circ = c1 >= IG_CLS_B0 ? circ_b : circ_a;
+            for (int u = 0; u < n_uniq; u++)
+                if (ig_class_pair_changed(s_sig[c1][u], s_sig[c2][u], cur_same, cur_circ, rigid)) m |= 1u << u;
+        }
+        ct.mask[t] = m;
     }
 }
 
@@ -411,12 +480,17 @@ k_rows_count(const CoordRec* __restrict__ coord, int ns, DevScalars* sc, int* __
 }
 __global__ void __launch_bounds__(IG_ROW_CHUNK)
 k_rows_write(const CoordRec* __restrict__ coord, int ns, const DevScalars* __restrict__ sc, const int* __restrict__ chunk_off,
-             int n_chunks, int* __restrict__ rows, int* __restrict__ rowidx, int* __restrict__ row_cnt, int rows_stride) {
+             int n_chunks, int* __restrict__ rows, int* __restrict__ rowidx, int* __restrict__ row_cnt, int rows_stride,
+             const IgClassTab* __restrict__ clstab) {
     const int k = blockIdx.y;
     if (k >= sc->n_cands) return;
     __shared__ int wsum[32];
+    __shared__ int s_bp[IG_MAX_BP + 4];
+    if (threadIdx.x < IG_MAX_BP + 4) s_bp[threadIdx.x] = reinterpret_cast<const int*>(clstab + k)[threadIdx.x];  // bp_sub, bp_sub_b, distinct_b, id_b
     const int r = blockIdx.x * IG_ROW_CHUNK + threadIdx.x;
-    const bool f = r < ns && row_affected(coord[r], sc->ci[k]);
+    CoordRec cr;
+    if (r < ns) cr = coord[r];
+    const bool f = r < ns && row_affected(cr, sc->ci[k]);
     const unsigned b = __ballot_sync(0xffffffffu, f);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (lane == 0) wsum[w] = __popc(b);
@@ -431,7 +505,8 @@ k_rows_write(const CoordRec* __restrict__ coord, int ns, const DevScalars* __res
     if (f) {
         const int off = chunk_off[k * n_chunks + blockIdx.x] + (w ? wsum[w - 1] : 0) + __popc(b & ((1u << lane) - 1));
         rows[(size_t)k * rows_stride + off] = r;
-        rowidx[(size_t)k * rows_stride + r] = off;
+        const int cls = ig_class_of(s_bp, s_bp + IG_MAX_BP, s_bp[IG_MAX_BP + 2], s_bp[IG_MAX_BP + 3], cr.id_c, cr.pos);
+        rowidx[(size_t)k * rows_stride + r] = off | (cls << IG_CLS_SHIFT);
         row_cnt[(size_t)k * rows_stride + off] = 0;  // k_score (block mode) accumulates into it
     }
 }
@@ -457,7 +532,7 @@ struct RowMut { float dist; int id_c; int pos; float s_tot; };  // one sub-fragm
 // K8a: mutated coordinates of every affected sub-fragment under every scored mutation, evaluated
 //      ONCE per (row, mutation) (replaces fill_vect_dist x24, KA:3699-3760) + the zero terms
 //      (eval_all_likelihood_on_zero_1st, KA:3919-4002) restricted to the affected contigs.
-//      Warp per affected row, lane u = uniq slot u, lane 24 = current state.
+//      Block per tile of 32 affected rows (lane = row), warp w = uniq slots w, w+8, w+16 (+ the current state).
 __global__ void __launch_bounds__(IG_THREADS)
 k_precompute(const CoordRec* __restrict__ coord, const int* __restrict__ clen, const FragRec* __restrict__ live,
              const SubRec* __restrict__ sub, const DevScalars* __restrict__ sc, const IgDescriptor* __restrict__ desc_g,
@@ -466,52 +541,83 @@ k_precompute(const CoordRec* __restrict__ coord, const int* __restrict__ clen, c
              int* __restrict__ part_i)     // [cand][25][gridDim.x]
 {
     const int k = blockIdx.y;
+    const int n_rows = sc->ci[k].n_rows;
     if (k >= sc->n_cands) return;
+    if ((int)blockIdx.x * 32 >= n_rows) {   // no tile for this block
+        if (threadIdx.x < 25) {
+            part_z[PART_IDX(k, 25, threadIdx.x, gridDim.x, blockIdx.x)] = 0.0;
+            part_i[PART_IDX(k, 25, threadIdx.x, gridDim.x, blockIdx.x)] = 0;
+        }
+        return;
+    }
     __shared__ IgDescriptor d;
-    __shared__ double red[IG_WARPS_PER_BLOCK][25];
-    __shared__ int redi[IG_WARPS_PER_BLOCK][25];
+    __shared__ double red[IG_WARPS_PER_BLOCK][4];   // warp w owns slots w, w + 8, w + 16 (and 24 = current state for w = 0)
+    __shared__ int redi[IG_WARPS_PER_BLOCK][4];
     {
         const int* src = reinterpret_cast<const int*>(desc_g + k);
         int* dst = reinterpret_cast<int*>(&d);
         for (int i = threadIdx.x; i < (int)(sizeof(IgDescriptor) / 4); i += blockDim.x) dst[i] = src[i];
     }
+    if (threadIdx.x < IG_WARPS_PER_BLOCK * 4) { (&red[0][0])[threadIdx.x] = 0.0; (&redi[0][0])[threadIdx.x] = 0; }
     __syncthreads();
     const Params p = sc->p;
-    const int n_rows = sc->ci[k].n_rows;
     const int n_uniq = d.n_uniq;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int wg = blockIdx.x * IG_WARPS_PER_BLOCK + w, nw = gridDim.x * IG_WARPS_PER_BLOCK;
     const int* my_rows = rows + (size_t)k * ns;
-    const int my_op = lane < n_uniq ? d.uniq[lane] : -1;
-    double zacc = 0.0;
-    int iacc = 0;
-    for (int ri = wg; ri < n_rows; ri += nw) {
-        const int r = my_rows[ri];
-        const SubRec si = sub[r];
-        if (my_op >= 0) {
-            const Frag fi = live[si.parent].f;
-            const Frag fm = ig_eval_op(d, my_op, fi, si.parent);
-            int len;
-            const CoordRec c = coords_of(fm, si, &len);
-            RowMut m; m.dist = c.dist; m.id_c = c.id_c; m.pos = c.pos; m.s_tot = c.s_tot;
-            const size_t ti = ((size_t)k * IG_N_OPS + lane) * ns + ri;
-            table[ti] = m; table_len[ti] = len;
-            if (c.pos == 0) iacc += intra_pairs(len);
-            zacc += zero_term(c.pos, len, c.s_tot, p, mbar);
-        } else if (lane == IG_LANE_CUR) {
-            const CoordRec ci = coord[r];
-            const int len = clen[r];
-            if (ci.pos == 0) iacc += intra_pairs(len);
-            zacc += zero_term(ci.pos, len, ci.s_tot, p, mbar);
+    // a block takes tiles of 32 rows (lane = row); each warp evaluates ITS slots for the tile, so the op is
+    // warp-uniform (no divergence between the 24 move functions) and the table writes are coalesced
+    for (int tile = blockIdx.x; tile * 32 < n_rows; tile += gridDim.x) {
+        const int ri = tile * 32 + lane;
+        const bool valid = ri < n_rows;
+        const int r = valid ? my_rows[ri] : 0;
+        SubRec si = {0, 0.f, 0.f, 0};
+        Frag fi = d.A;
+        if (valid) { si = sub[r]; fi = live[si.parent].f; }
+#pragma unroll 1
+        for (int j = 0; j < 4; j++) {
+            const int slot = w + IG_WARPS_PER_BLOCK * j;
+            if (slot > 24 || (slot >= n_uniq && slot != 24)) continue;
+            double z = 0.0;
+            int ia = 0;
+            if (valid) {
+                if (slot < 24) {
+                    const Frag fm = ig_eval_op(d, d.uniq[slot], fi, si.parent);
+                    int len;
+                    const CoordRec c = coords_of(fm, si, &len);
+                    RowMut m; m.dist = c.dist; m.id_c = c.id_c; m.pos = c.pos; m.s_tot = c.s_tot;
+                    const size_t ti = ((size_t)k * IG_N_OPS + slot) * ns + ri;
+                    table[ti] = m; table_len[ti] = len;
+                    if (c.pos == 0) ia = intra_pairs(len);
+                    z = zero_term(c.pos, len, c.s_tot, p, mbar);
+                } else {
+                    const CoordRec ci = coord[r];
+                    const int len = clen[r];
+                    if (ci.pos == 0) ia = intra_pairs(len);
+                    z = zero_term(ci.pos, len, ci.s_tot, p, mbar);
+                }
+            }
+            z = warp_sum(z);
+            ia = __reduce_add_sync(0xffffffffu, ia);
+            if (lane == 0) { red[w][j] += z; redi[w][j] += ia; }   // tiles are visited in a fixed order
         }
     }
-    if (lane < 25) { red[w][lane] = zacc; redi[w][lane] = iacc; }
     __syncthreads();
     if (threadIdx.x < 25) {
-        double v = 0.0; int iv = 0;
-        for (int ww = 0; ww < IG_WARPS_PER_BLOCK; ww++) { v += red[ww][threadIdx.x]; iv += redi[ww][threadIdx.x]; }
-        part_z[PART_IDX(k, 25, threadIdx.x, gridDim.x, blockIdx.x)] = v;
-        part_i[PART_IDX(k, 25, threadIdx.x, gridDim.x, blockIdx.x)] = iv;
+        const int ww = threadIdx.x % IG_WARPS_PER_BLOCK, j = threadIdx.x / IG_WARPS_PER_BLOCK;
+        part_z[PART_IDX(k, 25, threadIdx.x, gridDim.x, blockIdx.x)] = red[ww][j];
+        part_i[PART_IDX(k, 25, threadIdx.x, gridDim.x, blockIdx.x)] = redi[ww][j];
+    }
+}
+
+// L2 prefetch of the level's arrays at the start of a step, when they fit the L2 comfortably (yeast-scale
+// levels): a step is a chain of a dozen short dependent kernels, each of which would otherwise take its
+// first-touch misses to HBM one latency at a time.  Runs beside the candidate setup on its own stream.
+struct PfList { const char* p[12]; unsigned long long n[12]; int cnt; };
+__global__ void k_prefetch_l2(PfList L) {
+    for (int a = 0; a < L.cnt; a++) {
+        const unsigned long long lines = (L.n[a] + 127ull) >> 7;
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < lines; i += (unsigned long long)gridDim.x * blockDim.x)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(L.p[a] + (i << 7)));
     }
 }
 
@@ -534,9 +640,12 @@ k_precompute(const CoordRec* __restrict__ coord, const int* __restrict__ clen, c
 // QUEUED per warp in shared memory and executed 32 at a time with all lanes busy; the result is
 // added to the executing lane's accumulator (only the sum over lanes matters; the order is fixed,
 // hence deterministic).
-struct __align__(8) QEnt { float s; int dp; int slot; int pad; double ob; double obc; };  // 32 B
+struct __align__(16) QEnt { float s; int dp; unsigned mask; int val; };  // 16 B; mask bit 31: subtract
 #define IG_QCAP 64
+#define IG_QSUB 0x80000000u
 
+// term of a linear-contig contact at 0 < s < d_max WITHOUT the part that depends on the observed count only
+// (it cancels in t_mut - t_cur)
 __device__ __forceinline__ void eval_queue(const QEnt* __restrict__ q, int n, double* __restrict__ my_acc, const Params& p,
                                            double l10v, const float* __restrict__ exz_tab) {
     const int lane = threadIdx.x & 31;
@@ -545,19 +654,32 @@ __device__ __forceinline__ void eval_queue(const QEnt* __restrict__ q, int n, do
         const float exf = fmaxf((p.d == 2.0f) ? (p.c1 * powf(e.s, p.slope)) * p.fact
                                               : (p.c1 * powf(e.s, p.slope) * expf((p.d - 2) / (powf(e.s * p.lm / p.kuhn, 2.0f) + p.d))) * p.fact,
                                 p.v_inter);  // rippe_contacts for 0 < s < d_max (KA:153-163)
-        const double t = pxl_term(exf, e.ob, e.obc, l10v, p.v_inter) + (double)exz_tab[e.dp] * LOG10E_F;
-        my_acc[e.slot * IG_THREADS] += t;
+        double t = pxl_term(exf, (double)e.val, 0.0, l10v, p.v_inter) + (double)exz_tab[e.dp] * LOG10E_F;
+        if (e.mask & IG_QSUB) t = -t;
+        for (unsigned m = e.mask & 0xffffffu; m; m &= m - 1) my_acc[(__ffs(m) - 1) * IG_THREADS] += t;
     }
 }
 
+// The per-slot sums are DIFFERENCES to the current state: D[u] = sum over the selected contacts whose term
+// changes under mutation u of (t_u - t_cur); contacts that do not change contribute nothing and are not
+// evaluated at all (score[u] = Lnz_full(cur) + Lz[u] + D[u] is algebraically KA:4029-4046; the part of a term
+// that depends on the observed count only cancels and is left out).
+//   * Which (contact, mutation) pairs need a look at all is read from the candidate's class-pair bit table.
+//   * The mutated coordinate of the COLUMN end is recomputed on the fly from its current start_bp / offsets and
+//     the rigid motion of its class under the mutation (same float32 operations as fill_vect_dist, KA:3751, so
+//     bit-identical to the reference's 24 coordinate copies) -- no dependent global load inside the slot loop;
+//     the ROW end is warp-uniform and staged from the k_precompute table into shared memory once per item.
+//   * A pair whose (same-contig flag, s, sub-fragment separation) is bit-identical to the current state is
+//     skipped; the rest is either a cheap constant (other contig / outside (0, d_max)) or goes to the queue.
 __global__ void __launch_bounds__(IG_THREADS, 3)
 k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, const CoordRec* __restrict__ coord,
         const int* __restrict__ clen, const DevScalars* __restrict__ sc, const IgDescriptor* __restrict__ desc_g,
         const int* __restrict__ rows, const int* __restrict__ rowidx, int ns, int* __restrict__ row_cnt,
         const RowMut* __restrict__ table, const int* __restrict__ table_len, float mbar, const float* __restrict__ exz_tab,
-        double* __restrict__ part_nz,   // [cand][25][gridDim.x]  (24 uniq slots + current)
+        double* __restrict__ part_nz,   // [cand][25][gridDim.x]  (24 uniq slots; slot 24 unused = 0)
         int* __restrict__ part_c,       // [cand][2][gridDim.x]   (contacts selected, contacts read)
-        int gs_div)                     // work-splitting knob: split a row into slot groups while rows*groups < warps/gs_div
+        int gs_div,                     // work-splitting knob: split a row into slot groups while rows*groups < warps/gs_div
+        const IgClassTab* __restrict__ clstab, const SubX* __restrict__ subx)
 {
     const int k = blockIdx.y;
     if (k >= sc->n_cands) return;
@@ -565,12 +687,41 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
     __shared__ double red[IG_WARPS_PER_BLOCK][25];
     __shared__ int redi[IG_WARPS_PER_BLOCK][2];
     __shared__ QEnt queue[IG_WARPS_PER_BLOCK][IG_QCAP];
-    const Params p = sc->p;
-    const double l10v = sc->log10_vinter;
+    __shared__ RowMut s_row[IG_WARPS_PER_BLOCK][IG_N_OPS];
     const CandInfo ci_k = sc->ci[k];
     const int n_uniq = desc_g[k].n_uniq;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int wg = blockIdx.x * IG_WARPS_PER_BLOCK + w, nw = gridDim.x * IG_WARPS_PER_BLOCK;
+    // Work distribution: one warp per (affected row, group of gs uniq slots, part of the row); gs = 24 and one
+    // part when there are more rows than warps, fewer slots per item and rows cut into `parts` interleaved
+    // chunk sets when a candidate has few rows (yeast-scale assemblies), so that the grid stays occupied and
+    // the longest row does not set the kernel's critical path.
+    // (IG_BLOCK_MODE: one BLOCK per item, kept for experiments -- measured slower at yeast scale.)
+    const bool block_mode = (gs_div < 0) && ci_k.n_rows < nw / (-gs_div);
+    const int div = gs_div < 0 ? -gs_div : gs_div;
+    int gs = IG_N_OPS, parts = 1;
+    if (block_mode) {
+        const int want = (int)gridDim.x / 2;
+        gs = (ci_k.n_rows >= want) ? 24 : ((ci_k.n_rows * 4 >= want) ? 6 : ((ci_k.n_rows * 8 >= want) ? 3 : 1));
+    } else {
+        const int want = nw / div;
+        if (ci_k.n_rows < want) gs = (ci_k.n_rows * 4 >= want) ? 6 : ((ci_k.n_rows * 8 >= want) ? 3 : 1);
+        if (ci_k.n_rows * (IG_N_OPS / gs) * 2 <= nw) parts = 2;
+        if (ci_k.n_rows * (IG_N_OPS / gs) * 4 <= nw) parts = 4;
+    }
+    const int ng = IG_N_OPS / gs;
+    const int n_items = ci_k.n_rows * ng * parts;
+    const int it0 = block_mode ? (int)blockIdx.x : wg, it_step = block_mode ? (int)gridDim.x : nw;
+    if ((block_mode ? (int)blockIdx.x : (int)blockIdx.x * IG_WARPS_PER_BLOCK) >= n_items) {  // nothing for this block
+        if (threadIdx.x < 25) part_nz[PART_IDX(k, 25, threadIdx.x, gridDim.x, blockIdx.x)] = 0.0;
+        if (threadIdx.x < 2) part_c[PART_IDX(k, 2, threadIdx.x, gridDim.x, blockIdx.x)] = 0;
+        return;
+    }
+    const Params p = sc->p;
+    const double l10v = sc->log10_vinter;
     const unsigned lt_mask = (1u << lane) - 1;
+    const unsigned* g_mask = clstab[k].mask;    // small per-candidate tables: read through L1
+    const IgMotion* g_mot = clstab[k].mot;
     if (lane < 25) red[w][lane] = 0.0;
     if (lane < 2) redi[w][lane] = 0;
     __syncwarp();
@@ -579,106 +730,130 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
     int* my_cnt = row_cnt + (size_t)k * ns;
     const RowMut* tab = table + (size_t)k * IG_N_OPS * ns;
     const int* tlen = table_len + (size_t)k * IG_N_OPS * ns;
-    const int wg = blockIdx.x * IG_WARPS_PER_BLOCK + w, nw = gridDim.x * IG_WARPS_PER_BLOCK;
-    // group size: all slots per item when there are more rows than warps, fewer when a candidate has few rows
-    // Work distribution.  Mode W (many rows): one warp per (row, slot group), gs = 24.  Mode B (few rows,
-    // e.g. a yeast-scale assembly): one BLOCK per (row, slot group), its 8 warps striding the row's
-    // contacts, so that the longest row no longer sets the kernel's critical path; rows are split into
-    // slot groups only as far as needed to occupy the grid (each extra group repeats the per-contact
-    // selection + current-state term).
-    // (block mode is kept for experiments, IG_BLOCK_MODE=1: at yeast scale it measured slower than
-    //  splitting rows into slot groups -- 79 us vs 64 us -- because only 3 of 8 warps find contacts)
-    const bool block_mode = (gs_div < 0) && ci_k.n_rows < nw / (-gs_div);
-    const int div = gs_div < 0 ? -gs_div : gs_div;
-    int gs = IG_N_OPS;
-    if (block_mode) {
-        const int want = (int)gridDim.x / 2;
-        gs = (ci_k.n_rows >= want) ? 24 : ((ci_k.n_rows * 4 >= want) ? 6 : ((ci_k.n_rows * 8 >= want) ? 3 : 1));
-    } else {
-        const int want = nw / div;
-        if (ci_k.n_rows < want) gs = (ci_k.n_rows * 4 >= want) ? 6 : ((ci_k.n_rows * 8 >= want) ? 3 : 1);
-    }
-    const int ng = IG_N_OPS / gs;
-    const int n_items = ci_k.n_rows * ng;
     double* my_acc = acc_s + threadIdx.x;
     QEnt* myq = queue[w];
+    RowMut* myrow = s_row[w];
     // constant term of a contact whose endpoints lie in different contigs (KA:4348-4352) minus the ob part
     const double inter_const = (double)p.v_inter * LOG10E_F;
-    const int it0 = block_mode ? (int)blockIdx.x : wg, it_step = block_mode ? (int)gridDim.x : nw;
-    const int q_off = block_mode ? 32 * w : 0, q_step = block_mode ? 32 * IG_WARPS_PER_BLOCK : 32;
     for (int it = it0; it < n_items; it += it_step) {
-        const int ri = it / ng, g = it - ri * ng;
+        const int rg = it / parts, part = it - rg * parts;
+        const int ri = rg / ng, g = rg - ri * ng;
+        const int q_off = block_mode ? 32 * w : 32 * part, q_step = block_mode ? 32 * IG_WARPS_PER_BLOCK : 32 * parts;
         const int u0 = g * gs;
         if (u0 >= n_uniq && g != 0) continue;
         const int u1 = min(u0 + gs, n_uniq);
+        const unsigned gmask = (u1 > u0) ? (((1u << (u1 - u0)) - 1u) << u0) : 0u;
         const int r = my_rows[ri];
         const CoordRec ci = coord[r];
+        const unsigned* mrow = g_mask + (my_idx[r] >> IG_CLS_SHIFT) * IG_MAX_CLS;
         const long long b = row_ptr[r], e = row_ptr[r + 1];
+        __syncwarp();
+        if (u0 + lane < u1) myrow[lane] = tab[(size_t)(u0 + lane) * ns + ri];
         for (int u = u0; u < u1; u++) my_acc[(u - u0) * IG_THREADS] = 0.0;
-        double acc_cur = 0.0;
+        __syncwarp();
         int row_sel = 0;
         int qn = 0;  // warp-uniform queue fill
         for (long long q0 = b + q_off; q0 < e; q0 += q_step) {
             const long long q = q0 + lane;
-            bool active = false;
+            unsigned m = 0;
             int2 c = make_int2(0, 0);
             CoordRec cj = ci;
+            int rjc = 0;
             if (q < e) {
                 c = __ldg(&cv[q]);
                 cj = coord[c.x];
-                active = (cj.id_c == ci_k.id_a || cj.id_c == ci_k.id_b) && contact_selected(ci, cj, c.y, ci_k);
+                if ((cj.id_c == ci_k.id_a || cj.id_c == ci_k.id_b) && contact_selected(ci, cj, c.y, ci_k)) {
+                    row_sel++;
+                    rjc = my_idx[c.x];
+                    m = __ldg(&mrow[rjc >> IG_CLS_SHIFT]) & gmask;
+                }
             }
-            if (!__any_sync(0xffffffffu, active)) continue;
-            double ob = 0.0, obc = 0.0, t_cur = 0.0, t_inter = 0.0;
-            int rj = 0, cur_dp = 0;
+            const unsigned um = __reduce_or_sync(0xffffffffu, m);
+            if (!um) continue;
+            // current-state term of the lanes that have something to evaluate
+            double ob = 0.0, t_cur = 0.0, t_inter = 0.0;
+            int cur_dp = 0;
             float cur_s = 0.f;
-            bool cur_same = false;
-            if (active) {
-                row_sel++;
-                ob = (double)c.y; obc = ob_const(ob);
-                t_cur = contact_term(ci, cj, clen[c.x], ob, obc, p, l10v, mbar, exz_tab);
-                acc_cur += t_cur;
-                t_inter = pxl_term(p.v_inter, ob, obc, l10v, p.v_inter) + inter_const;
-                rj = my_idx[c.x];
+            bool cur_same = false, cur_deferred = false;
+            SubX sx = {0, 0, 0.f, 0.f};
+            if (m) {
+                sx = subx[c.x];
+                ob = (double)c.y;
+                t_inter = pxl_term(p.v_inter, ob, 0.0, l10v, p.v_inter) + inter_const;
                 cur_same = ci.id_c == cj.id_c;
                 cur_s = fabsf(ci.dist - cj.dist);
                 cur_dp = abs(ci.pos - cj.pos);
+                if (!cur_same) t_cur = t_inter;
+                else if (ci.s_tot != 0) t_cur = contact_term(ci, cj, clen[c.x], ob, 0.0, p, l10v, mbar, exz_tab);  // circular (rare)
+                else if (!((cur_s > 0.0f) && (cur_s < p.d_max))) t_cur = pxl_term(p.v_inter, ob, 0.0, l10v, p.v_inter) + (double)exz_tab[cur_dp] * LOG10E_F;
+                else cur_deferred = true;  // powf + log10: goes through the queue once, with the mask of changed slots
             }
-            const RowMut* ta = tab + (size_t)u0 * ns + ri;
-            const RowMut* tb = tab + (size_t)u0 * ns + rj;
+            const IgMotion* mcol = g_mot + (rjc >> IG_CLS_SHIFT) * IG_N_OPS;
+            const int len_j = abs(sx.len_ori);
+            const bool fw_j = sx.len_ori > 0;
+            unsigned chg = 0;
 #pragma unroll 1
-            for (int u = u0; u < u1; u++, ta += ns, tb += ns) {
+            for (unsigned uw = um; uw; uw &= uw - 1) {
+                const int u = __ffs(uw) - 1;
                 bool push = false;
                 float s_m = 0.f;
                 int dp_m = 0;
-                if (active) {
-                    const RowMut a = *ta;
-                    const RowMut bm = *tb;
-                    const bool m_same = a.id_c == bm.id_c;
-                    s_m = fabsf(a.dist - bm.dist);
-                    dp_m = abs(a.pos - bm.pos);
-                    double t;
-                    if (m_same == cur_same && a.s_tot == ci.s_tot && (!m_same || (a.s_tot == 0 && s_m == cur_s && dp_m == cur_dp))) {
-                        t = t_cur;            // bit-exact shortcut: identical inputs give the identical term
-                    } else if (!m_same) {
-                        t = t_inter;          // different contigs: both expectations are v_inter
-                    } else if (a.s_tot != 0) {  // circular contig (rare): evaluate in place
-                        CoordRec cim, cjm;
-                        cim.dist = a.dist; cim.id_c = a.id_c; cim.pos = a.pos; cim.s_tot = a.s_tot;
-                        cjm.dist = bm.dist; cjm.id_c = bm.id_c; cjm.pos = bm.pos; cjm.s_tot = bm.s_tot;
-                        t = contact_term(cim, cjm, tlen[(size_t)u * ns + rj], ob, obc, p, l10v, mbar, exz_tab);
-                    } else if (!((s_m > 0.0f) && (s_m < p.d_max))) {
-                        // linear, outside (0, d_max): rippe_contacts returns max(0, v_inter) = v_inter
-                        t = pxl_term(p.v_inter, ob, obc, l10v, p.v_inter) + (double)exz_tab[dp_m] * LOG10E_F;
-                    } else {
-                        push = true; t = 0.0;  // needs powf + log10: queue it
+                if ((m >> u) & 1u) {
+                    const RowMut a = myrow[u - u0];
+                    const int4 mo4 = __ldg(reinterpret_cast<const int4*>(mcol + u));
+                    IgMotion mo; mo.dbp = mo4.x; mo.dsp = mo4.y; mo.id_c = mo4.z; mo.flip = mo4.w;
+                    const bool m_same = a.id_c == mo.id_c;
+                    double t = t_inter;  // different contigs: both expectations are v_inter
+                    bool differs = true;
+                    if (m_same) {
+                        if (a.s_tot != 0) {  // circular contig (rare): mutated column end from the table, evaluated in place
+                            const int rj = rjc & ((1 << IG_CLS_SHIFT) - 1);
+                            const RowMut bm = tab[(size_t)u * ns + rj];
+                            CoordRec cim, cjm;
+                            cim.dist = a.dist; cim.id_c = a.id_c; cim.pos = a.pos; cim.s_tot = a.s_tot;
+                            cjm.dist = bm.dist; cjm.id_c = bm.id_c; cjm.pos = bm.pos; cjm.s_tot = bm.s_tot;
+                            t = contact_term(cim, cjm, tlen[(size_t)u * ns + rj], ob, 0.0, p, l10v, mbar, exz_tab);
+                        } else {
+                            // the column end under this mutation: start_bp and sub-position follow the class motion
+                            const int sb = mo.flip ? mo.dbp - sx.start_bp - len_j : sx.start_bp + mo.dbp;
+                            const float dj = __int2float_rn(sb) / 1000.0f + ((fw_j != (mo.flip != 0)) ? sx.watson : sx.crick);  // KA:3751
+                            const int pj = mo.flip ? mo.dsp - 1 - cj.pos : cj.pos + mo.dsp;
+                            s_m = fabsf(a.dist - dj);
+                            dp_m = abs(a.pos - pj);
+                            if (cur_same && ci.s_tot == 0 && s_m == cur_s && dp_m == cur_dp) differs = false;  // bit-identical inputs
+                            else if (!((s_m > 0.0f) && (s_m < p.d_max)))
+                                t = pxl_term(p.v_inter, ob, 0.0, l10v, p.v_inter) + (double)exz_tab[dp_m] * LOG10E_F;  // floor v_inter
+                            else { push = true; t = 0.0; }  // needs powf + log10: queue it
+                        }
+                    } else if (!cur_same) differs = false;  // two contigs before and after
+                    if (differs) {
+                        chg |= 1u << (u - u0);
+                        my_acc[(u - u0) * IG_THREADS] += t - t_cur;   // t_cur = 0 while deferred
                     }
-                    if (!push) my_acc[(u - u0) * IG_THREADS] += t;
                 }
                 const unsigned pm = __ballot_sync(0xffffffffu, push);
                 if (pm) {
                     if (push) {
-                        QEnt en; en.s = s_m; en.dp = dp_m; en.slot = u - u0; en.pad = 0; en.ob = ob; en.obc = obc;
+                        QEnt en; en.s = s_m; en.dp = dp_m; en.mask = 1u << (u - u0); en.val = c.y;
+                        myq[qn + __popc(pm & lt_mask)] = en;
+                    }
+                    qn += __popc(pm);
+                    __syncwarp();
+                    if (qn >= 32) {
+                        eval_queue(myq, 32, my_acc, p, l10v, exz_tab);
+                        __syncwarp();
+                        if (lane < qn - 32) { const QEnt mv = myq[32 + lane]; myq[lane] = mv; }
+                        qn -= 32;
+                        __syncwarp();
+                    }
+                }
+            }
+            {   // the deferred current-state terms, subtracted from every slot that changed
+                const bool push = cur_deferred && chg;
+                const unsigned pm = __ballot_sync(0xffffffffu, push);
+                if (pm) {
+                    if (push) {
+                        QEnt en; en.s = cur_s; en.dp = cur_dp; en.mask = chg | IG_QSUB; en.val = c.y;
                         myq[qn + __popc(pm & lt_mask)] = en;
                     }
                     qn += __popc(pm);
@@ -701,11 +876,11 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
             if (lane == 0) red[w][u] += v;
         }
         if (g == 0) {
-            const double v = warp_sum(acc_cur);
             row_sel = __reduce_add_sync(0xffffffffu, row_sel);
             if (lane == 0) {
-                red[w][24] += v; redi[w][0] += row_sel;
+                redi[w][0] += row_sel;
                 if (block_mode) { if (row_sel) atomicAdd(&my_cnt[ri], row_sel); if (w == 0) redi[w][1] += (int)(e - b); }
+                else if (parts > 1) { if (row_sel) atomicAdd(&my_cnt[ri], row_sel); if (part == 0) redi[w][1] += (int)(e - b); }
                 else { my_cnt[ri] = row_sel; redi[w][1] += (int)(e - b); }
             }
         }
@@ -843,7 +1018,7 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
             const int e = idx % t_cnt, u = t + idx / t_cnt;
             const int2 c = t_cv[e];
             const RowMut a = tab[(size_t)u * ns + t_ri[e]];
-            const int rj = rowidx[(size_t)k * ns + c.x];
+            const int rj = rowidx[(size_t)k * ns + c.x] & ((1 << IG_CLS_SHIFT) - 1);
             const RowMut bm = tab[(size_t)u * ns + rj];
             CoordRec cim, cjm;
             cim.dist = a.dist; cim.id_c = a.id_c; cim.pos = a.pos; cim.s_tot = a.s_tot;
@@ -988,7 +1163,7 @@ k_lnz_outside(const long long* __restrict__ row_ptr, const int2* __restrict__ cv
             const CoordRec cj = coord[c.x];
             if (cj.id_c != ci_k.id_a) continue;               // other contigs: inter-contig term, unchanged
             if (contact_selected(ci, cj, c.y, ci_k)) continue;  // already inside lnz_new
-            const int rj = my_idx[c.x];
+            const int rj = my_idx[c.x] & ((1 << IG_CLS_SHIFT) - 1);
             const RowMut bm = tab[rj];
             CoordRec cim, cjm;
             cim.dist = a.dist; cim.id_c = a.id_c; cim.pos = a.pos; cim.s_tot = a.s_tot;
@@ -1020,7 +1195,8 @@ k_lnz_outside(const long long* __restrict__ row_ptr, const int2* __restrict__ cv
 // everything else is unchanged; the scalar likelihood pieces were prepared by the previous step.
 __global__ void __launch_bounds__(256)
 k_commit_coords(CoordRec* __restrict__ coord, int* __restrict__ clen, DevScalars* sc, const int* __restrict__ rows, int ns,
-                const RowMut* __restrict__ table, const int* __restrict__ table_len) {
+                const RowMut* __restrict__ table, const int* __restrict__ table_len, const FragRec* __restrict__ live,
+                const SubRec* __restrict__ sub, SubX* __restrict__ subx) {
     const int k = sc->prev_k, u = sc->prev_u, n = sc->prev_n_rows;
     const int* my_rows = rows + (size_t)k * ns;
     const RowMut* tab = table + ((size_t)k * IG_N_OPS + u) * ns;
@@ -1030,6 +1206,10 @@ k_commit_coords(CoordRec* __restrict__ coord, int* __restrict__ clen, DevScalars
         const RowMut m = tab[ri];
         CoordRec c; c.dist = m.dist; c.id_c = m.id_c; c.pos = m.pos; c.s_tot = m.s_tot;
         coord[r] = c; clen[r] = tlen[ri];
+        const SubRec sr = sub[r];
+        const Frag f = live[sr.parent].f;   // the scaffold after the applied move
+        SubX x; x.start_bp = f.start_bp; x.len_ori = f.len_bp * f.ori; x.watson = sr.watson; x.crick = sr.crick;
+        subx[r] = x;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         sc->lnz_full = sc->lnz_next; sc->z_cur = sc->z_next; sc->nintra_cur = sc->nintra_next;
@@ -1204,8 +1384,9 @@ struct ig_handle {
     ig_config cfg;
     int nf, ns;
     long long nnz;
-    cudaStream_t stream, side;
-    cudaEvent_t ev_coords, ev_lnz, ev_fork, ev_sel, ev_out;
+    cudaStream_t stream, side, pf;
+    cudaEvent_t ev_coords, ev_lnz, ev_fork, ev_sel, ev_out, ev_cuts, ev_cls;
+    bool prefetch;  // the level's arrays fit the L2 comfortably: prefetch them at the start of a step
     FragRec *live, *init_live;
     SubRec* sub;
     CoordRec* coord;
@@ -1222,6 +1403,7 @@ struct ig_handle {
     double *part_nz, *part_z; int *part_i, *part_c;
     int grid_pre;
     RowMut* table; int *table_len, *rowidx;
+    IgClassTab* clstab; int rigid; SubX* subx;
     double *part_full; int n_part_full;
     double *part_zc; int* part_nc; int n_part_zc;
     int *d_nuniq, *d_nsub, *d_perm;
@@ -1233,7 +1415,7 @@ struct ig_handle {
     double* part_out;
     int gs_div;
     long long last_n_full;
-    cudaGraphExec_t graph[4];
+    cudaGraphExec_t graph[4][IG_MAX_CANDS + 1];   // [full + 2 * cycle][candidates in the grid]
     int* cyc_in; CycleOut* cyc_out; int cyc_cap; bool graph_failed, capturing, use_graph; long long n_full;
     // measurement (CUDA events on the launching stream)
     cudaEvent_t ev[6];
@@ -1291,20 +1473,25 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
     }
     if (cfg->device < 0 || cfg->device >= ndev) { g_err = "ig_create: bad device ordinal"; return -1; }
     if (cfg->n_frags <= 0 || cfg->n_sub_frags <= 0 || cfg->nnz < 0) { g_err = "ig_create: bad sizes"; return -1; }
+    if (cfg->n_sub_frags >= (1 << IG_CLS_SHIFT)) { g_err = "ig_create: more than 2^24 sub-fragments"; return -1; }
     h = new ig_handle();
     h->cfg = *cfg; h->nf = cfg->n_frags; h->ns = cfg->n_sub_frags; h->nnz = cfg->nnz;
+    h->rigid = cfg->rigid_pruning ? 1 : 0;
     h->params_set = false; h->coords_fresh = false; h->coords_ever = false;
     h->incr_valid = false; h->refresh_every = 4096; h->steps_since_full = 0;
     h->gs_div = 4;
     if (const char* e = getenv("IG_GS_DIV")) h->gs_div = std::max(1, atoi(e));
     if (const char* e = getenv("IG_BLOCK_MODE")) if (atoi(e)) h->gs_div = -h->gs_div;
-    h->graph[0] = h->graph[1] = h->graph[2] = h->graph[3] = nullptr; h->cyc_in = nullptr; h->cyc_out = nullptr; h->cyc_cap = 0; h->graph_failed = false; h->capturing = false; h->use_graph = true; h->n_full = 0;
+    memset(h->graph, 0, sizeof h->graph); h->cyc_in = nullptr; h->cyc_out = nullptr; h->cyc_cap = 0; h->graph_failed = false; h->capturing = false; h->use_graph = true; h->n_full = 0;
     cudaError_t e0 = cudaSetDevice(cfg->device);
     if (e0 != cudaSuccess) { g_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e0); delete h; return -2; }
 #define CKC(x) do { int r_ = (x); if (r_) { g_err = h->err; ig_destroy(h); return r_; } } while (0)
     auto body = [&]() -> int {
         CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&h->pf, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->ev_cuts, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_cls, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_coords, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_lnz, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -1328,7 +1515,12 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
         const int sms = prop.multiProcessorCount;
         h->grid_score = sms * 3;  // 3 resident CTAs of 8 warps per SM (launch bounds, 48 KB dynamic smem each)
         CK(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IG_SCORE_SMEM));
-        h->grid_pre = sms * 4;
+        h->grid_pre = sms * 2;
+        {
+            const char* e = getenv("IG_PREFETCH");
+            const size_t bytes = sizeof(int2) * (size_t)h->nnz + 64 * (size_t)ns + 80 * (size_t)nf;
+            h->prefetch = e ? (atoi(e) != 0) : (bytes <= ((size_t)48 << 20));
+        }
         if (dev_alloc(h, &h->part_nz, (size_t)IG_MAX_CANDS * h->grid_score * 25)) return -2;
         if (dev_alloc(h, &h->part_c, (size_t)IG_MAX_CANDS * h->grid_score * 2)) return -2;
         if (dev_alloc(h, &h->part_z, (size_t)IG_MAX_CANDS * h->grid_pre * 25)) return -2;
@@ -1336,6 +1528,7 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
         if (dev_alloc(h, &h->table, (size_t)IG_MAX_CANDS * IG_N_OPS * ns)) return -2;
         if (dev_alloc(h, &h->table_len, (size_t)IG_MAX_CANDS * IG_N_OPS * ns)) return -2;
         if (dev_alloc(h, &h->rowidx, (size_t)IG_MAX_CANDS * ns)) return -2;
+        if (dev_alloc(h, &h->clstab, (size_t)IG_MAX_CANDS) || dev_alloc(h, &h->subx, (size_t)ns)) return -2;
         h->n_part_full = sms * 8;
         if (dev_alloc(h, &h->part_full, h->n_part_full)) return -2;
         if (dev_alloc(h, &h->part_out, h->n_part_full)) return -2;
@@ -1397,7 +1590,7 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
 extern "C" void ig_destroy(ig_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
-    void* ptrs[] = {h->live, h->part_out, h->part_c, h->table, h->table_len, h->rowidx, h->init_live, h->sub, h->coord, h->clen, h->row_ptr, h->cv, h->sym_diag,
+    void* ptrs[] = {h->clstab, h->subx, h->live, h->part_out, h->part_c, h->table, h->table_len, h->rowidx, h->init_live, h->sub, h->coord, h->clen, h->row_ptr, h->cv, h->sym_diag,
                     h->init_prev, h->init_next, h->orientable, h->sc, h->desc, h->exz, h->exz_test, h->chunk_cnt,
                     h->rows, h->row_cnt, h->part_nz, h->part_z, h->part_i, h->part_full, h->part_zc, h->part_nc,
                     h->d_nuniq, h->d_nsub, h->d_perm, h->d_hist};
@@ -1406,10 +1599,13 @@ extern "C" void ig_destroy(ig_handle* h) {
     if (h->h_small) cudaFreeHost(h->h_small);
     for (int i = 0; i < 6; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 16; i++) if (h->evk[i]) cudaEventDestroy(h->evk[i]);
-    for (int i = 0; i < 4; i++) if (h->graph[i]) cudaGraphExecDestroy(h->graph[i]);
+    for (int i = 0; i < 4; i++) for (int j = 0; j <= IG_MAX_CANDS; j++) if (h->graph[i][j]) cudaGraphExecDestroy(h->graph[i][j]);
     if (h->cyc_in) cudaFree(h->cyc_in);
     if (h->cyc_out) cudaFree(h->cyc_out);
     if (h->side) cudaStreamDestroy(h->side);
+    if (h->pf) cudaStreamDestroy(h->pf);
+    if (h->ev_cuts) cudaEventDestroy(h->ev_cuts);
+    if (h->ev_cls) cudaEventDestroy(h->ev_cls);
     if (h->ev_coords) cudaEventDestroy(h->ev_coords);
     if (h->ev_lnz) cudaEventDestroy(h->ev_lnz);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -1515,7 +1711,7 @@ static int refresh_current(ig_handle* h, cudaStream_t st, bool fork) {
         cudaEventRecord(h->ev_fork, h->stream);
         cudaStreamWaitEvent(st, h->ev_fork, 0);
     }
-    k_coords<<<h->n_part_zc, IG_THREADS, 0, st>>>(h->live, h->sub, h->coord, h->clen, h->ns, h->sc, mbar, 0, h->part_zc, h->part_nc, 1);
+    k_coords<<<h->n_part_zc, IG_THREADS, 0, st>>>(h->live, h->sub, h->coord, h->clen, h->ns, h->sc, mbar, 0, h->part_zc, h->part_nc, 1, h->subx);
     k_reduce<<<1, 256, 0, st>>>(h->part_zc, h->n_part_zc, &h->sc->z_cur, h->part_nc, &h->sc->nintra_cur);
     if (fork) cudaEventRecord(h->ev_coords, st);
     if (h->profile) cudaEventRecord(h->ev[2], st);
@@ -1539,17 +1735,18 @@ static int score_candidates(ig_handle* h, int a, const int32_t* cands, int n, in
     CK(cudaMemcpyAsync(&h->sc->n_cands, hs, (2 + IG_MAX_CANDS) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     const FragRec* live = h->live;
     k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, first_flip_eject, nullptr);
-    k_find_cuts<<<dim3((h->nf + 255) / 256, n), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc);
+    k_find_cuts<<<dim3((h->nf + 255) / 256, n), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc, h->clstab);
+    k_classes<<<n, 256, 0, h->stream>>>(h->sc, h->desc, h->clstab, h->rigid);
     if (overlap) cudaStreamWaitEvent(h->stream, h->ev_coords, 0);
     k_rows_count<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks);
     k_rows_write<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks, h->rows,
-                                                                       h->rowidx, h->row_cnt, h->ns);
+                                                                       h->rowidx, h->row_cnt, h->ns, h->clstab);
     k_precompute<<<dim3(h->grid_pre, n), IG_THREADS, 0, h->stream>>>(h->coord, h->clen, live, h->sub, h->sc, h->desc, h->rows, h->ns,
                                                                     h->table, h->table_len, mbar, h->part_z, h->part_i);
     if (h->profile) cudaEventRecord(h->ev[4], h->stream);
     k_score<<<dim3(h->grid_score, n), IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
                                                                  h->ns, h->row_cnt, h->table, h->table_len, mbar, h->exz, h->part_nz,
-                                                                 h->part_c, h->gs_div);
+                                                                 h->part_c, h->gs_div, h->clstab, h->subx);
     if (h->profile) cudaEventRecord(h->ev[5], h->stream);
     h->n_launches += 7;
     if (overlap) cudaStreamWaitEvent(h->stream, h->ev_lnz, 0);
@@ -1603,9 +1800,23 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands, int cycle = 0)
     if (!cycle) cudaMemcpyAsync(&h->sc->n_cands, h->h_small, (2 + IG_MAX_CANDS) * sizeof(int), cudaMemcpyHostToDevice, h->stream);
     cudaEventRecord(h->ev_fork, h->stream);
     cudaStreamWaitEvent(h->side, h->ev_fork, 0);
+    cudaStreamWaitEvent(h->pf, h->ev_fork, 0);
+    if (h->prefetch) {
+        PfList L;
+        int c = 0;
+        auto add = [&](const void* ptr, size_t bytes) { L.p[c] = (const char*)ptr; L.n[c] = bytes; c++; };
+        add(h->cv, sizeof(int2) * (size_t)h->nnz); add(h->row_ptr, sizeof(long long) * ((size_t)h->ns + 1));
+        add(h->coord, sizeof(CoordRec) * (size_t)h->ns); add(h->clen, sizeof(int) * (size_t)h->ns);
+        add(h->subx, sizeof(SubX) * (size_t)h->ns); add(h->sub, sizeof(SubRec) * (size_t)h->ns);
+        add(h->live, sizeof(FragRec) * (size_t)h->nf); add(h->exz, sizeof(float) * ((size_t)h->ns + 1));
+        add(h->init_prev, sizeof(int) * (size_t)h->nf); add(h->init_next, sizeof(int) * (size_t)h->nf);
+        add(h->orientable, sizeof(int) * (size_t)h->nf);
+        L.cnt = c;
+        k_prefetch_l2<<<h->n_part_zc, 256, 0, h->pf>>>(L);
+    }
     if (full) {
         k_coords<<<h->n_part_zc, IG_THREADS, 0, h->side>>>(h->live, h->sub, h->coord, h->clen, h->ns, h->sc, mbar, 0, h->part_zc,
-                                                          h->part_nc, 1);
+                                                          h->part_nc, 1, h->subx);
         k_reduce<<<1, 256, 0, h->side>>>(h->part_zc, h->n_part_zc, &h->sc->z_cur, h->part_nc, &h->sc->nintra_cur);
         cudaEventRecord(h->ev_coords, h->side);
         if (h->profile && !h->capturing) cudaEventRecord(h->ev[2], h->side);
@@ -1616,7 +1827,7 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands, int cycle = 0)
         cudaEventRecord(h->ev_lnz, h->side);
     } else {
         k_commit_coords<<<std::min(h->n_part_zc, (h->ns + 255) / 256), 256, 0, h->side>>>(h->coord, h->clen, h->sc, h->rows, h->ns,
-                                                                                         h->table, h->table_len);
+                                                                                         h->table, h->table_len, h->live, h->sub, h->subx);
         cudaEventRecord(h->ev_coords, h->side);
         cudaEventRecord(h->ev_lnz, h->side);
     }
@@ -1625,21 +1836,26 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands, int cycle = 0)
     IG_MARK(0);
     k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, 1, cycle ? h->cyc_in : nullptr);
     IG_MARK(1);
-    k_find_cuts<<<dim3((h->nf + 255) / 256, n), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc);
+    k_find_cuts<<<dim3((h->nf + 255) / 256, n), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc, h->clstab);
+    cudaEventRecord(h->ev_cuts, h->stream);
+    cudaStreamWaitEvent(h->pf, h->ev_cuts, 0);
+    k_classes<<<n, 256, 0, h->pf>>>(h->sc, h->desc, h->clstab, h->rigid);   // beside the row list; k_score needs it
+    cudaEventRecord(h->ev_cls, h->pf);
     cudaStreamWaitEvent(h->stream, h->ev_coords, 0);
     IG_MARK(2);
     k_rows_count<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks);
     IG_MARK(3);
     k_rows_write<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks, h->rows,
-                                                                       h->rowidx, h->row_cnt, h->ns);
+                                                                       h->rowidx, h->row_cnt, h->ns, h->clstab);
     IG_MARK(4);
     k_precompute<<<dim3(h->grid_pre, n), IG_THREADS, 0, h->stream>>>(h->coord, h->clen, live, h->sub, h->sc, h->desc, h->rows, h->ns,
                                                                     h->table, h->table_len, mbar, h->part_z, h->part_i);
     if (h->profile && !h->capturing) cudaEventRecord(h->ev[4], h->stream);
+    cudaStreamWaitEvent(h->stream, h->ev_cls, 0);
     IG_MARK(5);
     k_score<<<dim3(h->grid_score, n), IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
                                                                  h->ns, h->row_cnt, h->table, h->table_len, mbar, h->exz, h->part_nz,
-                                                                 h->part_c, h->gs_div);
+                                                                 h->part_c, h->gs_div, h->clstab, h->subx);
     if (h->profile && !h->capturing) cudaEventRecord(h->ev[5], h->stream);
     cudaStreamWaitEvent(h->stream, h->ev_lnz, 0);
     IG_MARK(6);
@@ -1651,8 +1867,10 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands, int cycle = 0)
     // independent of apply/post: runs beside them on the side stream, joined before the result copy
     cudaEventRecord(h->ev_sel, h->stream);
     cudaStreamWaitEvent(h->side, h->ev_sel, 0);
-    k_lnz_outside<<<h->grid_score, IG_THREADS, 0, h->side>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->rows, h->rowidx, h->ns,
-                                                             h->table, h->table_len, mbar, h->exz, h->part_out);
+    // (not with rigid pruning: there the contacts outside the slice windows keep their terms, as they do mathematically)
+    if (!h->rigid)
+        k_lnz_outside<<<h->grid_score, IG_THREADS, 0, h->side>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->rows, h->rowidx, h->ns,
+                                                                 h->table, h->table_len, mbar, h->exz, h->part_out);
     cudaEventRecord(h->ev_out, h->side);
     IG_MARK(9);
     k_apply<<<(h->nf + 255) / 256, 256, 0, h->stream>>>(h->live, h->nf, h->sc, h->desc, -1, -1);
@@ -1668,17 +1886,17 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands, int cycle = 0)
     }
     return launch_ok(h, "enqueue_step");
 }
-#define IG_LAUNCHES_FULL 14
-#define IG_LAUNCHES_INCR 11
+#define IG_LAUNCHES_FULL 15
+#define IG_LAUNCHES_INCR 12
 
-static int get_graph(ig_handle* h, int full, cudaGraphExec_t* out, int cycle = 0) {
-    cudaGraphExec_t& ge = h->graph[full + 2 * cycle];
+static int get_graph(ig_handle* h, int full, cudaGraphExec_t* out, int cycle, int n) {
+    cudaGraphExec_t& ge = h->graph[full + 2 * cycle][n];
     if (!ge && !h->graph_failed) {
         cudaGraph_t g = nullptr;
         h->capturing = true;
         cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
         if (e == cudaSuccess) {
-            enqueue_step(h, full, IG_MAX_CANDS, cycle);
+            enqueue_step(h, full, n, cycle);
             e = cudaStreamEndCapture(h->stream, &g);
         }
         h->capturing = false;
@@ -1703,7 +1921,7 @@ extern "C" int ig_step(ig_handle* h, int32_t id_frag, const int32_t* cands, int3
     for (int i = 0; i < IG_MAX_CANDS; i++) hs[2 + i] = i < n_cands ? cands[i] : 0;
     const int full = (!h->incr_valid || (h->refresh_every > 0 && h->steps_since_full >= h->refresh_every)) ? 1 : 0;
     cudaGraphExec_t ge = nullptr;
-    if (h->use_graph && !h->profile) get_graph(h, full, &ge);
+    if (h->use_graph && !h->profile) get_graph(h, full, &ge, 0, n_cands);
     cudaEventRecord(h->ev[0], h->stream);
     if (ge) {
         CK(cudaGraphLaunch(ge, h->stream));
@@ -1712,7 +1930,7 @@ extern "C" int ig_step(ig_handle* h, int32_t id_frag, const int32_t* cands, int3
     }
     cudaEventRecord(h->ev[1], h->stream);
     CK(cudaStreamSynchronize(h->stream));
-    h->n_launches += full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR;
+    h->n_launches += (full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR) - (h->rigid ? 1 : 0) + (h->prefetch ? 1 : 0);
     h->steps_since_full = full ? 1 : h->steps_since_full + 1;
     h->n_full += full;
     h->incr_valid = true;
@@ -1757,7 +1975,7 @@ extern "C" int ig_run_cycle(ig_handle* h, int32_t n_steps, const int32_t* frags,
         if (h->cyc_in) cudaFree(h->cyc_in);
         if (h->cyc_out) cudaFree(h->cyc_out);
         h->cyc_in = nullptr; h->cyc_out = nullptr; h->cyc_cap = 0;
-        for (int i = 2; i < 4; i++) if (h->graph[i]) { cudaGraphExecDestroy(h->graph[i]); h->graph[i] = nullptr; }  // pointers are baked in
+        for (int i = 2; i < 4; i++) for (int j = 0; j <= IG_MAX_CANDS; j++) if (h->graph[i][j]) { cudaGraphExecDestroy(h->graph[i][j]); h->graph[i][j] = nullptr; }  // pointers are baked in
         if (dev_alloc(h, &h->cyc_in, (size_t)n_steps * (2 + IG_MAX_CANDS)) || dev_alloc(h, &h->cyc_out, (size_t)n_steps)) return -2;
         h->cyc_cap = n_steps;
     }
@@ -1767,13 +1985,13 @@ extern "C" int ig_run_cycle(ig_handle* h, int32_t n_steps, const int32_t* frags,
     for (int t = 0; t < n_steps; t++) {
         const int full = (!h->incr_valid || (h->refresh_every > 0 && h->steps_since_full >= h->refresh_every)) ? 1 : 0;
         cudaGraphExec_t ge = nullptr;
-        if (h->use_graph) get_graph(h, full, &ge, 1);
+        if (h->use_graph) get_graph(h, full, &ge, 1, n_cands[t]);
         if (ge) { CK(cudaGraphLaunch(ge, h->stream)); }
-        else if (enqueue_step(h, full, IG_MAX_CANDS, 1)) return -2;
+        else if (enqueue_step(h, full, n_cands[t], 1)) return -2;
         h->steps_since_full = full ? 1 : h->steps_since_full + 1;
         h->n_full += full;
         h->incr_valid = true;
-        h->n_launches += full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR;
+        h->n_launches += (full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR) - (h->rigid ? 1 : 0) + (h->prefetch ? 1 : 0);
     }
     cudaEventRecord(h->ev[1], h->stream);
     std::vector<CycleOut> res(n_steps);
@@ -1834,7 +2052,7 @@ extern "C" int ig_apply(ig_handle* h, int32_t id_frag, int32_t id_cand, int32_t 
     CK(cudaStreamSynchronize(h->stream));
     const FragRec* live = h->live;
     k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, 0, nullptr);
-    k_find_cuts<<<dim3((h->nf + 255) / 256, 1), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc);
+    k_find_cuts<<<dim3((h->nf + 255) / 256, 1), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc, h->clstab);
     // test_copy_struct only re-runs get_bounds for op >= 12 (CL:2121-2126): restore the list otherwise
     CK(cudaMemcpyAsync(h->sc->valid, saved, sizeof saved, cudaMemcpyHostToDevice, h->stream));
     if (apply_and_post(h, 0, op)) return -2;
@@ -1854,7 +2072,7 @@ extern "C" int ig_full_likelihood(ig_handle* h, const float p8[8], int32_t use_s
     const int write = (use_stale_coords && h->coords_ever) ? 0 : 1;
     if (write) { h->coords_ever = true; h->coords_fresh = true; }
     k_coords<<<h->n_part_zc, IG_THREADS, 0, h->stream>>>(h->live, h->sub, h->coord, h->clen, h->ns, h->sc, mbar, 1,
-                                                        h->part_zc, h->part_nc, write);
+                                                        h->part_zc, h->part_nc, write, h->subx);
     k_reduce<<<1, 256, 0, h->stream>>>(h->part_zc, h->n_part_zc, &h->sc->full_out[1], h->part_nc, &h->sc->full_nintra);
     k_full_lnz<<<h->n_part_full, IG_THREADS, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->ns, h->sc, mbar, 1,
                                                             h->exz_test, h->part_full);

@@ -527,3 +527,97 @@ IG_HD Frag ig_eval_op(const IgDescriptor& d, int op, const Frag& f, int i) {
     Frag e = ig_extract_block(f, i, d.A, o.C, o.cut, up, d.max_id);
     return ig_insert_block(e, f, i, o.EA, d.a, o.EB, d.b, o.cut, o.valid, up);
 }
+
+// =============================================================================================
+// Rigid-motion classes.  Every op moves the fragments of the <=2 affected contigs PIECEWISE
+// RIGIDLY: between two consecutive breakpoints (the positions of A, B and the 12 cut fragments)
+// all fragments of a contig undergo the same motion (shift or reflection of start_bp / sub_pos,
+// same target contig).  A contact whose two ends undergo the same motion keeps its distance, so
+// its likelihood term cannot change mathematically -- but the reference recomputes the float32
+// coordinate start_bp/1000 + offset of every shifted sub-fragment (KA:3751), so |s_i - s_j| moves
+// by up to an ulp of the COORDINATE (not of s) and its terms pick up that noise.  The scoring kernel
+// reads a per-candidate (row class, column class) bit table saying which mutations need evaluating:
+// by default only pairs that are bit-identical are skipped (both ends at rest, or ends in two contigs
+// before and after); with rigid pruning every pair that moves rigidly together is skipped too.
+#define IG_MAX_BP 16      // contig(A): A, A+1, 6 upstream cuts, 6 downstream cuts (+1), B, B+1
+#define IG_CLS_B0 17      // first class of contig(B) when it differs from contig(A)
+#define IG_MAX_CLS 20
+#define IG_BP_NONE 0x7fffffff
+#define IG_CLS_SHIFT 24   // rowidx packs (class << 24) | index in the affected-row list
+
+struct IgSig { int id_c, flip, dbp, dsp, circ; };
+struct __attribute__((aligned(16))) IgMotion { int dbp, dsp, id_c, flip; };  // what the scoring kernel needs of IgSig
+struct IgClassTab {
+    int bp_sub[IG_MAX_BP];   // contig(A) breakpoints in sub-fragment position units (IG_BP_NONE = unused)
+    int bp_sub_b[2];         // contig(B) != contig(A)
+    int distinct_b, id_b;    // 1 when B lives in another contig; its label
+    unsigned mask[IG_MAX_CLS * IG_MAX_CLS];  // bit u set: uniq slot u must be evaluated for this class pair
+    IgMotion mot[IG_MAX_CLS * IG_N_OPS];     // [class][uniq slot]
+};
+
+// breakpoints in fragment-position units (bpf) and sub-fragment-position units (bps)
+IG_HD void ig_class_breakpoints(const IgDescriptor& d, int* bpf, int* bps, int* bpbf, int* bpbs) {
+    const int same = d.A.id_c == d.B.id_c;
+    bpf[0] = d.A.pos;     bps[0] = d.A.sub_pos;
+    bpf[1] = d.A.pos + 1; bps[1] = d.A.sub_pos + d.A.sub_len;
+    for (int i = 0; i < IG_N_CUT; i++) {
+        const IgBlockOp& up = d.blk[2 * i];
+        const IgBlockOp& dn = d.blk[2 * i + 1];
+        bpf[2 + i] = up.cut >= 0 ? up.C.pos : IG_BP_NONE;
+        bps[2 + i] = up.cut >= 0 ? up.C.sub_pos : IG_BP_NONE;
+        bpf[8 + i] = dn.cut >= 0 ? dn.C.pos + 1 : IG_BP_NONE;
+        bps[8 + i] = dn.cut >= 0 ? dn.C.sub_pos + dn.C.sub_len : IG_BP_NONE;
+    }
+    bpf[14] = same ? d.B.pos : IG_BP_NONE;     bps[14] = same ? d.B.sub_pos : IG_BP_NONE;
+    bpf[15] = same ? d.B.pos + 1 : IG_BP_NONE; bps[15] = same ? d.B.sub_pos + d.B.sub_len : IG_BP_NONE;
+    bpbf[0] = d.B.pos;     bpbs[0] = d.B.sub_pos;
+    bpbf[1] = d.B.pos + 1; bpbs[1] = d.B.sub_pos + d.B.sub_len;
+}
+IG_HD int ig_class_count(const int* bp, int n, int pos) {
+    int c = 0;
+    for (int i = 0; i < n; i++) c += (bp[i] <= pos) ? 1 : 0;
+    return c;
+}
+// class of a (sub-)fragment at position `pos` of contig `id_c` (same units as the breakpoint lists)
+IG_HD int ig_class_of(const int* bp, const int* bpb, int distinct_b, int id_b, int id_c, int pos) {
+    if (distinct_b && id_c == id_b) return IG_CLS_B0 + ig_class_count(bpb, 2, pos);
+    return ig_class_count(bp, IG_MAX_BP, pos);
+}
+// representative fragment position of class-representative `rep` (0..19), or -1 when it does not exist
+IG_HD int ig_class_rep_pos(const IgDescriptor& d, const int* bpf, const int* bpbf, int rep, int* on_b) {
+    const int distinct_b = d.A.id_c != d.B.id_c;
+    int pos, len;
+    if (rep < IG_CLS_B0) { *on_b = 0; pos = rep == 0 ? 0 : bpf[rep - 1]; len = d.A.l_cont; }
+    else { if (!distinct_b) return -1; *on_b = 1; pos = rep == IG_CLS_B0 ? 0 : bpbf[rep - IG_CLS_B0 - 1]; len = d.B.l_cont; }
+    if (pos == IG_BP_NONE || pos < 0 || pos >= len) return -1;
+    return pos;
+}
+// motion of the fragments around position `pos` of contig(A) (on_b = 0) or contig(B) under op
+IG_HD IgSig ig_class_signature(const IgDescriptor& d, int on_b, int pos, int op) {
+    const Frag& P = on_b ? d.B : d.A;
+    Frag v;
+    int i;
+    if (!on_b && pos == d.A.pos) { v = d.A; i = d.a; }
+    else if (P.id_c == d.B.id_c && pos == d.B.pos) { v = d.B; i = d.b; }
+    else {  // a virtual fragment: the motion does not depend on its own start/length
+        v = P; v.pos = pos; v.sub_pos = 0; v.start_bp = 0; v.len_bp = 1; v.sub_len = 1; v.ori = 1; v.prev = -2; v.next = -2;
+        i = -2;
+    }
+    const Frag m = ig_eval_op(d, op, v, i);
+    IgSig s;
+    s.id_c = m.id_c; s.flip = (m.ori != v.ori) ? 1 : 0; s.circ = m.circ;
+    s.dbp = s.flip ? m.start_bp + v.start_bp + v.len_bp : m.start_bp - v.start_bp;
+    s.dsp = s.flip ? m.sub_pos + v.sub_pos + v.sub_len : m.sub_pos - v.sub_pos;
+    return s;
+}
+// must uniq slot (signatures s1, s2 of the two classes) be evaluated for a contact between them?
+//   rigid = 0: skip only what is BIT-IDENTICAL to the current state (both ends do not move at all, or the
+//              ends stay in two different contigs);
+//   rigid = 1: also skip pairs whose ends undergo the same shift / reflection (distance preserved
+//              mathematically; the reference re-rounds the shifted float32 coordinates, this does not).
+IG_HD int ig_class_pair_changed(const IgSig& s1, const IgSig& s2, int cur_same, int cur_circ, int rigid) {
+    if (!cur_same) return s1.id_c == s2.id_c;   // two contigs stay two contigs: both terms are the inter-contig constant
+    if (cur_circ || s1.circ || s2.circ) return 1;
+    if (!(s1.id_c == s2.id_c && s1.flip == s2.flip && s1.dbp == s2.dbp && s1.dsp == s2.dsp)) return 1;
+    return rigid ? 0 : !(s1.flip == 0 && s1.dbp == 0 && s1.dsp == 0);
+}

@@ -75,7 +75,7 @@ class sampler:
                  np_sub_frags_2_frags, mean_squared_frags_per_bin, norm_vect_accu, sub_candidates_dup,
                  sub_candidates_output_data, S_o_A_sub_frags, sub_collector_id_repeats, sub_frag_dispatcher,
                  sparse_matrix, mean_value_trans, n_iterations, is_simu, vel, pos, device=0,
-                 compat_last_block=True, compat_int32_wrap=True):
+                 compat_last_block=True, compat_int32_wrap=True, rigid_pruning=False):
         if not use_rippe:
             raise NotImplementedError("only the Rippe p(s) model is on the live path (IG:564 use_rippe=True)")
         if len(id_frag_duplicated) or len(sub_candidates_dup) or len(id_frags_blacklisted):
@@ -147,7 +147,7 @@ class sampler:
 
         cfg = L.ig_config(device=int(device), n_frags=nf, n_sub_frags=ns, nnz=self.n_non_zero,
                           max_bounds_insert=int(self.max_bounds_insert), mean_sub_len_kb=float(self._mbar),
-                          n_pix=float(self.n_pixl_sub_mat), compat_last_block=int(bool(compat_last_block)), reserved=0)
+                          n_pix=float(self.n_pixl_sub_mat), compat_last_block=int(bool(compat_last_block)), rigid_pruning=int(bool(rigid_pruning)))
         data = L.ig_level_data(
             frags13=_ptr(self._state0), sub_parent=_ptr(self._sub_parent), sub_watson=_ptr(self._sub_watson),
             sub_crick=_ptr(self._sub_crick), sub_j=_ptr(self._sub_j), row_ptr=_ptr(self._row_ptr), col=_ptr(self._col),

@@ -21,8 +21,8 @@ def make_sampler(level, **kw):
 
 
 class GpuImpl:
-    def __init__(self, level):
-        self.s = make_sampler(level)
+    def __init__(self, level, **kw):
+        self.s = make_sampler(level, **kw)
         self.dt = np.float32(0.01)
 
     def set_state(self, st):
@@ -412,3 +412,37 @@ def test_contact_thumbnail_matches_numpy_binning(built, tmp_path):
     out = s.display_current_matrix(str(tmp_path / "m.pgm"), size=K)
     assert len(out[0]) == level.n_frags and (tmp_path / "m.pgm").stat().st_size > K * K
     s.free_gpu()
+
+
+def test_rigid_pruning_mode_differs_only_by_coordinate_rounding_noise(built):
+    """rigid_pruning=True skips contacts whose two ends undergo the same rigid motion (their term cannot
+    change mathematically); the default re-evaluates them like the reference and picks up the float32
+    re-rounding of shifted coordinates (an ulp of the COORDINATE, i.e. ~1e-5 relative on short distances).
+    The two modes must agree up to that noise and choose the same move unless two scores are that close."""
+    level = make_level(WORKLOADS["T"])
+    ss = [make_sampler(level, rigid_pruning=e) for e in (True, False)]
+    for s in ss:
+        s.set_param_simu(P8_RIPPE)
+        np.random.seed(5)
+        s.bomb_the_genome()
+    rng = np.random.RandomState(9)
+    worst_rel, n_div = 0.0, 0
+    for t in range(1500):
+        a = int(rng.randint(level.n_frags))
+        cands = [int(c) for c in rng.choice(level.n_frags, 5, replace=False) if c != a]
+        outs = [s.step_sampler(a, 5, np.float32(0.01), candidates=cands) for s in ss]
+        f, e = ss[0].all_scores.copy(), ss[1].all_scores.copy()
+        assert np.array_equal(f != 0, e != 0)
+        nz = e != 0
+        rel = float(np.max(np.abs(f[nz] - e[nz]) / np.abs(e[nz])))
+        worst_rel = max(worst_rel, rel)
+        assert rel < 2e-6, (t, rel)
+        if (outs[0][2], outs[0][3]) != (outs[1][2], outs[1][3]):
+            top = np.sort(e[nz])[-2:]
+            assert abs(top[1] - top[0]) <= 4e-6 * abs(top[1]), "diverged without a near-tie"
+            n_div += 1
+            ss[0]._set_state(ss[1]._get_state())
+            ss[0].set_valid_insert(ss[1].get_valid_insert())
+    print("rigid pruning vs default: worst relative score difference", worst_rel, "divergences", n_div)
+    for s in ss:
+        s.free_gpu()

@@ -62,6 +62,28 @@ def test_product_move_functions_vs_oracle(built, seed):
                 assert np.array_equal(out[m, i], ref[m][k]), (seed, a, b, m, k)
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_rigid_motion_classes(built, seed):
+    """Every op moves the fragments between two breakpoints rigidly: the motion of each fragment of the
+    affected contigs equals the motion of its class representative (what the scoring kernel's
+    class-pair table is built from), for linear and circular contigs, all 24 ops."""
+    lib = ctypes.CDLL(HOST_LIB)
+    rng = np.random.RandomState(500 + seed)
+    vp = ctypes.c_void_p
+    total = 0
+    for it in range(300):
+        n = int(rng.randint(2, 96 if it % 3 else 400))
+        st = random_state(n, rng)
+        max_id = int(st["id_c"].max())
+        a, b = [int(x) for x in rng.choice(n, 2, replace=False)]
+        inp = np.ascontiguousarray(np.stack([st[k] for k in mv.FIELDS]).astype(np.int32))
+        ncls, nchk = ctypes.c_int(0), ctypes.c_int(0)
+        bad = lib.ig_host_check_classes(n, inp.ctypes.data_as(vp), a, b, max_id, ctypes.byref(ncls), ctypes.byref(nchk))
+        assert bad == 0, (seed, it, n, a, b)
+        total += nchk.value
+    assert total > 10000
+
+
 def test_scaffold_invariants_after_moves():
     """SURVEY A.3 invariants hold for every op applied to a valid scaffold (linear contigs)."""
     rng = np.random.RandomState(7)
