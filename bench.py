@@ -146,7 +146,7 @@ def run_ours(args):
 
     level, t_gen = build_level(args.workload)
     p8 = params_for(level)
-    s = sampler(*level.sampler_args(), device=local)
+    s = sampler(*level.sampler_args(), device=local, rigid_pruning=bool(args.rigid_pruning))
     s.set_param_simu(p8)
     burn = args.burn_cycles if args.burn_cycles >= 0 else (2 if level.n_frags <= 5000 else 0)
     t0 = time.time()
@@ -281,7 +281,7 @@ def run_ours(args):
                                        if args.refresh_every == 1 else
                                        "maintained incrementally, full recompute every %d steps (same values up to f64 "
                                        "summation order; tests/test_gpu_parity.py)" % args.refresh_every),
-                   "cuda_graph": bool(args.graph), "full_refreshes_in_timed_region": st["full_refreshes"],
+                   "cuda_graph": bool(args.graph), "rigid_pruning": bool(args.rigid_pruning), "full_refreshes_in_timed_region": st["full_refreshes"],
                    "gather_every": args.gather_every if world > 1 else None},
         "mcmc_cycle_s": dev_ms_max / 1e3 / args.steps * level.n_frags,
         "proposals_per_step": prop_sum / world / args.steps,
@@ -437,6 +437,8 @@ def main():
     ap.add_argument("--gather-every", type=int, default=500)
     ap.add_argument("--refresh-every", type=int, default=4096)
     ap.add_argument("--graph", type=int, default=1)
+    ap.add_argument("--rigid-pruning", type=int, default=0,
+                    help="1: skip contacts whose ends move rigidly together (not the reference's float32 re-rounding; see DESIGN.md)")
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")

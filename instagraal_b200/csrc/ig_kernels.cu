@@ -39,6 +39,8 @@ struct CoordRec { float dist; int id_c; int pos; float s_tot; };          // 16 
 struct __align__(16) SubX { int start_bp; int len_ori; float watson; float crick; };  // 16 B: what a rigid motion needs to
                                                                           // recompute a sub-fragment's coordinate (len_ori = len_bp * ori)
 
+struct __align__(16) RowInfo { int r; int cls; int n; int pad; long long b; long long pad2; CoordRec ci; };  // 48 B: all
+                                   // k_score needs to start on an affected row, in one round trip
 struct CandInfo {  // per-candidate slice description (slice_sp_mat prologue, KA:526-551)
     int id_a, id_b, same, is_circ;
     int up_a, down_a, up_b, down_b;
@@ -381,7 +383,7 @@ k_find_cuts(const FragRec* __restrict__ live, int nf, DevScalars* sc, IgDescript
 //     representative, then the class-pair bit table read by k_score.  One block per candidate, on the side
 //     stream (only k_score needs the result).
 __global__ void __launch_bounds__(256)
-k_classes(const DevScalars* __restrict__ sc, const IgDescriptor* __restrict__ desc, IgClassTab* __restrict__ clstab, int rigid) {
+k_classes(const DevScalars* __restrict__ sc, const IgDescriptor* __restrict__ desc, IgClassTab* __restrict__ clstab, int rigid, float mbar) {
     const int k = blockIdx.x;
     if (k >= sc->n_cands) return;
     __shared__ IgDescriptor d;
@@ -428,6 +430,26 @@ k_classes(const DevScalars* __restrict__ sc, const IgDescriptor* __restrict__ de
                 if (ig_class_pair_changed(s_sig[c1][u], s_sig[c2][u], cur_same, cur_circ, rigid)) m |= 1u << u;
         }
         ct.mask[t] = m;
+        unsigned fo = 0;
+        if (s_have[c1] && s_have[c2])
+            for (int u = 0; u < n_uniq; u++)
+                if (ig_class_pair_far_ok(s_sig[c1][u], s_sig[c2][u])) fo |= 1u << u;
+        ct.farok[t] = fo;
+    }
+    // margin: twice the largest shift of any class under any non-reflecting mutation
+    if (threadIdx.x < 32) {
+        int mb = 0, ms = 0;
+        for (int c = threadIdx.x; c < IG_MAX_CLS; c += 32)
+            if (s_have[c])
+                for (int u = 0; u < n_uniq; u++)
+                    if (!s_sig[c][u].flip) { mb = max(mb, abs(s_sig[c][u].dbp)); ms = max(ms, abs(s_sig[c][u].dsp)); }
+        mb = __reduce_max_sync(0xffffffffu, mb);
+        ms = __reduce_max_sync(0xffffffffu, ms);
+        if (threadIdx.x == 0) {
+            const float d_max = sc->p.d_max;
+            ct.far_s = d_max + 2.0f * (__int2float_ru(mb) / 1000.0f) + 1.0f;
+            ct.far_dp = (int)ceilf(d_max / mbar) + 2 * ms + 2;
+        }
     }
 }
 
@@ -481,7 +503,7 @@ k_rows_count(const CoordRec* __restrict__ coord, int ns, DevScalars* sc, int* __
 __global__ void __launch_bounds__(IG_ROW_CHUNK)
 k_rows_write(const CoordRec* __restrict__ coord, int ns, const DevScalars* __restrict__ sc, const int* __restrict__ chunk_off,
              int n_chunks, int* __restrict__ rows, int* __restrict__ rowidx, int* __restrict__ row_cnt, int rows_stride,
-             const IgClassTab* __restrict__ clstab) {
+             const IgClassTab* __restrict__ clstab, const long long* __restrict__ row_ptr, RowInfo* __restrict__ rinfo) {
     const int k = blockIdx.y;
     if (k >= sc->n_cands) return;
     __shared__ int wsum[32];
@@ -507,6 +529,9 @@ k_rows_write(const CoordRec* __restrict__ coord, int ns, const DevScalars* __res
         rows[(size_t)k * rows_stride + off] = r;
         const int cls = ig_class_of(s_bp, s_bp + IG_MAX_BP, s_bp[IG_MAX_BP + 2], s_bp[IG_MAX_BP + 3], cr.id_c, cr.pos);
         rowidx[(size_t)k * rows_stride + r] = off | (cls << IG_CLS_SHIFT);
+        const long long b = row_ptr[r];
+        RowInfo ri; ri.r = r; ri.cls = cls; ri.n = (int)(row_ptr[r + 1] - b); ri.pad = 0; ri.b = b; ri.pad2 = 0; ri.ci = cr;
+        rinfo[(size_t)k * rows_stride + off] = ri;
         row_cnt[(size_t)k * rows_stride + off] = 0;  // k_score (block mode) accumulates into it
     }
 }
@@ -646,7 +671,12 @@ struct __align__(16) QEnt { float s; int dp; unsigned mask; int val; };  // 16 B
 
 // term of a linear-contig contact at 0 < s < d_max WITHOUT the part that depends on the observed count only
 // (it cancels in t_mut - t_cur)
-__device__ __forceinline__ void eval_queue(const QEnt* __restrict__ q, int n, double* __restrict__ my_acc, const Params& p,
+#ifdef IG_EVALQ_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+void eval_queue(const QEnt* __restrict__ q, int n, double* __restrict__ my_acc, const Params& p,
                                            double l10v, const float* __restrict__ exz_tab) {
     const int lane = threadIdx.x & 31;
     if (lane < n) {
@@ -657,6 +687,69 @@ __device__ __forceinline__ void eval_queue(const QEnt* __restrict__ q, int n, do
         double t = pxl_term(exf, (double)e.val, 0.0, l10v, p.v_inter) + (double)exz_tab[e.dp] * LOG10E_F;
         if (e.mask & IG_QSUB) t = -t;
         for (unsigned m = e.mask & 0xffffffu; m; m &= m - 1) my_acc[(__ffs(m) - 1) * IG_THREADS] += t;
+    }
+}
+
+// one selected contact as the slot loop needs it (column end + current state)
+struct Ctc { int pos, start_bp, len_ori; float watson, crick; int val; float cur_s; int cur_dp; int rjc; double t_cur; int flags; };
+                                                                                 // flags: 1 same contig now, 2 current term deferred
+
+// term of contact x under uniq slot u: returns false when it is bit-identical to the current state; otherwise
+// `add` = t_u - t_cur for the cheap cases, or push = true (s_m, dp_m to be evaluated through the queue; add = -t_cur)
+__device__ __forceinline__ bool eval_pair(const Ctc& x, int u, const RowMut a, const IgMotion* __restrict__ g_mot, float row_s_tot,
+                                          const Params& p, double l10v, double inter_const, float mbar, const float* __restrict__ exz_tab,
+                                          const RowMut* __restrict__ tab, const int* __restrict__ tlen, int ns,
+                                          float& s_m, int& dp_m, bool& push, double& add) {
+    const int4 mo4 = __ldg(reinterpret_cast<const int4*>(g_mot + (x.rjc >> IG_CLS_SHIFT) * IG_N_OPS + u));  // dbp, dsp, id_c, flip
+    const bool m_same = a.id_c == mo4.z;
+    const bool cur_same = x.flags & 1;
+    const double ob = (double)x.val;
+    double t = pxl_term(p.v_inter, ob, 0.0, l10v, p.v_inter) + inter_const;  // different contigs: both expectations are v_inter
+    if (m_same) {
+        if (a.s_tot != 0) {  // circular contig (rare): mutated column end from the table, evaluated in place
+            const int rj = x.rjc & ((1 << IG_CLS_SHIFT) - 1);
+            const RowMut bm = tab[(size_t)u * ns + rj];
+            CoordRec cim, cjm;
+            cim.dist = a.dist; cim.id_c = a.id_c; cim.pos = a.pos; cim.s_tot = a.s_tot;
+            cjm.dist = bm.dist; cjm.id_c = bm.id_c; cjm.pos = bm.pos; cjm.s_tot = bm.s_tot;
+            t = contact_term(cim, cjm, tlen[(size_t)u * ns + rj], ob, 0.0, p, l10v, mbar, exz_tab);
+        } else {
+            // the column end under this mutation: start_bp and sub-position follow the class motion
+            const int len_j = abs(x.len_ori);
+            const bool fw = (x.len_ori > 0) != (mo4.w != 0);
+            const int sb = mo4.w ? mo4.x - x.start_bp - len_j : x.start_bp + mo4.x;
+            const float dj = __int2float_rn(sb) / 1000.0f + (fw ? x.watson : x.crick);  // KA:3751
+            const int pj = mo4.w ? mo4.y - 1 - x.pos : x.pos + mo4.y;
+            s_m = fabsf(a.dist - dj);
+            dp_m = abs(a.pos - pj);
+            if (cur_same && row_s_tot == 0 && s_m == x.cur_s && dp_m == x.cur_dp) return false;  // bit-identical inputs
+            if (!((s_m > 0.0f) && (s_m < p.d_max)))
+                t = pxl_term(p.v_inter, ob, 0.0, l10v, p.v_inter) + (double)exz_tab[dp_m] * LOG10E_F;  // floor v_inter
+            else { push = true; t = 0.0; }  // needs powf + log10: queue it
+        }
+    } else if (!cur_same) return false;  // two contigs before and after
+    add = t - x.t_cur;  // t_cur = 0 while deferred
+    return true;
+}
+
+// warp-collective append to the warp's queue of expensive evaluations; a full batch of 32 is evaluated at once
+__device__ __forceinline__ void queue_push(bool push, float s, int dp, unsigned mask, int val, QEnt* __restrict__ myq, int& qn,
+                                           double* __restrict__ my_acc, const Params& p, double l10v, const float* __restrict__ exz_tab) {
+    const unsigned pm = __ballot_sync(0xffffffffu, push);
+    if (!pm) return;
+    const int lane = threadIdx.x & 31;
+    if (push) {
+        QEnt en; en.s = s; en.dp = dp; en.mask = mask; en.val = val;
+        myq[qn + __popc(pm & ((1u << lane) - 1))] = en;
+    }
+    qn += __popc(pm);
+    __syncwarp();
+    if (qn >= 32) {
+        eval_queue(myq, 32, my_acc, p, l10v, exz_tab);
+        __syncwarp();
+        if (lane < qn - 32) { const QEnt mv = myq[32 + lane]; myq[lane] = mv; }
+        qn -= 32;
+        __syncwarp();
     }
 }
 
@@ -679,7 +772,8 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
         double* __restrict__ part_nz,   // [cand][25][gridDim.x]  (24 uniq slots; slot 24 unused = 0)
         int* __restrict__ part_c,       // [cand][2][gridDim.x]   (contacts selected, contacts read)
         int gs_div,                     // work-splitting knob: split a row into slot groups while rows*groups < warps/gs_div
-        const IgClassTab* __restrict__ clstab, const SubX* __restrict__ subx)
+        const IgClassTab* __restrict__ clstab, const SubX* __restrict__ subx, const RowInfo* __restrict__ rinfo,
+        int sparse_div)                 // deal (contact, mutation) pairs to the lanes when fewer than 32/sparse_div lanes are busy
 {
     const int k = blockIdx.y;
     if (k >= sc->n_cands) return;
@@ -688,6 +782,8 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
     __shared__ int redi[IG_WARPS_PER_BLOCK][2];
     __shared__ QEnt queue[IG_WARPS_PER_BLOCK][IG_QCAP];
     __shared__ RowMut s_row[IG_WARPS_PER_BLOCK][IG_N_OPS];
+    __shared__ unsigned s_chg[IG_WARPS_PER_BLOCK][32];
+    __shared__ int s_off[IG_WARPS_PER_BLOCK][32];
     const CandInfo ci_k = sc->ci[k];
     const int n_uniq = desc_g[k].n_uniq;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -719,13 +815,15 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
     }
     const Params p = sc->p;
     const double l10v = sc->log10_vinter;
-    const unsigned lt_mask = (1u << lane) - 1;
     const unsigned* g_mask = clstab[k].mask;    // small per-candidate tables: read through L1
+    const unsigned* g_farok = clstab[k].farok;
     const IgMotion* g_mot = clstab[k].mot;
+    const float far_s = clstab[k].far_s;
+    const int far_dp = clstab[k].far_dp;
     if (lane < 25) red[w][lane] = 0.0;
     if (lane < 2) redi[w][lane] = 0;
+    for (int u = 0; u < IG_N_OPS; u++) acc_s[u * IG_THREADS + threadIdx.x] = 0.0;  // kept zero between items (see the item epilogue)
     __syncwarp();
-    const int* my_rows = rows + (size_t)k * ns;
     const int* my_idx = rowidx + (size_t)k * ns;
     int* my_cnt = row_cnt + (size_t)k * ns;
     const RowMut* tab = table + (size_t)k * IG_N_OPS * ns;
@@ -733,6 +831,8 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
     double* my_acc = acc_s + threadIdx.x;
     QEnt* myq = queue[w];
     RowMut* myrow = s_row[w];
+    unsigned* mychg = s_chg[w];
+    int* myoff = s_off[w];
     // constant term of a contact whose endpoints lie in different contigs (KA:4348-4352) minus the ob part
     const double inter_const = (double)p.v_inter * LOG10E_F;
     for (int it = it0; it < n_items; it += it_step) {
@@ -743,137 +843,134 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
         if (u0 >= n_uniq && g != 0) continue;
         const int u1 = min(u0 + gs, n_uniq);
         const unsigned gmask = (u1 > u0) ? (((1u << (u1 - u0)) - 1u) << u0) : 0u;
-        const int r = my_rows[ri];
-        const CoordRec ci = coord[r];
-        const unsigned* mrow = g_mask + (my_idx[r] >> IG_CLS_SHIFT) * IG_MAX_CLS;
-        const long long b = row_ptr[r], e = row_ptr[r + 1];
+        const RowInfo info = rinfo[(size_t)k * ns + ri];
+        const CoordRec ci = info.ci;
+        const int cls_r = info.cls;
+        const unsigned* mrow = g_mask + cls_r * IG_MAX_CLS;
+        const long long b = info.b, e = info.b + info.n;
         __syncwarp();
         if (u0 + lane < u1) myrow[lane] = tab[(size_t)(u0 + lane) * ns + ri];
-        for (int u = u0; u < u1; u++) my_acc[(u - u0) * IG_THREADS] = 0.0;
         __syncwarp();
         int row_sel = 0;
         int qn = 0;  // warp-uniform queue fill
+        unsigned touched = 0;  // slots (relative to u0) that received a term in this item
+        // the (col, val) pair and the column's coordinates are fetched one chunk ahead
+        // (only when whole rows are processed: short row parts gain nothing from it)
+        const bool ahead = parts == 1;
+        int2 c_nxt = make_int2(0, 0);
+        CoordRec cj_nxt = ci;
+        if (ahead && b + q_off + lane < e) { c_nxt = __ldg(&cv[b + q_off + lane]); cj_nxt = coord[c_nxt.x]; }
         for (long long q0 = b + q_off; q0 < e; q0 += q_step) {
             const long long q = q0 + lane;
+            int2 c = c_nxt;
+            CoordRec cj = cj_nxt;
+            if (!ahead && q < e) { c = __ldg(&cv[q]); cj = coord[c.x]; }
+            if (ahead && q + q_step < e) c_nxt = __ldg(&cv[q + q_step]);
             unsigned m = 0;
-            int2 c = make_int2(0, 0);
-            CoordRec cj = ci;
-            int rjc = 0;
+            Ctc x;
+            x.pos = 0; x.start_bp = 0; x.len_ori = 0; x.watson = 0.f; x.crick = 0.f; x.val = 0; x.cur_s = 0.f; x.cur_dp = 0;
+            x.rjc = 0; x.t_cur = 0.0; x.flags = 0;
             if (q < e) {
-                c = __ldg(&cv[q]);
-                cj = coord[c.x];
                 if ((cj.id_c == ci_k.id_a || cj.id_c == ci_k.id_b) && contact_selected(ci, cj, c.y, ci_k)) {
                     row_sel++;
-                    rjc = my_idx[c.x];
-                    m = __ldg(&mrow[rjc >> IG_CLS_SHIFT]) & gmask;
+                    x.rjc = my_idx[c.x];
+                    x.pos = cj.pos; x.val = c.y;
+                    x.cur_s = fabsf(ci.dist - cj.dist);
+                    x.cur_dp = abs(ci.pos - cj.pos);
+                    const bool cur_same = ci.id_c == cj.id_c;
+                    m = __ldg(&mrow[x.rjc >> IG_CLS_SHIFT]) & gmask;
+                    // far beyond d_max before and after: every non-reflecting mutation leaves the floor term
+#ifndef IG_NO_FAR
+                    if (m && cur_same && ci.s_tot == 0 && x.cur_s >= far_s && x.cur_dp >= far_dp)
+                        m &= ~__ldg(&g_farok[cls_r * IG_MAX_CLS + (x.rjc >> IG_CLS_SHIFT)]);
+#endif
+                    if (m) {  // current-state term of the lanes that have something to evaluate
+                        const SubX sx = subx[c.x];
+                        x.start_bp = sx.start_bp; x.len_ori = sx.len_ori; x.watson = sx.watson; x.crick = sx.crick;
+                        const double ob = (double)c.y;
+                        if (!cur_same) x.t_cur = pxl_term(p.v_inter, ob, 0.0, l10v, p.v_inter) + inter_const;
+                        else if (ci.s_tot != 0) x.t_cur = contact_term(ci, cj, clen[c.x], ob, 0.0, p, l10v, mbar, exz_tab);  // circular (rare)
+                        else if (!((x.cur_s > 0.0f) && (x.cur_s < p.d_max))) x.t_cur = pxl_term(p.v_inter, ob, 0.0, l10v, p.v_inter) + (double)exz_tab[x.cur_dp] * LOG10E_F;
+                        else x.flags |= 2;  // powf + log10: goes through the queue once, with the mask of changed slots
+                        x.flags |= cur_same ? 1 : 0;
+                    }
                 }
             }
+            if (ahead && q + q_step < e) cj_nxt = coord[c_nxt.x];
             const unsigned um = __reduce_or_sync(0xffffffffu, m);
             if (!um) continue;
-            // current-state term of the lanes that have something to evaluate
-            double ob = 0.0, t_cur = 0.0, t_inter = 0.0;
-            int cur_dp = 0;
-            float cur_s = 0.f;
-            bool cur_same = false, cur_deferred = false;
-            SubX sx = {0, 0, 0.f, 0.f};
-            if (m) {
-                sx = subx[c.x];
-                ob = (double)c.y;
-                t_inter = pxl_term(p.v_inter, ob, 0.0, l10v, p.v_inter) + inter_const;
-                cur_same = ci.id_c == cj.id_c;
-                cur_s = fabsf(ci.dist - cj.dist);
-                cur_dp = abs(ci.pos - cj.pos);
-                if (!cur_same) t_cur = t_inter;
-                else if (ci.s_tot != 0) t_cur = contact_term(ci, cj, clen[c.x], ob, 0.0, p, l10v, mbar, exz_tab);  // circular (rare)
-                else if (!((cur_s > 0.0f) && (cur_s < p.d_max))) t_cur = pxl_term(p.v_inter, ob, 0.0, l10v, p.v_inter) + (double)exz_tab[cur_dp] * LOG10E_F;
-                else cur_deferred = true;  // powf + log10: goes through the queue once, with the mask of changed slots
-            }
-            const IgMotion* mcol = g_mot + (rjc >> IG_CLS_SHIFT) * IG_N_OPS;
-            const int len_j = abs(sx.len_ori);
-            const bool fw_j = sx.len_ori > 0;
             unsigned chg = 0;
+            // number of (contact, mutation) pairs of this chunk
+            const int n_pairs = __reduce_add_sync(0xffffffffu, __popc(m));
+            if (n_pairs * sparse_div > __popc(um) * 32) {
+                // DENSE: most lanes take part in most mutations -> loop over the mutations, lane = contact
 #pragma unroll 1
-            for (unsigned uw = um; uw; uw &= uw - 1) {
-                const int u = __ffs(uw) - 1;
-                bool push = false;
-                float s_m = 0.f;
-                int dp_m = 0;
-                if ((m >> u) & 1u) {
-                    const RowMut a = myrow[u - u0];
-                    const int4 mo4 = __ldg(reinterpret_cast<const int4*>(mcol + u));
-                    IgMotion mo; mo.dbp = mo4.x; mo.dsp = mo4.y; mo.id_c = mo4.z; mo.flip = mo4.w;
-                    const bool m_same = a.id_c == mo.id_c;
-                    double t = t_inter;  // different contigs: both expectations are v_inter
-                    bool differs = true;
-                    if (m_same) {
-                        if (a.s_tot != 0) {  // circular contig (rare): mutated column end from the table, evaluated in place
-                            const int rj = rjc & ((1 << IG_CLS_SHIFT) - 1);
-                            const RowMut bm = tab[(size_t)u * ns + rj];
-                            CoordRec cim, cjm;
-                            cim.dist = a.dist; cim.id_c = a.id_c; cim.pos = a.pos; cim.s_tot = a.s_tot;
-                            cjm.dist = bm.dist; cjm.id_c = bm.id_c; cjm.pos = bm.pos; cjm.s_tot = bm.s_tot;
-                            t = contact_term(cim, cjm, tlen[(size_t)u * ns + rj], ob, 0.0, p, l10v, mbar, exz_tab);
-                        } else {
-                            // the column end under this mutation: start_bp and sub-position follow the class motion
-                            const int sb = mo.flip ? mo.dbp - sx.start_bp - len_j : sx.start_bp + mo.dbp;
-                            const float dj = __int2float_rn(sb) / 1000.0f + ((fw_j != (mo.flip != 0)) ? sx.watson : sx.crick);  // KA:3751
-                            const int pj = mo.flip ? mo.dsp - 1 - cj.pos : cj.pos + mo.dsp;
-                            s_m = fabsf(a.dist - dj);
-                            dp_m = abs(a.pos - pj);
-                            if (cur_same && ci.s_tot == 0 && s_m == cur_s && dp_m == cur_dp) differs = false;  // bit-identical inputs
-                            else if (!((s_m > 0.0f) && (s_m < p.d_max)))
-                                t = pxl_term(p.v_inter, ob, 0.0, l10v, p.v_inter) + (double)exz_tab[dp_m] * LOG10E_F;  // floor v_inter
-                            else { push = true; t = 0.0; }  // needs powf + log10: queue it
+                for (unsigned uw = um; uw; uw &= uw - 1) {
+                    const int u = __ffs(uw) - 1;
+                    float s_m = 0.f; int dp_m = 0; bool push = false;
+                    if ((m >> u) & 1u) {
+                        double add;
+                        if (eval_pair(x, u, myrow[u - u0], g_mot, ci.s_tot, p, l10v, inter_const, mbar, exz_tab, tab, tlen, ns, s_m, dp_m, push, add)) {
+                            chg |= 1u << (u - u0);
+                            my_acc[(u - u0) * IG_THREADS] += add;
                         }
-                    } else if (!cur_same) differs = false;  // two contigs before and after
-                    if (differs) {
-                        chg |= 1u << (u - u0);
-                        my_acc[(u - u0) * IG_THREADS] += t - t_cur;   // t_cur = 0 while deferred
                     }
+                    queue_push(push, s_m, dp_m, 1u << (u - u0), x.val, myq, qn, my_acc, p, l10v, exz_tab);
                 }
-                const unsigned pm = __ballot_sync(0xffffffffu, push);
-                if (pm) {
-                    if (push) {
-                        QEnt en; en.s = s_m; en.dp = dp_m; en.mask = 1u << (u - u0); en.val = c.y;
-                        myq[qn + __popc(pm & lt_mask)] = en;
+            } else {
+                // SPARSE (long contigs: only the contacts that cross a breakpoint change): the pairs are dealt
+                // densely to the lanes; the executing lane fetches the contact from its owner by shuffles
+                int pre = __popc(m);   // inclusive prefix over the lanes
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += y; }
+                __syncwarp();
+                mychg[lane] = 0; myoff[lane] = pre - __popc(m);
+                __syncwarp();
+#pragma unroll 1
+                for (int base = 0; base < n_pairs; base += 32) {
+                    const int pi = base + lane;
+                    const bool valid = pi < n_pairs;
+                    int src = 0;
+                    if (valid) {  // last lane whose exclusive offset is <= pi
+#pragma unroll
+                        for (int stp = 16; stp > 0; stp >>= 1) if (src + stp < 32 && myoff[src + stp] <= pi) src += stp;
                     }
-                    qn += __popc(pm);
-                    __syncwarp();
-                    if (qn >= 32) {
-                        eval_queue(myq, 32, my_acc, p, l10v, exz_tab);
-                        __syncwarp();
-                        if (lane < qn - 32) { const QEnt mv = myq[32 + lane]; myq[lane] = mv; }
-                        qn -= 32;
-                        __syncwarp();
+                    const unsigned msrc = __shfl_sync(0xffffffffu, m, src);
+                    Ctc y;
+                    y.pos = __shfl_sync(0xffffffffu, x.pos, src); y.start_bp = __shfl_sync(0xffffffffu, x.start_bp, src);
+                    y.len_ori = __shfl_sync(0xffffffffu, x.len_ori, src); y.watson = __shfl_sync(0xffffffffu, x.watson, src);
+                    y.crick = __shfl_sync(0xffffffffu, x.crick, src); y.val = __shfl_sync(0xffffffffu, x.val, src);
+                    y.cur_s = __shfl_sync(0xffffffffu, x.cur_s, src); y.cur_dp = __shfl_sync(0xffffffffu, x.cur_dp, src);
+                    y.rjc = __shfl_sync(0xffffffffu, x.rjc, src); y.t_cur = __shfl_sync(0xffffffffu, x.t_cur, src);
+                    y.flags = __shfl_sync(0xffffffffu, x.flags, src);
+                    float s_m = 0.f; int dp_m = 0; bool push = false;
+                    int u = u0;
+                    if (valid) {
+                        u = __fns(msrc, 0, pi - myoff[src] + 1);
+                        double add;
+                        if (eval_pair(y, u, myrow[u - u0], g_mot, ci.s_tot, p, l10v, inter_const, mbar, exz_tab, tab, tlen, ns, s_m, dp_m, push, add)) {
+                            atomicOr(&mychg[src], 1u << (u - u0));
+                            my_acc[(u - u0) * IG_THREADS] += add;
+                        }
                     }
+                    queue_push(push, s_m, dp_m, 1u << (u - u0), y.val, myq, qn, my_acc, p, l10v, exz_tab);
                 }
+                __syncwarp();
+                chg = mychg[lane];
             }
-            {   // the deferred current-state terms, subtracted from every slot that changed
-                const bool push = cur_deferred && chg;
-                const unsigned pm = __ballot_sync(0xffffffffu, push);
-                if (pm) {
-                    if (push) {
-                        QEnt en; en.s = cur_s; en.dp = cur_dp; en.mask = chg | IG_QSUB; en.val = c.y;
-                        myq[qn + __popc(pm & lt_mask)] = en;
-                    }
-                    qn += __popc(pm);
-                    __syncwarp();
-                    if (qn >= 32) {
-                        eval_queue(myq, 32, my_acc, p, l10v, exz_tab);
-                        __syncwarp();
-                        if (lane < qn - 32) { const QEnt mv = myq[32 + lane]; myq[lane] = mv; }
-                        qn -= 32;
-                        __syncwarp();
-                    }
-                }
-            }
+            // the deferred current-state terms, subtracted from every slot that changed
+            queue_push((x.flags & 2) && chg, x.cur_s, x.cur_dp, chg | IG_QSUB, x.val, myq, qn, my_acc, p, l10v, exz_tab);
+            touched |= __reduce_or_sync(0xffffffffu, chg);
         }
         if (qn > 0) { eval_queue(myq, qn, my_acc, p, l10v, exz_tab); }
         __syncwarp();
-        // fixed-order accumulation into this warp's slot sums (work items are visited in a fixed order)
-        for (int u = u0; u < u1; u++) {
-            const double v = warp_sum(my_acc[(u - u0) * IG_THREADS]);
-            if (lane == 0) red[w][u] += v;
+        // fixed-order accumulation into this warp's slot sums (work items are visited in a fixed order); only
+        // the slots that received a term are reduced, and their accumulators are put back to zero
+        for (unsigned tw = touched; tw; tw &= tw - 1) {
+            const int us = __ffs(tw) - 1;
+            const double v = warp_sum(my_acc[us * IG_THREADS]);
+            my_acc[us * IG_THREADS] = 0.0;
+            if (lane == 0) red[w][u0 + us] += v;
         }
         if (g == 0) {
             row_sel = __reduce_add_sync(0xffffffffu, row_sel);
@@ -1403,7 +1500,7 @@ struct ig_handle {
     double *part_nz, *part_z; int *part_i, *part_c;
     int grid_pre;
     RowMut* table; int *table_len, *rowidx;
-    IgClassTab* clstab; int rigid; SubX* subx;
+    IgClassTab* clstab; int rigid; SubX* subx; RowInfo* rinfo;
     double *part_full; int n_part_full;
     double *part_zc; int* part_nc; int n_part_zc;
     int *d_nuniq, *d_nsub, *d_perm;
@@ -1413,7 +1510,7 @@ struct ig_handle {
     bool params_set, coords_fresh, coords_ever;
     bool incr_valid; int refresh_every; long long steps_since_full;
     double* part_out;
-    int gs_div;
+    int gs_div, sparse_div;
     long long last_n_full;
     cudaGraphExec_t graph[4][IG_MAX_CANDS + 1];   // [full + 2 * cycle][candidates in the grid]
     int* cyc_in; CycleOut* cyc_out; int cyc_cap; bool graph_failed, capturing, use_graph; long long n_full;
@@ -1480,6 +1577,8 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
     h->params_set = false; h->coords_fresh = false; h->coords_ever = false;
     h->incr_valid = false; h->refresh_every = 4096; h->steps_since_full = 0;
     h->gs_div = 4;
+    h->sparse_div = 4;
+    if (const char* e = getenv("IG_SPARSE_DIV")) h->sparse_div = atoi(e);
     if (const char* e = getenv("IG_GS_DIV")) h->gs_div = std::max(1, atoi(e));
     if (const char* e = getenv("IG_BLOCK_MODE")) if (atoi(e)) h->gs_div = -h->gs_div;
     memset(h->graph, 0, sizeof h->graph); h->cyc_in = nullptr; h->cyc_out = nullptr; h->cyc_cap = 0; h->graph_failed = false; h->capturing = false; h->use_graph = true; h->n_full = 0;
@@ -1528,7 +1627,7 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
         if (dev_alloc(h, &h->table, (size_t)IG_MAX_CANDS * IG_N_OPS * ns)) return -2;
         if (dev_alloc(h, &h->table_len, (size_t)IG_MAX_CANDS * IG_N_OPS * ns)) return -2;
         if (dev_alloc(h, &h->rowidx, (size_t)IG_MAX_CANDS * ns)) return -2;
-        if (dev_alloc(h, &h->clstab, (size_t)IG_MAX_CANDS) || dev_alloc(h, &h->subx, (size_t)ns)) return -2;
+        if (dev_alloc(h, &h->clstab, (size_t)IG_MAX_CANDS) || dev_alloc(h, &h->subx, (size_t)ns) || dev_alloc(h, &h->rinfo, (size_t)IG_MAX_CANDS * ns)) return -2;
         h->n_part_full = sms * 8;
         if (dev_alloc(h, &h->part_full, h->n_part_full)) return -2;
         if (dev_alloc(h, &h->part_out, h->n_part_full)) return -2;
@@ -1590,7 +1689,7 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
 extern "C" void ig_destroy(ig_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
-    void* ptrs[] = {h->clstab, h->subx, h->live, h->part_out, h->part_c, h->table, h->table_len, h->rowidx, h->init_live, h->sub, h->coord, h->clen, h->row_ptr, h->cv, h->sym_diag,
+    void* ptrs[] = {h->clstab, h->subx, h->rinfo, h->live, h->part_out, h->part_c, h->table, h->table_len, h->rowidx, h->init_live, h->sub, h->coord, h->clen, h->row_ptr, h->cv, h->sym_diag,
                     h->init_prev, h->init_next, h->orientable, h->sc, h->desc, h->exz, h->exz_test, h->chunk_cnt,
                     h->rows, h->row_cnt, h->part_nz, h->part_z, h->part_i, h->part_full, h->part_zc, h->part_nc,
                     h->d_nuniq, h->d_nsub, h->d_perm, h->d_hist};
@@ -1736,17 +1835,17 @@ static int score_candidates(ig_handle* h, int a, const int32_t* cands, int n, in
     const FragRec* live = h->live;
     k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, first_flip_eject, nullptr);
     k_find_cuts<<<dim3((h->nf + 255) / 256, n), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc, h->clstab);
-    k_classes<<<n, 256, 0, h->stream>>>(h->sc, h->desc, h->clstab, h->rigid);
+    k_classes<<<n, 256, 0, h->stream>>>(h->sc, h->desc, h->clstab, h->rigid, h->cfg.mean_sub_len_kb);
     if (overlap) cudaStreamWaitEvent(h->stream, h->ev_coords, 0);
     k_rows_count<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks);
     k_rows_write<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks, h->rows,
-                                                                       h->rowidx, h->row_cnt, h->ns, h->clstab);
+                                                                       h->rowidx, h->row_cnt, h->ns, h->clstab, h->row_ptr, h->rinfo);
     k_precompute<<<dim3(h->grid_pre, n), IG_THREADS, 0, h->stream>>>(h->coord, h->clen, live, h->sub, h->sc, h->desc, h->rows, h->ns,
                                                                     h->table, h->table_len, mbar, h->part_z, h->part_i);
     if (h->profile) cudaEventRecord(h->ev[4], h->stream);
     k_score<<<dim3(h->grid_score, n), IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
                                                                  h->ns, h->row_cnt, h->table, h->table_len, mbar, h->exz, h->part_nz,
-                                                                 h->part_c, h->gs_div, h->clstab, h->subx);
+                                                                 h->part_c, h->gs_div, h->clstab, h->subx, h->rinfo, h->sparse_div);
     if (h->profile) cudaEventRecord(h->ev[5], h->stream);
     h->n_launches += 7;
     if (overlap) cudaStreamWaitEvent(h->stream, h->ev_lnz, 0);
@@ -1839,14 +1938,14 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands, int cycle = 0)
     k_find_cuts<<<dim3((h->nf + 255) / 256, n), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc, h->clstab);
     cudaEventRecord(h->ev_cuts, h->stream);
     cudaStreamWaitEvent(h->pf, h->ev_cuts, 0);
-    k_classes<<<n, 256, 0, h->pf>>>(h->sc, h->desc, h->clstab, h->rigid);   // beside the row list; k_score needs it
+    k_classes<<<n, 256, 0, h->pf>>>(h->sc, h->desc, h->clstab, h->rigid, h->cfg.mean_sub_len_kb);   // beside the row list; k_score needs it
     cudaEventRecord(h->ev_cls, h->pf);
     cudaStreamWaitEvent(h->stream, h->ev_coords, 0);
     IG_MARK(2);
     k_rows_count<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks);
     IG_MARK(3);
     k_rows_write<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks, h->rows,
-                                                                       h->rowidx, h->row_cnt, h->ns, h->clstab);
+                                                                       h->rowidx, h->row_cnt, h->ns, h->clstab, h->row_ptr, h->rinfo);
     IG_MARK(4);
     k_precompute<<<dim3(h->grid_pre, n), IG_THREADS, 0, h->stream>>>(h->coord, h->clen, live, h->sub, h->sc, h->desc, h->rows, h->ns,
                                                                     h->table, h->table_len, mbar, h->part_z, h->part_i);
@@ -1855,7 +1954,7 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands, int cycle = 0)
     IG_MARK(5);
     k_score<<<dim3(h->grid_score, n), IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
                                                                  h->ns, h->row_cnt, h->table, h->table_len, mbar, h->exz, h->part_nz,
-                                                                 h->part_c, h->gs_div, h->clstab, h->subx);
+                                                                 h->part_c, h->gs_div, h->clstab, h->subx, h->rinfo, h->sparse_div);
     if (h->profile && !h->capturing) cudaEventRecord(h->ev[5], h->stream);
     cudaStreamWaitEvent(h->stream, h->ev_lnz, 0);
     IG_MARK(6);

@@ -553,6 +553,11 @@ struct IgClassTab {
     int distinct_b, id_b;    // 1 when B lives in another contig; its label
     unsigned mask[IG_MAX_CLS * IG_MAX_CLS];  // bit u set: uniq slot u must be evaluated for this class pair
     IgMotion mot[IG_MAX_CLS * IG_N_OPS];     // [class][uniq slot]
+    // Contacts of one linear contig that lie beyond d_max both in kb (s >= far_s) and in sub-fragment separation
+    // (dp >= far_dp), with a margin for the largest shift any mutation applies, have the floor value v_inter
+    // before AND after every mutation that does not reflect either end: bit u of farok[c1][c2] marks those.
+    unsigned farok[IG_MAX_CLS * IG_MAX_CLS];
+    float far_s; int far_dp;
 };
 
 // breakpoints in fragment-position units (bpf) and sub-fragment-position units (bps)
@@ -609,6 +614,12 @@ IG_HD IgSig ig_class_signature(const IgDescriptor& d, int on_b, int pos, int op)
     s.dbp = s.flip ? m.start_bp + v.start_bp + v.len_bp : m.start_bp - v.start_bp;
     s.dsp = s.flip ? m.sub_pos + v.sub_pos + v.sub_len : m.sub_pos - v.sub_pos;
     return s;
+}
+// far-contact shortcut (see IgClassTab::farok): no reflection and no circular contig on either side, or the
+// ends land in two different contigs (inter-contig constant = the same floor value)
+IG_HD int ig_class_pair_far_ok(const IgSig& s1, const IgSig& s2) {
+    if (s1.id_c != s2.id_c) return 1;
+    return s1.flip == 0 && s2.flip == 0 && s1.circ == 0 && s2.circ == 0;
 }
 // must uniq slot (signatures s1, s2 of the two classes) be evaluated for a contact between them?
 //   rigid = 0: skip only what is BIT-IDENTICAL to the current state (both ends do not move at all, or the
