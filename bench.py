@@ -238,6 +238,18 @@ def run_ours(args):
     cyc_prop = float(cyc["n_proposals"].sum())
     st3 = s.get_stats(reset=True)
 
+    # ---------------- pass 4: the same with the neighbour draws made on the device (production RNG mode)
+    s.run_cycle_device(frag_stream(8), 5, seed=7 + rank, cycle=0)   # uploads the neighbour weights, builds graphs
+    s.get_stats(reset=True)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    cycd = s.run_cycle_device(frag_stream(args.steps), 5, seed=7 + rank, cycle=1)
+    t_cycd = time.perf_counter() - t0
+    cycd_prop = float(cycd["n_proposals"].sum())
+    st4 = s.get_stats(reset=True)
+
     # ---------------- aggregate over ranks (max time, summed proposals)
     vals = np.array([dev_ms, proposals, t_e2e, st2["proposals"], t_wall], dtype=np.float64)
     if dist is not None:
@@ -292,6 +304,10 @@ def run_ours(args):
                           "device_ms_per_step": st3["ms_step"] / args.steps,
                           "note": "sampler.run_cycle: host draws every step's neighbours (reference RNG order), uploads the "
                                   "plan once, the GPU replays one CUDA graph per step without host synchronisation"},
+        "e2e_cycle_device_rng": {"value": cycd_prop / t_cycd, "unit": "proposals/s", "ms_per_step": t_cycd / args.steps * 1e3,
+                                 "device_ms_per_step": st4["ms_step"] / args.steps,
+                                 "note": "sampler.run_cycle_device: the host uploads the visiting order only; candidates are "
+                                         "drawn on the GPU (Philox4x32-10), steps replay as CUDA graphs"},
         "gpu_launches": int(st["launches"]),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach[dom], "peak": peak, "unit": "GB/s",
                      "frac": ach[dom] / peak, "traffic": measured_traffic(args.workload, dom), "peak_source": peak_src,

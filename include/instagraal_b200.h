@@ -107,6 +107,16 @@ int ig_step(ig_handle* h, int32_t id_frag, const int32_t* cands, int32_t n_cands
  * synchronisation in between; cands8 = [n_steps][IG_MAX_CANDS] sorted candidates, n_cands = [n_steps]. */
 int ig_run_cycle(ig_handle* h, int32_t n_steps, const int32_t* frags, const int32_t* cands8, const int32_t* n_cands,
                  ig_cycle_step* out);
+/* Production RNG mode (SURVEY 8b "RNG contract"): the neighbour draws of return_neighbours (CL:3103-3141) on the
+ * device.  ig_set_neighbour_weights uploads setup_distri_frags (CL:3053-3101) as a CSR: for fragment f the
+ * candidates idx[ptr[f]..ptr[f+1]) (f itself excluded), the running sum cdf of their probabilities pk and the
+ * number of non-zero pk.  ig_run_cycle_device = ig_run_cycle with every step's candidates drawn by one kernel
+ * (Philox4x32-10, key = seed, counter = (step, cycle, draw, attempt); successive draws without replacement,
+ * sorted, A dropped): no per-step host work at all.  ig_get_cycle_plan returns what was drawn. */
+int ig_set_neighbour_weights(ig_handle* h, const int64_t* ptr, const int32_t* idx, const double* cdf, const int32_t* n_nonzero);
+int ig_run_cycle_device(ig_handle* h, int32_t n_steps, const int32_t* frags, int32_t n_neighbours, uint64_t seed,
+                        uint32_t cycle, ig_cycle_step* out);
+int ig_get_cycle_plan(ig_handle* h, int32_t n_steps, int32_t* out /* [n_steps][2 + IG_MAX_CANDS] */);
 /* eval = score every mutation of one (A,B) pair without applying: extract_uniq_mutations +
  * perform_mutations + slice_sparse_mat + extract_current_sub_likelihood + eval_all_sub_likelihood
  * (CL:1417-1431).  Refreshes the coordinates / full likelihood like the head of step_sampler. */

@@ -21,7 +21,8 @@ EXPORTS = (
     "ig_create", "ig_destroy", "ig_last_error", "ig_device_count", "ig_set_params", "ig_get_state",
     "ig_set_state", "ig_get_valid_insert", "ig_set_valid_insert", "ig_bomb", "ig_step", "ig_eval_scores",
     "ig_apply", "ig_full_likelihood", "ig_distance_histogram", "ig_set_sym_diag", "ig_device_state_ptr",
-    "ig_set_profiling", "ig_get_stats", "ig_set_options", "ig_get_full_refresh_count", "ig_get_kernel_times", "ig_run_cycle", "ig_contact_thumbnail",
+    "ig_set_profiling", "ig_get_stats", "ig_set_options", "ig_get_full_refresh_count", "ig_get_kernel_times", "ig_run_cycle", "ig_contact_thumbnail", "ig_set_neighbour_weights",
+           "ig_run_cycle_device", "ig_get_cycle_plan",
 )
 
 
@@ -90,6 +91,9 @@ def lib():
         L.ig_get_kernel_times.argtypes = [vp, vp, i32]
         L.ig_run_cycle.argtypes = [vp, i32, vp, vp, vp, vp]
         L.ig_contact_thumbnail.argtypes = [vp, vp, i32, vp]
+        L.ig_set_neighbour_weights.argtypes = [vp, vp, vp, vp, vp]
+        L.ig_run_cycle_device.argtypes = [vp, i32, vp, i32, C.c_uint64, C.c_uint32, vp]
+        L.ig_get_cycle_plan.argtypes = [vp, i32, vp]
         L.ig_get_full_refresh_count.argtypes = [vp, C.POINTER(i64)]
         for name in EXPORTS:
             if name not in ("ig_destroy", "ig_last_error"):

@@ -1475,6 +1475,87 @@ k_thumbnail(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Production RNG mode: the neighbour draws of a whole cycle on the device.
+// Philox4x32-10 keyed by the seed, counter = (step, cycle, draw index, attempt); one thread per step.
+// Distribution = return_neighbours (CL:3103-3141): min(delta, #non-zero weights) fragments drawn without
+// replacement with probability proportional to the level's contact counts (successive draws, a drawn
+// fragment is rejected when drawn again), or `delta` distinct uniform fragments when A has no neighbour;
+// then sorted (CL:1404) and A itself dropped.  The stream differs from NumPy's by design
+// (the tests hold a NumPy restatement of this kernel).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+__device__ __forceinline__ double philox_uniform(unsigned step, unsigned cycle, unsigned draw, unsigned attempt, uint2 key) {
+    const uint4 r = philox4x32_10(make_uint4(step, cycle, draw, attempt), key);
+    const unsigned long long bits = ((unsigned long long)r.x << 32) | r.y;
+    return (double)(bits >> 11) * (1.0 / 9007199254740992.0);  // 53 bits -> [0, 1)
+}
+__global__ void k_draw_plan(int* __restrict__ plan, const int* __restrict__ frags, int n_steps, int delta, int nf,
+                            const long long* __restrict__ nb_ptr, const int* __restrict__ nb_idx, const double* __restrict__ nb_cdf,
+                            const int* __restrict__ nb_nnz, unsigned seed_lo, unsigned seed_hi, unsigned cycle) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_steps) return;
+    const uint2 key = make_uint2(seed_lo, seed_hi);
+    const int a = frags[t];
+    const long long b = nb_ptr[a], e = nb_ptr[a + 1];
+    const int len = (int)(e - b);
+    int got[IG_MAX_CANDS];
+    int n = 0;
+    if (len > 0) {
+        const int n_max = min(delta, nb_nnz[a]);
+        const double total = nb_cdf[e - 1];
+        for (int i = 0; i < n_max; i++) {
+            int pick = -1;
+            for (unsigned att = 0; att < 256u && pick < 0; att++) {
+                const double u = philox_uniform((unsigned)t, cycle, (unsigned)i, att, key) * total;
+                int lo = 0, hi = len - 1;  // first j with cdf[j] > u
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (nb_cdf[b + mid] > u) hi = mid; else lo = mid + 1; }
+                const int c = nb_idx[b + lo];
+                bool dup = false;
+                for (int j = 0; j < n; j++) dup |= (got[j] == c);
+                if (!dup) pick = c;
+            }
+            if (pick < 0) {  // a weight so dominant that 256 redraws all hit it: take the first free non-zero entry
+                for (int j = 0; j < len && pick < 0; j++) {
+                    const double wj = nb_cdf[b + j] - (j ? nb_cdf[b + j - 1] : 0.0);
+                    const int c = nb_idx[b + j];
+                    bool dup = false;
+                    for (int q = 0; q < n; q++) dup |= (got[q] == c);
+                    if (wj > 0.0 && !dup) pick = c;
+                }
+            }
+            if (pick >= 0) got[n++] = pick;
+        }
+    } else {
+        const int n_max = min(delta, nf - 1);
+        for (int i = 0; i < n_max; i++) {
+            int pick = -1;
+            for (unsigned att = 0; att < 256u && pick < 0; att++) {
+                const int c = min(nf - 1, (int)(philox_uniform((unsigned)t, cycle, (unsigned)i, att, key) * (double)nf));
+                bool dup = (c == a);
+                for (int j = 0; j < n; j++) dup |= (got[j] == c);
+                if (!dup) pick = c;
+            }
+            if (pick >= 0) got[n++] = pick;
+        }
+    }
+    // sorted, without A itself
+    for (int i = 1; i < n; i++) { const int v = got[i]; int j = i - 1; while (j >= 0 && got[j] > v) { got[j + 1] = got[j]; j--; } got[j + 1] = v; }
+    int* p = plan + (size_t)t * (2 + IG_MAX_CANDS);
+    int m = 0;
+    for (int i = 0; i < n; i++) if (got[i] != a) p[2 + m++] = got[i];
+    for (int i = m; i < IG_MAX_CANDS; i++) p[2 + i] = 0;
+    p[0] = m; p[1] = a;
+}
+
 // ================================================================================================
 // host side
 struct ig_handle {
@@ -1501,6 +1582,7 @@ struct ig_handle {
     int grid_pre;
     RowMut* table; int *table_len, *rowidx;
     IgClassTab* clstab; int rigid; SubX* subx; RowInfo* rinfo;
+    long long* nb_ptr; int* nb_idx; double* nb_cdf; int* nb_nnz; int* cyc_frags;
     double *part_full; int n_part_full;
     double *part_zc; int* part_nc; int n_part_zc;
     int *d_nuniq, *d_nsub, *d_perm;
@@ -1581,7 +1663,8 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
     if (const char* e = getenv("IG_SPARSE_DIV")) h->sparse_div = atoi(e);
     if (const char* e = getenv("IG_GS_DIV")) h->gs_div = std::max(1, atoi(e));
     if (const char* e = getenv("IG_BLOCK_MODE")) if (atoi(e)) h->gs_div = -h->gs_div;
-    memset(h->graph, 0, sizeof h->graph); h->cyc_in = nullptr; h->cyc_out = nullptr; h->cyc_cap = 0; h->graph_failed = false; h->capturing = false; h->use_graph = true; h->n_full = 0;
+    memset(h->graph, 0, sizeof h->graph); h->cyc_in = nullptr; h->cyc_out = nullptr; h->cyc_frags = nullptr; h->cyc_cap = 0;
+    h->nb_ptr = nullptr; h->nb_idx = nullptr; h->nb_cdf = nullptr; h->nb_nnz = nullptr; h->graph_failed = false; h->capturing = false; h->use_graph = true; h->n_full = 0;
     cudaError_t e0 = cudaSetDevice(cfg->device);
     if (e0 != cudaSuccess) { g_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e0); delete h; return -2; }
 #define CKC(x) do { int r_ = (x); if (r_) { g_err = h->err; ig_destroy(h); return r_; } } while (0)
@@ -1689,7 +1772,7 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
 extern "C" void ig_destroy(ig_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
-    void* ptrs[] = {h->clstab, h->subx, h->rinfo, h->live, h->part_out, h->part_c, h->table, h->table_len, h->rowidx, h->init_live, h->sub, h->coord, h->clen, h->row_ptr, h->cv, h->sym_diag,
+    void* ptrs[] = {h->clstab, h->subx, h->rinfo, h->nb_ptr, h->nb_idx, h->nb_cdf, h->nb_nnz, h->cyc_frags, h->live, h->part_out, h->part_c, h->table, h->table_len, h->rowidx, h->init_live, h->sub, h->coord, h->clen, h->row_ptr, h->cv, h->sym_diag,
                     h->init_prev, h->init_next, h->orientable, h->sc, h->desc, h->exz, h->exz_test, h->chunk_cnt,
                     h->rows, h->row_cnt, h->part_nz, h->part_z, h->part_i, h->part_full, h->part_zc, h->part_nc,
                     h->d_nuniq, h->d_nsub, h->d_perm, h->d_hist};
@@ -2053,6 +2136,61 @@ extern "C" int ig_step(ig_handle* h, int32_t id_frag, const int32_t* cands, int3
 // RNG calls, which do not depend on the chain state), every step is one CUDA-graph replay that reads its
 // plan entry and writes a compact record on the device, and the host synchronises once at the end.
 // Semantically identical to n_steps calls of ig_step (IG.full_em inner loop, instagraal.py:217-241).
+static int cycle_buffers(ig_handle* h, int n_steps) {
+    if (n_steps > h->cyc_cap) {
+        if (h->cyc_in) cudaFree(h->cyc_in);
+        if (h->cyc_out) cudaFree(h->cyc_out);
+        if (h->cyc_frags) cudaFree(h->cyc_frags);
+        h->cyc_in = nullptr; h->cyc_out = nullptr; h->cyc_frags = nullptr; h->cyc_cap = 0;
+        for (int i = 2; i < 4; i++) for (int j = 0; j <= IG_MAX_CANDS; j++) if (h->graph[i][j]) { cudaGraphExecDestroy(h->graph[i][j]); h->graph[i][j] = nullptr; }  // pointers are baked in
+        if (dev_alloc(h, &h->cyc_in, (size_t)n_steps * (2 + IG_MAX_CANDS)) || dev_alloc(h, &h->cyc_out, (size_t)n_steps) ||
+            dev_alloc(h, &h->cyc_frags, (size_t)n_steps)) return -2;
+        h->cyc_cap = n_steps;
+    }
+    return 0;
+}
+
+// replay n_steps steps from the plan in h->cyc_in (already on the device, or being written by an earlier kernel of
+// the stream); grid_n(t) = number of candidate slots the step's grid is built for
+template <class GridN>
+static int run_plan(ig_handle* h, int n_steps, GridN grid_n, ig_cycle_step* out) {
+    CK(cudaMemsetAsync(&h->sc->step_idx, 0, sizeof(int), h->stream));
+    cudaEventRecord(h->ev[0], h->stream);
+    for (int t = 0; t < n_steps; t++) {
+        const int full = (!h->incr_valid || (h->refresh_every > 0 && h->steps_since_full >= h->refresh_every)) ? 1 : 0;
+        cudaGraphExec_t ge = nullptr;
+        if (h->use_graph) get_graph(h, full, &ge, 1, grid_n(t));
+        if (ge) { CK(cudaGraphLaunch(ge, h->stream)); }
+        else if (enqueue_step(h, full, grid_n(t), 1)) return -2;
+        h->steps_since_full = full ? 1 : h->steps_since_full + 1;
+        h->n_full += full;
+        h->incr_valid = true;
+        h->n_launches += (full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR) - (h->rigid ? 1 : 0) + (h->prefetch ? 1 : 0);
+    }
+    cudaEventRecord(h->ev[1], h->stream);
+    std::vector<CycleOut> res(n_steps);
+    std::vector<int> plan((size_t)n_steps * (2 + IG_MAX_CANDS));
+    CK(cudaMemcpyAsync(res.data(), h->cyc_out, sizeof(CycleOut) * n_steps, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(plan.data(), h->cyc_in, plan.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->coords_fresh = false; h->coords_ever = true;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->ms_step += ms;
+    h->n_steps += n_steps;
+    for (int t = 0; t < n_steps; t++) {
+        const CycleOut& r = res[t];
+        const int* pl = &plan[(size_t)t * (2 + IG_MAX_CANDS)];
+        ig_cycle_step& o = out[t];
+        o.likelihood = r.likelihood; o.lnz_full = r.lnz_full;
+        o.dist = (3.0 * h->nf - 0.5 * (double)r.dist_half) / (3.0 * h->nf);
+        o.sum_l_cont = r.sum_l_cont; o.n_contigs = r.n_heads; o.op_sampled = r.win_op; o.cand_index = r.win_cand;
+        o.id_f_sampled = pl[2 + r.win_cand];
+        o.q4_hits = r.q4_hits; o.n_proposals = 0;
+        for (int i = 0; i < pl[0]; i++) o.n_proposals += r.n_uniq[i];
+    }
+    return 0;
+}
+
 extern "C" int ig_run_cycle(ig_handle* h, int32_t n_steps, const int32_t* frags, const int32_t* cands8, const int32_t* n_cands,
                             ig_cycle_step* out) {
     if (use(h)) return -1;
@@ -2070,46 +2208,56 @@ extern "C" int ig_run_cycle(ig_handle* h, int32_t n_steps, const int32_t* frags,
             p[2 + i] = c;
         }
     }
-    if (n_steps > h->cyc_cap) {
-        if (h->cyc_in) cudaFree(h->cyc_in);
-        if (h->cyc_out) cudaFree(h->cyc_out);
-        h->cyc_in = nullptr; h->cyc_out = nullptr; h->cyc_cap = 0;
-        for (int i = 2; i < 4; i++) for (int j = 0; j <= IG_MAX_CANDS; j++) if (h->graph[i][j]) { cudaGraphExecDestroy(h->graph[i][j]); h->graph[i][j] = nullptr; }  // pointers are baked in
-        if (dev_alloc(h, &h->cyc_in, (size_t)n_steps * (2 + IG_MAX_CANDS)) || dev_alloc(h, &h->cyc_out, (size_t)n_steps)) return -2;
-        h->cyc_cap = n_steps;
-    }
+    if (cycle_buffers(h, n_steps)) return -2;
     CK(cudaMemcpyAsync(h->cyc_in, plan.data(), plan.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemsetAsync(&h->sc->step_idx, 0, sizeof(int), h->stream));
-    cudaEventRecord(h->ev[0], h->stream);
-    for (int t = 0; t < n_steps; t++) {
-        const int full = (!h->incr_valid || (h->refresh_every > 0 && h->steps_since_full >= h->refresh_every)) ? 1 : 0;
-        cudaGraphExec_t ge = nullptr;
-        if (h->use_graph) get_graph(h, full, &ge, 1, n_cands[t]);
-        if (ge) { CK(cudaGraphLaunch(ge, h->stream)); }
-        else if (enqueue_step(h, full, n_cands[t], 1)) return -2;
-        h->steps_since_full = full ? 1 : h->steps_since_full + 1;
-        h->n_full += full;
-        h->incr_valid = true;
-        h->n_launches += (full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR) - (h->rigid ? 1 : 0) + (h->prefetch ? 1 : 0);
+    return run_plan(h, n_steps, [&](int t) { return n_cands[t]; }, out);
+}
+
+// setup_distri_frags (CL:3053-3101) on the device: per fragment the candidate fragments (self excluded), the
+// running sum of their probabilities pk, and the number of non-zero pk (CL:3113).
+extern "C" int ig_set_neighbour_weights(ig_handle* h, const int64_t* ptr, const int32_t* idx, const double* cdf, const int32_t* n_nonzero) {
+    if (use(h)) return -1;
+    if (!ptr || !n_nonzero) { h->err = "ig_set_neighbour_weights: null argument"; return -1; }
+    const size_t n = (size_t)ptr[h->nf];
+    for (void* q : {(void*)h->nb_ptr, (void*)h->nb_idx, (void*)h->nb_cdf, (void*)h->nb_nnz}) if (q) cudaFree(q);
+    h->nb_ptr = nullptr; h->nb_idx = nullptr; h->nb_cdf = nullptr; h->nb_nnz = nullptr;
+    if (dev_alloc(h, &h->nb_ptr, (size_t)h->nf + 1) || dev_alloc(h, &h->nb_idx, n + 1) || dev_alloc(h, &h->nb_cdf, n + 1) ||
+        dev_alloc(h, &h->nb_nnz, (size_t)h->nf)) return -2;
+    CK(cudaMemcpy(h->nb_ptr, ptr, sizeof(long long) * ((size_t)h->nf + 1), cudaMemcpyHostToDevice));
+    if (n) {
+        CK(cudaMemcpy(h->nb_idx, idx, sizeof(int) * n, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->nb_cdf, cdf, sizeof(double) * n, cudaMemcpyHostToDevice));
     }
-    cudaEventRecord(h->ev[1], h->stream);
-    std::vector<CycleOut> res(n_steps);
-    CK(cudaMemcpyAsync(res.data(), h->cyc_out, sizeof(CycleOut) * n_steps, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    h->coords_fresh = false; h->coords_ever = true;
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->ms_step += ms;
-    h->n_steps += n_steps;
-    for (int t = 0; t < n_steps; t++) {
-        const CycleOut& r = res[t];
-        ig_cycle_step& o = out[t];
-        o.likelihood = r.likelihood; o.lnz_full = r.lnz_full;
-        o.dist = (3.0 * h->nf - 0.5 * (double)r.dist_half) / (3.0 * h->nf);
-        o.sum_l_cont = r.sum_l_cont; o.n_contigs = r.n_heads; o.op_sampled = r.win_op; o.cand_index = r.win_cand;
-        o.id_f_sampled = cands8[(size_t)t * IG_MAX_CANDS + r.win_cand];
-        o.q4_hits = r.q4_hits; o.n_proposals = 0;
-        for (int i = 0; i < n_cands[t]; i++) o.n_proposals += r.n_uniq[i];
-    }
+    CK(cudaMemcpy(h->nb_nnz, n_nonzero, sizeof(int) * (size_t)h->nf, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// One sweep of step_sampler over `frags` with the neighbour draws made ON THE DEVICE (Philox4x32-10 keyed by
+// (seed, cycle, step, draw)): the host uploads the visiting order, one kernel draws every step's candidates,
+// then the steps replay without host synchronisation.  Needs ig_set_neighbour_weights.
+extern "C" int ig_run_cycle_device(ig_handle* h, int32_t n_steps, const int32_t* frags, int32_t n_neighbours, uint64_t seed,
+                                   uint32_t cycle, ig_cycle_step* out) {
+    if (use(h)) return -1;
+    if (!h->params_set) { h->err = "ig_run_cycle_device: parameters not set"; return -1; }
+    if (!h->nb_ptr) { h->err = "ig_run_cycle_device: neighbour weights not set (ig_set_neighbour_weights)"; return -1; }
+    if (n_neighbours <= 0 || n_neighbours > IG_MAX_CANDS) { h->err = "ig_run_cycle_device: n_neighbours out of range"; return -1; }
+    if (h->nf < 2) { h->err = "ig_run_cycle_device: needs at least two fragments"; return -1; }
+    if (n_steps <= 0) return 0;
+    for (int t = 0; t < n_steps; t++) if (frags[t] < 0 || frags[t] >= h->nf) { h->err = "ig_run_cycle_device: fragment out of range"; return -1; }
+    if (cycle_buffers(h, n_steps)) return -2;
+    CK(cudaMemcpyAsync(h->cyc_frags, frags, sizeof(int) * (size_t)n_steps, cudaMemcpyHostToDevice, h->stream));
+    k_draw_plan<<<(n_steps + 127) / 128, 128, 0, h->stream>>>(h->cyc_in, h->cyc_frags, n_steps, n_neighbours, h->nf, h->nb_ptr, h->nb_idx,
+                                                            h->nb_cdf, h->nb_nnz, (unsigned)(seed & 0xffffffffu), (unsigned)(seed >> 32), cycle);
+    if (launch_ok(h, "draw_plan")) return -2;
+    h->n_launches += 1;
+    return run_plan(h, n_steps, [&](int) { return (int)n_neighbours; }, out);
+}
+
+// download the plan of the last cycle ([n_steps][2 + IG_MAX_CANDS]: n_cands, fragment, candidates) -- tests / logging
+extern "C" int ig_get_cycle_plan(ig_handle* h, int32_t n_steps, int32_t* out) {
+    if (use(h)) return -1;
+    if (n_steps > h->cyc_cap) { h->err = "ig_get_cycle_plan: no such plan"; return -1; }
+    CK(cudaMemcpy(out, h->cyc_in, sizeof(int) * (size_t)n_steps * (2 + IG_MAX_CANDS), cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -385,6 +385,55 @@ class sampler:
             self.candidates = c8[-1, :nc[-1]].tolist()
         return out
 
+    def neighbour_weights_csr(self):
+        """setup_distri_frags (CL:3053-3101) as the CSR ig_set_neighbour_weights takes: (ptr int64[NF+1], idx int32,
+        cdf float64 = running sum of pk per fragment, n_nonzero int32[NF])."""
+        nf = int(self.n_frags)
+        ptr = np.zeros(nf + 1, dtype=np.int64)
+        idx, cdf = [], []
+        nnz = np.zeros(nf, dtype=np.int32)
+        for i in range(nf):
+            d = self.distri_frags[i]
+            if d["distri"] is not None:
+                pk = np.asarray(d["pk"], dtype=np.float64)
+                idx.append(np.asarray(d["xk"], dtype=np.int32))
+                cdf.append(np.cumsum(pk))
+                nnz[i] = int(np.count_nonzero(pk))
+                ptr[i + 1] = ptr[i] + len(pk)
+            else:
+                ptr[i + 1] = ptr[i]
+        idx = np.ascontiguousarray(np.concatenate(idx) if idx else np.zeros(0, np.int32), dtype=np.int32)
+        cdf = np.ascontiguousarray(np.concatenate(cdf) if cdf else np.zeros(0, np.float64), dtype=np.float64)
+        return ptr, idx, cdf, nnz
+
+    def run_cycle_device(self, list_frags, n_neighbours=5, seed=0, cycle=0):
+        """Production RNG mode: like run_cycle, but every step's neighbours are drawn ON THE DEVICE (Philox4x32-10
+        keyed by (seed, cycle, step, draw); same distribution as return_neighbours, a different random stream than
+        NumPy's).  The host only provides the visiting order (np.random.shuffle in full_em, IG:213)."""
+        if not getattr(self, "_nb_uploaded", False):
+            ptr, idx, cdf, nnz = self.neighbour_weights_csr()
+            L.check(self._h, L.lib().ig_set_neighbour_weights(self._h, _ptr(ptr), _ptr(idx), _ptr(cdf), _ptr(nnz)),
+                    "ig_set_neighbour_weights")
+            self._nb_uploaded = True
+        n = len(list_frags)
+        frags = np.ascontiguousarray(list_frags, dtype=np.int32)
+        out = np.zeros(n, dtype=L.CYCLE_DTYPE)
+        L.check(self._h, L.lib().ig_run_cycle_device(self._h, n, _ptr(frags), int(n_neighbours), int(seed), int(cycle), _ptr(out)),
+                "ig_run_cycle_device")
+        if n:
+            last = out[-1]
+            self.n_contigs = np.int32(last["n_contigs"])
+            self.mean_length_contigs = np.float32(last["sum_l_cont"]) / np.float32(last["n_contigs"])
+            self.likelihood_t = self.o = np.float64(last["likelihood"])
+            self.n_proposals_scored += int(out["n_proposals"].sum())
+        return out
+
+    def last_cycle_plan(self, n_steps):
+        """(n_cands, fragment, candidates[8]) per step of the last run_cycle / run_cycle_device call."""
+        plan = np.zeros((int(n_steps), 2 + L.IG_MAX_CANDS), dtype=np.int32)
+        L.check(self._h, L.lib().ig_get_cycle_plan(self._h, int(n_steps), _ptr(plan)), "ig_get_cycle_plan")
+        return plan
+
     def eval_likelihood(self):
         """CL:1245-1294: refresh the coordinates and the full non-zero likelihood of the live scaffold."""
         out = np.zeros(3, dtype=np.float64)

@@ -446,3 +446,36 @@ def test_rigid_pruning_mode_differs_only_by_coordinate_rounding_noise(built):
     print("rigid pruning vs default: worst relative score difference", worst_rel, "divergences", n_div)
     for s in ss:
         s.free_gpu()
+
+
+def test_device_rng_cycle_matches_oracle_plan_and_host_plan_run(built):
+    """Production RNG mode: the candidates drawn on the device (Philox4x32-10) equal the NumPy restatement
+    (oracle/device_rng.py) draw for draw, and the chain they drive is bit-identical to run_cycle fed with
+    that plan from the host."""
+    from oracle.device_rng import draw_plan
+    level = make_level(WORKLOADS["toy"])
+    a, b = make_sampler(level), make_sampler(level)
+    for s in (a, b):
+        s.set_param_simu(P8_RIPPE)
+        np.random.seed(4)
+        s.bomb_the_genome()
+    rng = np.random.RandomState(21)
+    seed = 0x1234_5678_9ABC_DEF0
+    for cyc in range(2):
+        frags = rng.permutation(level.n_frags).astype(np.int32)
+        out_dev = a.run_cycle_device(frags, 5, seed=seed, cycle=cyc)
+        plan = a.last_cycle_plan(len(frags))
+        ptr, idx, cdf, nnz = a.neighbour_weights_csr()
+        want = draw_plan(frags, 5, level.n_frags, ptr, idx, cdf, nnz, seed, cyc)
+        assert np.array_equal(plan, want)
+        assert plan[:, 0].min() >= 1 and plan[:, 0].max() <= 5
+        cands = [plan[t, 2:2 + plan[t, 0]].tolist() for t in range(len(frags))]
+        out_host = b.run_cycle(frags, 5, candidates=cands)
+        for f in ("op_sampled", "id_f_sampled", "n_contigs", "sum_l_cont", "n_proposals", "likelihood", "dist"):
+            assert np.array_equal(out_dev[f], out_host[f]), f
+        assert np.array_equal(a._get_state(), b._get_state())
+    # a different seed gives a different plan; draws are proportional to the weights
+    a.run_cycle_device(frags, 5, seed=seed + 1, cycle=0)
+    assert not np.array_equal(a.last_cycle_plan(len(frags)), plan)
+    for s in (a, b):
+        s.free_gpu()

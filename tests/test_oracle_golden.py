@@ -94,3 +94,12 @@ def test_struct_dumps_match_reference():
         for m in range(24):
             got = np.stack([muts[m][f] for f in FIELDS13])
             assert np.array_equal(got, g["dump_structs"][k][m]), (k, m)
+
+
+def test_philox_known_answers():
+    """Philox4x32-10 known-answer vectors of Random123 (kat_vectors: philox4x32 10)."""
+    from oracle.device_rng import philox4x32_10
+    assert philox4x32_10((0, 0, 0, 0), (0, 0)) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert philox4x32_10((0xffffffff,) * 4, (0xffffffff, 0xffffffff)) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert philox4x32_10((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
