@@ -31,6 +31,7 @@
 #define IG_WARPS_PER_BLOCK 8
 #define IG_THREADS (IG_WARPS_PER_BLOCK * 32)
 #define IG_ROW_CHUNK 1024
+#define IG_ROWS_SMALL_CHUNKS 16  // levels of up to 16 Ki sub-fragments build the affected-row list in one launch
 #define IG_LANE_CUR 24  // lane that owns the current-state zero term in the score kernel
 
 struct Params { float kuhn, lm, c1, slope, d, d_max, fact, v_inter; };  // KA:91-100
@@ -382,7 +383,7 @@ k_find_cuts(const FragRec* __restrict__ live, int nf, DevScalars* sc, IgDescript
 // K4: rigid-motion classes of each candidate (ig_moves.cuh): one motion per (class, uniq slot) from a class
 //     representative, then the class-pair bit table read by k_score.  One block per candidate, on the side
 //     stream (only k_score needs the result).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(IG_N_OPS * 32)
 k_classes(const DevScalars* __restrict__ sc, const IgDescriptor* __restrict__ desc, IgClassTab* __restrict__ clstab, int rigid, float mbar) {
     const int k = blockIdx.x;
     if (k >= sc->n_cands) return;
@@ -536,6 +537,51 @@ k_rows_write(const CoordRec* __restrict__ coord, int ns, const DevScalars* __res
     }
 }
 
+// K5-7 for small levels (a handful of row chunks): count + scan + write in ONE launch, one block per candidate
+// walking the chunks with a running offset (saves a dependent launch of the step's chain).
+__global__ void __launch_bounds__(IG_ROW_CHUNK)
+k_rows_small(const CoordRec* __restrict__ coord, int ns, DevScalars* sc, int n_chunks, int* __restrict__ rows,
+             int* __restrict__ rowidx, int* __restrict__ row_cnt, int rows_stride, const IgClassTab* __restrict__ clstab,
+             const long long* __restrict__ row_ptr, RowInfo* __restrict__ rinfo) {
+    const int k = blockIdx.x;
+    if (k >= sc->n_cands) return;
+    __shared__ int wsum[32];
+    __shared__ int s_bp[IG_MAX_BP + 4];
+    if (threadIdx.x < IG_MAX_BP + 4) s_bp[threadIdx.x] = reinterpret_cast<const int*>(clstab + k)[threadIdx.x];
+    const CandInfo ci_k = sc->ci[k];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int base = 0;
+    for (int ch = 0; ch < n_chunks; ch++) {
+        const int r = ch * IG_ROW_CHUNK + threadIdx.x;
+        CoordRec cr;
+        if (r < ns) cr = coord[r];
+        const bool f = r < ns && row_affected(cr, ci_k);
+        const unsigned b = __ballot_sync(0xffffffffu, f);
+        __syncthreads();   // wsum of the previous chunk fully consumed
+        if (lane == 0) wsum[w] = __popc(b);
+        __syncthreads();
+        if (w == 0) {
+            int s = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+            wsum[lane] = s;
+        }
+        __syncthreads();
+        if (f) {
+            const int off = base + (w ? wsum[w - 1] : 0) + __popc(b & ((1u << lane) - 1));
+            rows[(size_t)k * rows_stride + off] = r;
+            const int cls = ig_class_of(s_bp, s_bp + IG_MAX_BP, s_bp[IG_MAX_BP + 2], s_bp[IG_MAX_BP + 3], cr.id_c, cr.pos);
+            rowidx[(size_t)k * rows_stride + r] = off | (cls << IG_CLS_SHIFT);
+            const long long rb = row_ptr[r];
+            RowInfo ri; ri.r = r; ri.cls = cls; ri.n = (int)(row_ptr[r + 1] - rb); ri.pad = 0; ri.b = rb; ri.pad2 = 0; ri.ci = cr;
+            rinfo[(size_t)k * rows_stride + off] = ri;
+            row_cnt[(size_t)k * rows_stride + off] = 0;
+        }
+        base += wsum[31];
+    }
+    if (threadIdx.x == 0) sc->ci[k].n_rows = base;
+}
+
 // ------------------------------------------------------------------------------------------------
 // slice_sp_mat membership of one contact (KA:557-606, incl. the precedence quirk Q11 and dat>0)
 __device__ __forceinline__ bool contact_selected(const CoordRec& ci, const CoordRec& cj, int val, const CandInfo& c) {
@@ -557,8 +603,9 @@ struct RowMut { float dist; int id_c; int pos; float s_tot; };  // one sub-fragm
 // K8a: mutated coordinates of every affected sub-fragment under every scored mutation, evaluated
 //      ONCE per (row, mutation) (replaces fill_vect_dist x24, KA:3699-3760) + the zero terms
 //      (eval_all_likelihood_on_zero_1st, KA:3919-4002) restricted to the affected contigs.
-//      Block per tile of 32 affected rows (lane = row), warp w = uniq slots w, w+8, w+16 (+ the current state).
-__global__ void __launch_bounds__(IG_THREADS)
+//      Block (25 warps) per tile of 32 affected rows (lane = row), warp w = uniq slot w, warp 24 = the current state.
+#define IG_PRE_THREADS (25 * 32)
+__global__ void __launch_bounds__(IG_PRE_THREADS)
 k_precompute(const CoordRec* __restrict__ coord, const int* __restrict__ clen, const FragRec* __restrict__ live,
              const SubRec* __restrict__ sub, const DevScalars* __restrict__ sc, const IgDescriptor* __restrict__ desc_g,
              const int* __restrict__ rows, int ns, RowMut* __restrict__ table, int* __restrict__ table_len, float mbar,
@@ -576,36 +623,31 @@ k_precompute(const CoordRec* __restrict__ coord, const int* __restrict__ clen, c
         return;
     }
     __shared__ IgDescriptor d;
-    __shared__ double red[IG_WARPS_PER_BLOCK][4];   // warp w owns slots w, w + 8, w + 16 (and 24 = current state for w = 0)
-    __shared__ int redi[IG_WARPS_PER_BLOCK][4];
+    __shared__ double red[25];   // warp w owns uniq slot w (warp 24: the current state)
+    __shared__ int redi[25];
     {
         const int* src = reinterpret_cast<const int*>(desc_g + k);
         int* dst = reinterpret_cast<int*>(&d);
         for (int i = threadIdx.x; i < (int)(sizeof(IgDescriptor) / 4); i += blockDim.x) dst[i] = src[i];
     }
-    if (threadIdx.x < IG_WARPS_PER_BLOCK * 4) { (&red[0][0])[threadIdx.x] = 0.0; (&redi[0][0])[threadIdx.x] = 0; }
+    if (threadIdx.x < 25) { red[threadIdx.x] = 0.0; redi[threadIdx.x] = 0; }
     __syncthreads();
     const Params p = sc->p;
     const int n_uniq = d.n_uniq;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, slot = threadIdx.x >> 5;
     const int* my_rows = rows + (size_t)k * ns;
-    // a block takes tiles of 32 rows (lane = row); each warp evaluates ITS slots for the tile, so the op is
+    // a block takes tiles of 32 rows (lane = row); warp w evaluates uniq slot w for the tile, so the op is
     // warp-uniform (no divergence between the 24 move functions) and the table writes are coalesced
-    for (int tile = blockIdx.x; tile * 32 < n_rows; tile += gridDim.x) {
-        const int ri = tile * 32 + lane;
-        const bool valid = ri < n_rows;
-        const int r = valid ? my_rows[ri] : 0;
-        SubRec si = {0, 0.f, 0.f, 0};
-        Frag fi = d.A;
-        if (valid) { si = sub[r]; fi = live[si.parent].f; }
-#pragma unroll 1
-        for (int j = 0; j < 4; j++) {
-            const int slot = w + IG_WARPS_PER_BLOCK * j;
-            if (slot > 24 || (slot >= n_uniq && slot != 24)) continue;
+    if (slot < n_uniq || slot == 24) {
+        for (int tile = blockIdx.x; tile * 32 < n_rows; tile += gridDim.x) {
+            const int ri = tile * 32 + lane;
             double z = 0.0;
             int ia = 0;
-            if (valid) {
+            if (ri < n_rows) {
+                const int r = my_rows[ri];
                 if (slot < 24) {
+                    const SubRec si = sub[r];
+                    const Frag fi = live[si.parent].f;
                     const Frag fm = ig_eval_op(d, d.uniq[slot], fi, si.parent);
                     int len;
                     const CoordRec c = coords_of(fm, si, &len);
@@ -623,20 +665,20 @@ k_precompute(const CoordRec* __restrict__ coord, const int* __restrict__ clen, c
             }
             z = warp_sum(z);
             ia = __reduce_add_sync(0xffffffffu, ia);
-            if (lane == 0) { red[w][j] += z; redi[w][j] += ia; }   // tiles are visited in a fixed order
+            if (lane == 0) { red[slot] += z; redi[slot] += ia; }   // tiles are visited in a fixed order
         }
     }
     __syncthreads();
     if (threadIdx.x < 25) {
-        const int ww = threadIdx.x % IG_WARPS_PER_BLOCK, j = threadIdx.x / IG_WARPS_PER_BLOCK;
-        part_z[PART_IDX(k, 25, threadIdx.x, gridDim.x, blockIdx.x)] = red[ww][j];
-        part_i[PART_IDX(k, 25, threadIdx.x, gridDim.x, blockIdx.x)] = redi[ww][j];
+        part_z[PART_IDX(k, 25, threadIdx.x, gridDim.x, blockIdx.x)] = red[threadIdx.x];
+        part_i[PART_IDX(k, 25, threadIdx.x, gridDim.x, blockIdx.x)] = redi[threadIdx.x];
     }
 }
 
-// L2 prefetch of the level's arrays at the start of a step, when they fit the L2 comfortably (yeast-scale
-// levels): a step is a chain of a dozen short dependent kernels, each of which would otherwise take its
-// first-touch misses to HBM one latency at a time.  Runs beside the candidate setup on its own stream.
+// Optional (IG_PREFETCH=1) L2 prefetch of the level's arrays at the start of a step, when they fit the L2
+// comfortably (yeast-scale levels): a step is a chain of a dozen short dependent kernels, each of which takes its
+// first-touch misses to HBM one latency at a time when the L2 is cold.  Measured on T: +1.5 % with the L2 flushed
+// between steps, -3 % when steps run back to back (warm L2, the production case) -- hence off by default.
 struct PfList { const char* p[12]; unsigned long long n[12]; int cnt; };
 __global__ void k_prefetch_l2(PfList L) {
     for (int a = 0; a < L.cnt; a++) {
@@ -804,6 +846,7 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
         if (ci_k.n_rows < want) gs = (ci_k.n_rows * 4 >= want) ? 6 : ((ci_k.n_rows * 8 >= want) ? 3 : 1);
         if (ci_k.n_rows * (IG_N_OPS / gs) * 2 <= nw) parts = 2;
         if (ci_k.n_rows * (IG_N_OPS / gs) * 4 <= nw) parts = 4;
+        if (sparse_div >> 16) { gs = (sparse_div >> 16) & 0xff; parts = (sparse_div >> 24) & 0xff; }  // experiments: forced split
     }
     const int ng = IG_N_OPS / gs;
     const int n_items = ci_k.n_rows * ng * parts;
@@ -902,7 +945,7 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
             unsigned chg = 0;
             // number of (contact, mutation) pairs of this chunk
             const int n_pairs = __reduce_add_sync(0xffffffffu, __popc(m));
-            if (n_pairs * sparse_div > __popc(um) * 32) {
+            if (n_pairs * (sparse_div & 0xffff) > __popc(um) * 32) {
                 // DENSE: most lanes take part in most mutations -> loop over the mutations, lane = contact
 #pragma unroll 1
                 for (unsigned uw = um; uw; uw &= uw - 1) {
@@ -1660,7 +1703,11 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
     h->incr_valid = false; h->refresh_every = 4096; h->steps_since_full = 0;
     h->gs_div = 4;
     h->sparse_div = 4;
-    if (const char* e = getenv("IG_SPARSE_DIV")) h->sparse_div = atoi(e);
+    if (const char* e = getenv("IG_SPARSE_DIV")) h->sparse_div = atoi(e) & 0xffff;
+    if (const char* e = getenv("IG_FORCE_SPLIT")) {  // "gs,parts" (experiments)
+        int g = 0, pp = 0;
+        if (sscanf(e, "%d,%d", &g, &pp) == 2 && g > 0 && pp > 0 && IG_N_OPS % g == 0) h->sparse_div |= (g << 16) | (pp << 24);
+    }
     if (const char* e = getenv("IG_GS_DIV")) h->gs_div = std::max(1, atoi(e));
     if (const char* e = getenv("IG_BLOCK_MODE")) if (atoi(e)) h->gs_div = -h->gs_div;
     memset(h->graph, 0, sizeof h->graph); h->cyc_in = nullptr; h->cyc_out = nullptr; h->cyc_frags = nullptr; h->cyc_cap = 0;
@@ -1697,11 +1744,11 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
         const int sms = prop.multiProcessorCount;
         h->grid_score = sms * 3;  // 3 resident CTAs of 8 warps per SM (launch bounds, 48 KB dynamic smem each)
         CK(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IG_SCORE_SMEM));
-        h->grid_pre = sms * 2;
+        h->grid_pre = sms * 2;   // 2 resident CTAs of 25 warps per SM
         {
             const char* e = getenv("IG_PREFETCH");
             const size_t bytes = sizeof(int2) * (size_t)h->nnz + 64 * (size_t)ns + 80 * (size_t)nf;
-            h->prefetch = e ? (atoi(e) != 0) : (bytes <= ((size_t)48 << 20));
+            h->prefetch = e ? (atoi(e) != 0 && bytes <= ((size_t)48 << 20)) : false;
         }
         if (dev_alloc(h, &h->part_nz, (size_t)IG_MAX_CANDS * h->grid_score * 25)) return -2;
         if (dev_alloc(h, &h->part_c, (size_t)IG_MAX_CANDS * h->grid_score * 2)) return -2;
@@ -1918,12 +1965,17 @@ static int score_candidates(ig_handle* h, int a, const int32_t* cands, int n, in
     const FragRec* live = h->live;
     k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, first_flip_eject, nullptr);
     k_find_cuts<<<dim3((h->nf + 255) / 256, n), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc, h->clstab);
-    k_classes<<<n, 256, 0, h->stream>>>(h->sc, h->desc, h->clstab, h->rigid, h->cfg.mean_sub_len_kb);
+    k_classes<<<n, IG_N_OPS * 32, 0, h->stream>>>(h->sc, h->desc, h->clstab, h->rigid, h->cfg.mean_sub_len_kb);
     if (overlap) cudaStreamWaitEvent(h->stream, h->ev_coords, 0);
-    k_rows_count<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks);
-    k_rows_write<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks, h->rows,
-                                                                       h->rowidx, h->row_cnt, h->ns, h->clstab, h->row_ptr, h->rinfo);
-    k_precompute<<<dim3(h->grid_pre, n), IG_THREADS, 0, h->stream>>>(h->coord, h->clen, live, h->sub, h->sc, h->desc, h->rows, h->ns,
+    if (h->n_chunks <= IG_ROWS_SMALL_CHUNKS) {
+        k_rows_small<<<n, IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->n_chunks, h->rows, h->rowidx, h->row_cnt, h->ns,
+                                                        h->clstab, h->row_ptr, h->rinfo);
+    } else {
+        k_rows_count<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks);
+        k_rows_write<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks, h->rows,
+                                                                           h->rowidx, h->row_cnt, h->ns, h->clstab, h->row_ptr, h->rinfo);
+    }
+    k_precompute<<<dim3(h->grid_pre, n), IG_PRE_THREADS, 0, h->stream>>>(h->coord, h->clen, live, h->sub, h->sc, h->desc, h->rows, h->ns,
                                                                     h->table, h->table_len, mbar, h->part_z, h->part_i);
     if (h->profile) cudaEventRecord(h->ev[4], h->stream);
     k_score<<<dim3(h->grid_score, n), IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
@@ -2021,16 +2073,22 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands, int cycle = 0)
     k_find_cuts<<<dim3((h->nf + 255) / 256, n), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc, h->clstab);
     cudaEventRecord(h->ev_cuts, h->stream);
     cudaStreamWaitEvent(h->pf, h->ev_cuts, 0);
-    k_classes<<<n, 256, 0, h->pf>>>(h->sc, h->desc, h->clstab, h->rigid, h->cfg.mean_sub_len_kb);   // beside the row list; k_score needs it
+    k_classes<<<n, IG_N_OPS * 32, 0, h->pf>>>(h->sc, h->desc, h->clstab, h->rigid, h->cfg.mean_sub_len_kb);   // beside the row list; k_score needs it
     cudaEventRecord(h->ev_cls, h->pf);
     cudaStreamWaitEvent(h->stream, h->ev_coords, 0);
     IG_MARK(2);
-    k_rows_count<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks);
-    IG_MARK(3);
-    k_rows_write<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks, h->rows,
-                                                                       h->rowidx, h->row_cnt, h->ns, h->clstab, h->row_ptr, h->rinfo);
+    if (h->n_chunks <= IG_ROWS_SMALL_CHUNKS) {
+        IG_MARK(3);
+        k_rows_small<<<n, IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->n_chunks, h->rows, h->rowidx, h->row_cnt, h->ns,
+                                                        h->clstab, h->row_ptr, h->rinfo);
+    } else {
+        k_rows_count<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks);
+        IG_MARK(3);
+        k_rows_write<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks, h->rows,
+                                                                           h->rowidx, h->row_cnt, h->ns, h->clstab, h->row_ptr, h->rinfo);
+    }
     IG_MARK(4);
-    k_precompute<<<dim3(h->grid_pre, n), IG_THREADS, 0, h->stream>>>(h->coord, h->clen, live, h->sub, h->sc, h->desc, h->rows, h->ns,
+    k_precompute<<<dim3(h->grid_pre, n), IG_PRE_THREADS, 0, h->stream>>>(h->coord, h->clen, live, h->sub, h->sc, h->desc, h->rows, h->ns,
                                                                     h->table, h->table_len, mbar, h->part_z, h->part_i);
     if (h->profile && !h->capturing) cudaEventRecord(h->ev[4], h->stream);
     cudaStreamWaitEvent(h->stream, h->ev_cls, 0);
@@ -2112,7 +2170,7 @@ extern "C" int ig_step(ig_handle* h, int32_t id_frag, const int32_t* cands, int3
     }
     cudaEventRecord(h->ev[1], h->stream);
     CK(cudaStreamSynchronize(h->stream));
-    h->n_launches += (full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR) - (h->rigid ? 1 : 0) + (h->prefetch ? 1 : 0);
+    h->n_launches += (full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR) - (h->rigid ? 1 : 0) + (h->prefetch ? 1 : 0) - (h->n_chunks <= IG_ROWS_SMALL_CHUNKS ? 1 : 0);
     h->steps_since_full = full ? 1 : h->steps_since_full + 1;
     h->n_full += full;
     h->incr_valid = true;
@@ -2165,7 +2223,7 @@ static int run_plan(ig_handle* h, int n_steps, GridN grid_n, ig_cycle_step* out)
         h->steps_since_full = full ? 1 : h->steps_since_full + 1;
         h->n_full += full;
         h->incr_valid = true;
-        h->n_launches += (full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR) - (h->rigid ? 1 : 0) + (h->prefetch ? 1 : 0);
+        h->n_launches += (full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR) - (h->rigid ? 1 : 0) + (h->prefetch ? 1 : 0) - (h->n_chunks <= IG_ROWS_SMALL_CHUNKS ? 1 : 0);
     }
     cudaEventRecord(h->ev[1], h->stream);
     std::vector<CycleOut> res(n_steps);
