@@ -47,8 +47,11 @@ class GpuImpl:
         return dict(scores=self.s.all_scores, op=r[2], B=r[3], o=r[0], dist=r[1], mean_len=r[4], n_contigs=r[5])
 
 
+@pytest.mark.parametrize("split", ["", "24,1"])
 @pytest.mark.parametrize("name", GOLDEN_CASES)
-def test_cuda_replays_reference_trajectory(built, name):
+def test_cuda_replays_reference_trajectory(built, name, split, monkeypatch):
+    if split:
+        monkeypatch.setenv("IG_FORCE_SPLIT", split)
     g = load_golden(name)
     level = make_level(WORKLOADS[str(g["workload"])])
     impl = GpuImpl(level)
@@ -65,12 +68,17 @@ def _oracle(level, p8):
     return OracleSampler(level, p8)
 
 
+@pytest.mark.parametrize("split", ["", "24,1", "6,4"])
 @pytest.mark.parametrize("seed", [0, 1, 2])
-def test_cuda_vs_oracle_random_scaffolds_with_circular_contigs(built, seed):
+def test_cuda_vs_oracle_random_scaffolds_with_circular_contigs(built, seed, split, monkeypatch):
     """eval (score) + apply on random scaffolds the trajectories never reach (circular contigs,
-    reversed fragments), every op forced once through ig_apply."""
+    reversed fragments), every op forced once through ig_apply.  `split` forces the scoring kernel's work
+    split (all 24 mutations per item = the large-assembly path with one evaluation per group of identical
+    motions; 6 mutations x 4 row parts = the small-assembly path), which small test levels would not reach."""
     from oracle import moves as mv
     from oracle.fuzz import random_state
+    if split:
+        monkeypatch.setenv("IG_FORCE_SPLIT", split)
     level = make_level(WORKLOADS["micro"])
     rng = np.random.RandomState(seed)
     s = make_sampler(level)
