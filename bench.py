@@ -334,7 +334,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def _oracle_chain(level, p8, state13, seed, budget_s):
+def _oracle_chain(level, p8, state13, seed, budget_s, max_steps=None, warm=0):
     from oracle.sampler_oracle import OracleSampler
     from instagraal_b200._lib import FIELDS13
     o = OracleSampler(level, p8)
@@ -343,13 +343,15 @@ def _oracle_chain(level, p8, state13, seed, budget_s):
     np.random.seed(seed)
     frs = np.arange(level.n_frags)
     np.random.shuffle(frs)
+    for f in frs[:warm]:
+        o.step_sampler(int(f), 5)
     t0 = time.perf_counter()
     n_prop = n_steps = 0
-    for f in frs:
+    for f in frs[warm:]:
         o.step_sampler(int(f), 5)
         n_prop += int(sum(o.n_uniq_list))
         n_steps += 1
-        if time.perf_counter() - t0 > budget_s:
+        if time.perf_counter() - t0 > budget_s or (max_steps is not None and n_steps >= max_steps):
             break
     return n_prop, n_steps, time.perf_counter() - t0
 
@@ -396,15 +398,17 @@ def ref_gpu_baseline(level, p8, state13, budget_s, device=0):
 
 
 def _ref_worker(a):
-    name, seed, budget = a
+    name, seed, budget, max_steps, warm = a
     level, _ = build_level(name)
     p8 = params_for(level)
-    return _oracle_chain(level, p8, None, seed, budget)
+    return _oracle_chain(level, p8, None, seed, budget, max_steps, warm)
 
 
 def run_reference(args):
     """CPU arm: the reference's algorithm (oracle port: NumPy transcription of its kernels + its
-    orchestration) on every host core, one independent chain per process."""
+    orchestration) on every host core, one independent chain per process.  A "step" of this arm is one
+    step_sampler call on every core; at most --steps of them are timed after min(--warmup, 2) untimed ones, and
+    the sample is cut at --cpu-budget-s seconds so the run stays bounded whatever K is."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -414,7 +418,8 @@ def run_reference(args):
     level, _ = build_level(args.workload)
     t0 = time.perf_counter()
     with mp.get_context("fork").Pool(cores) as pool:
-        res = pool.map(_ref_worker, [(args.workload, 100 + i, budget) for i in range(cores)])
+        warm = max(0, min(args.warmup, 2))
+        res = pool.map(_ref_worker, [(args.workload, 100 + i, budget, args.steps, warm) for i in range(cores)])
     wall = time.perf_counter() - t0
     n_prop = sum(r[0] for r in res)
     n_steps = sum(r[1] for r in res)
@@ -422,14 +427,16 @@ def run_reference(args):
     v = n_prop / t_max
     out = {
         "metric": "delta-log-L proposals scored per second (MCMC step_sampler, pyramid level 4)",
-        "value": v, "unit": "proposals/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": n_steps,
-        "warmup": 0, "ms_per_step": t_max / max(n_steps / cores, 1) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "value": v, "unit": "proposals/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": max(r[1] for r in res), "warmup": warm, "requested_steps": args.steps, "requested_warmup": args.warmup,
+        "ms_per_step": t_max / max(n_steps / cores, 1) * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 expected contacts / f64 accumulation / int32 scaffold", "data": "synthetic",
         "impl": "reference",
         "config": {"workload": args.workload, "n_frags": level.n_frags, "n_sub_frags": level.n_sub_frags,
                    "chains": cores, "n_neighbours": 5,
                    "note": "the reference is GPU-only (pycuda); this arm is its algorithm transcribed to NumPy (oracle/), "
-                           "one chain per host core from the contig-order start"},
+                           "one chain per host core from the contig-order start (the in-arm cpu_baseline of the GPU arm "
+                           "times the same port on the GPU arm's burnt-in scaffold: same rate per core)"},
         "cpu_baseline": {"value": v, "unit": "proposals/s", "cores": cores, "kind": "port",
                          "sample": "%d processes x %.0f s of step_sampler calls (%d steps, %d proposals), wall %.1f s"
                                    % (cores, budget, n_steps, n_prop, wall)},
