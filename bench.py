@@ -109,9 +109,9 @@ def measured_traffic(workload, kernel):
 
 
 def build_level(name):
-    from instagraal_b200.synth import WORKLOADS, make_level
+    from instagraal_b200.synth import WORKLOADS, make_level, make_workload
     t0 = time.time()
-    level = make_level(WORKLOADS[name])
+    level = make_workload(name)
     return level, time.time() - t0
 
 

@@ -160,23 +160,42 @@ def _soa(contig_of, len_bp, sub_len):
     return {k: np.ascontiguousarray(v, dtype=np.int32) for k, v in d.items()}
 
 
-def make_level(spec: SynthSpec) -> LevelData:
+def load_geometry(path):
+    """Fragment geometry of a real digested assembly (written by oracle/make_yeast_toy.py from the reference's
+    tests/data contigs): fragments per contig, sub-fragments per fragment, sub-fragment lengths, true layout."""
+    z = np.load(path)
+    order = np.lexsort((z["contig_start"], z["contig_chrom"]))   # contigs along the true genome
+    return {"sizes": z["frags_per_contig"].astype(np.int64), "sub_len": z["frag_nsub"].astype(np.int64),
+            "sub_len_bp": z["sub_len_bp"].astype(np.int64), "order": order.astype(np.int64),
+            "chrom_of_rank": z["contig_chrom"][order].astype(np.int64)}
+
+
+def make_level(spec: SynthSpec, geometry=None) -> LevelData:
     rng = np.random.RandomState(spec.seed)
-    nf, nc = int(spec.n_frags), int(spec.n_contigs)
-    assert nc >= 1 and nf >= nc
-    # ---- initial contigs: log-normal lengths (in fragments), each >= 1
-    w = rng.lognormal(0.0, 0.6, nc)
-    sizes = np.maximum(1, np.floor(w / w.sum() * nf)).astype(np.int64)
-    while sizes.sum() > nf:
-        sizes[np.argmax(sizes)] -= 1
-    sizes[np.argmax(sizes)] += nf - sizes.sum()
-    contig_of = np.repeat(np.arange(1, nc + 1), sizes)
-    # ---- sub-fragments: 3 per fragment, last fragment of each contig 1..3
-    sub_len = np.full(nf, 3, dtype=np.int64)
-    last_idx = np.cumsum(sizes) - 1
-    sub_len[last_idx] = rng.randint(1, 4, nc)
-    ns = int(sub_len.sum())
-    sub_len_bp = np.maximum(200, rng.lognormal(np.log(spec.mean_sub_len_bp), spec.sigma_sub_len, ns)).astype(np.int64)
+    if geometry is not None:
+        sizes = np.asarray(geometry["sizes"], dtype=np.int64)
+        nf, nc = int(sizes.sum()), int(sizes.size)
+        contig_of = np.repeat(np.arange(1, nc + 1), sizes)
+        sub_len = np.asarray(geometry["sub_len"], dtype=np.int64)
+        ns = int(sub_len.sum())
+        sub_len_bp = np.asarray(geometry["sub_len_bp"], dtype=np.int64)
+        assert sub_len.size == nf and sub_len_bp.size == ns
+    else:
+        nf, nc = int(spec.n_frags), int(spec.n_contigs)
+        assert nc >= 1 and nf >= nc
+        # ---- initial contigs: log-normal lengths (in fragments), each >= 1
+        w = rng.lognormal(0.0, 0.6, nc)
+        sizes = np.maximum(1, np.floor(w / w.sum() * nf)).astype(np.int64)
+        while sizes.sum() > nf:
+            sizes[np.argmax(sizes)] -= 1
+        sizes[np.argmax(sizes)] += nf - sizes.sum()
+        contig_of = np.repeat(np.arange(1, nc + 1), sizes)
+        # ---- sub-fragments: 3 per fragment, last fragment of each contig 1..3
+        sub_len = np.full(nf, 3, dtype=np.int64)
+        last_idx = np.cumsum(sizes) - 1
+        sub_len[last_idx] = rng.randint(1, 4, nc)
+        ns = int(sub_len.sum())
+        sub_len_bp = np.maximum(200, rng.lognormal(np.log(spec.mean_sub_len_bp), spec.sigma_sub_len, ns)).astype(np.int64)
     parent = np.repeat(np.arange(nf), sub_len)
     first_sub = np.cumsum(sub_len) - sub_len
     j_in_parent = np.arange(ns) - first_sub[parent]
@@ -224,10 +243,14 @@ def make_level(spec: SynthSpec) -> LevelData:
     #      (what the sampler sees) is a shuffled / partly reversed version of the truth.
     order = np.arange(nc)
     flip = np.zeros(nc, dtype=bool)
-    if spec.shuffle_contigs:
-        order = rng.permutation(nc)
-        flip = rng.rand(nc) < 0.5
-    chrom_of_contig = np.sort(rng.randint(0, spec.n_chrom, nc))  # in true order
+    if geometry is not None:
+        order = np.asarray(geometry["order"], dtype=np.int64)
+        chrom_of_contig = np.asarray(geometry["chrom_of_rank"], dtype=np.int64)
+    else:
+        if spec.shuffle_contigs:
+            order = rng.permutation(nc)
+            flip = rng.rand(nc) < 0.5
+        chrom_of_contig = np.sort(rng.randint(0, spec.n_chrom, nc))  # in true order
     sub_first_of_contig = np.cumsum(np.add.reduceat(sub_len, np.cumsum(sizes) - sizes)) - np.add.reduceat(
         sub_len, np.cumsum(sizes) - sizes)
     sub_count_of_contig = np.add.reduceat(sub_len, np.cumsum(sizes) - sizes)
@@ -320,7 +343,20 @@ def make_level(spec: SynthSpec) -> LevelData:
 
 # Named workloads.  T = toy/yeast-like level 4; Y3 = yeast level 3;
 # G = ~1 Gb synthetic (1e5 fragments, ~3e5 sub-fragments, ~1e8 contacts).
+YEAST_TOY_GEOMETRY = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)),
+                                                "..", "tests", "golden", "yeast_toy_geometry.npz")
+
+
+def make_workload(name):
+    """Named workload -> LevelData.  "yeast_toy" = BASELINE.json configs[0]: the reference's tests/data contigs
+    digested with DpnII + HinfI and binned to level 4 (geometry fixture), contacts simulated with seed 0."""
+    if name == "yeast_toy":
+        return make_level(WORKLOADS["yeast_toy"], load_geometry(YEAST_TOY_GEOMETRY))
+    return make_level(WORKLOADS[name])
+
+
 WORKLOADS = {
+    "yeast_toy": SynthSpec(max_offset=800, lambda1=300.0, trans_per_row=40.0, seed=0),
     "micro": SynthSpec(n_frags=40, n_contigs=5, n_chrom=2, max_offset=60, lambda1=20.0, seed=1),
     "toy": SynthSpec(n_frags=150, n_contigs=10, n_chrom=3, max_offset=200, lambda1=25.0, seed=42),
     "T": SynthSpec(n_frags=900, n_contigs=146, n_chrom=16, max_offset=800, lambda1=300.0, trans_per_row=40.0, seed=42),

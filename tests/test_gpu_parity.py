@@ -487,3 +487,14 @@ def test_device_rng_cycle_matches_oracle_plan_and_host_plan_run(built):
     assert not np.array_equal(a.last_cycle_plan(len(frags)), plan)
     for s in (a, b):
         s.free_gpu()
+
+
+def test_yeast_toy_config0_lockstep(built):
+    """BASELINE.json configs[0]: the reference's tests/data contigs digested (DpnII + HinfI) and binned to
+    level 4 (1015 fragments / 2857 sub-fragments, 146 contigs incl. single-fragment ones with 1-2
+    sub-fragments), simulated contacts; product and oracle in lockstep from the contig-order start."""
+    from instagraal_b200.synth import make_workload
+    level = make_workload("yeast_toy")
+    assert (level.n_frags, level.n_sub_frags) == (1015, 2857)
+    ties = _lockstep(level, P8_RIPPE, 40, seed=2)
+    assert ties <= 8

@@ -1,3 +1,4 @@
+import os
 """Pins the oracle (oracle/*.py, NumPy restatement) against golden vectors recorded from the
 UNMODIFIED reference sampler running on the CPU emulation of its own kernels
 (oracle/make_golden.py).  CPU only."""
@@ -103,3 +104,29 @@ def test_philox_known_answers():
     assert philox4x32_10((0xffffffff,) * 4, (0xffffffff, 0xffffffff)) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     assert philox4x32_10((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == \
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_yeast_toy_config0_oracle_cycle_sample():
+    """BASELINE.json configs[0] on the CPU: geometry fixture of the reference's tests/data contigs (75,032
+    restriction fragments -> 1015 level-4 fragments), every move of a few steps of one cycle scored by the
+    NumPy transcription."""
+    import numpy as np
+    from instagraal_b200.synth import make_workload
+    from oracle.sampler_oracle import OracleSampler
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "yeast_toy_geometry.npz"))
+    assert int(z["n_level0"]) == 75032 and len(z["contig_names"]) == 146
+    level = make_workload("yeast_toy")
+    assert (level.n_frags, level.n_sub_frags) == (1015, 2857)
+    assert 1.5e6 < level.sparse_matrix.sum() < 3.5e6      # "~2 M pairs"
+    p8 = np.array([50.0, 9.6, np.float32(0.53 * (9.6 / 50.0) ** -1.5 * 50.0 ** -3), -1.5, 2.0, 900.0, 4.0e5, 0.02], dtype=np.float32)
+    o = OracleSampler(level, p8)
+    np.random.seed(0)
+    frs = np.random.permutation(level.n_frags)[:4]
+    n_prop = 0
+    for f in frs:
+        r = o.step_sampler(int(f), 5)
+        nz = o.all_scores != 0
+        assert nz.any() and np.all(np.isfinite(o.all_scores))
+        assert 0 <= int(r[2]) < 24 and 0 <= int(r[3]) < level.n_frags
+        n_prop += int(sum(o.n_uniq_list))
+    assert n_prop >= 4 * 10
