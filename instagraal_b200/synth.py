@@ -15,6 +15,7 @@ plus a uniform trans/noise floor.  Everything is seeded.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -161,8 +162,8 @@ def _soa(contig_of, len_bp, sub_len):
 
 
 def load_geometry(path):
-    """Fragment geometry of a real digested assembly (written by oracle/make_yeast_toy.py from the reference's
-    tests/data contigs): fragments per contig, sub-fragments per fragment, sub-fragment lengths, true layout."""
+    """Fragment geometry of a real digested assembly (a fixture generated from the reference's tests/data contigs
+    by the test tooling, see tests/golden/): fragments per contig, sub-fragments per fragment, sub-fragment lengths, true layout."""
     z = np.load(path)
     order = np.lexsort((z["contig_start"], z["contig_chrom"]))   # contigs along the true genome
     return {"sizes": z["frags_per_contig"].astype(np.int64), "sub_len": z["frag_nsub"].astype(np.int64),
@@ -343,8 +344,7 @@ def make_level(spec: SynthSpec, geometry=None) -> LevelData:
 
 # Named workloads.  T = toy/yeast-like level 4; Y3 = yeast level 3;
 # G = ~1 Gb synthetic (1e5 fragments, ~3e5 sub-fragments, ~1e8 contacts).
-YEAST_TOY_GEOMETRY = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)),
-                                                "..", "tests", "golden", "yeast_toy_geometry.npz")
+YEAST_TOY_GEOMETRY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "yeast_toy_geometry.npz")
 
 
 def make_workload(name):
