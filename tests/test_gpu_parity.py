@@ -68,13 +68,14 @@ def _oracle(level, p8):
     return OracleSampler(level, p8)
 
 
-@pytest.mark.parametrize("split", ["", "24,1", "6,4"])
+@pytest.mark.parametrize("split,d_exp", [("", 2.0), ("24,1", 2.0), ("6,4", 2.0), ("", 2.37), ("24,1", 1.8)])
 @pytest.mark.parametrize("seed", [0, 1, 2])
-def test_cuda_vs_oracle_random_scaffolds_with_circular_contigs(built, seed, split, monkeypatch):
+def test_cuda_vs_oracle_random_scaffolds_with_circular_contigs(built, seed, split, d_exp, monkeypatch):
     """eval (score) + apply on random scaffolds the trajectories never reach (circular contigs,
     reversed fragments), every op forced once through ig_apply.  `split` forces the scoring kernel's work
     split (all 24 mutations per item = the large-assembly path with one evaluation per group of identical
-    motions; 6 mutations x 4 row parts = the small-assembly path), which small test levels would not reach."""
+    motions; 6 mutations x 4 row parts = the small-assembly path), which small test levels would not reach;
+    `d_exp` = the exponent-cutoff parameter d of the p(s) model."""
     from oracle import moves as mv
     from oracle.fuzz import random_state
     if split:
@@ -82,8 +83,10 @@ def test_cuda_vs_oracle_random_scaffolds_with_circular_contigs(built, seed, spli
     level = make_level(WORKLOADS["micro"])
     rng = np.random.RandomState(seed)
     s = make_sampler(level)
-    s.set_param_simu(P8)
-    o = _oracle(level, P8)
+    p8 = P8.copy()
+    p8[4] = d_exp   # d != 2 takes the expf branch of rippe_contacts (KA:153-163), the usual case after the p(s) fit
+    s.set_param_simu(p8)
+    o = _oracle(level, p8)
     nf = level.n_frags
     for it in range(12):
         st = random_state(nf, rng, p_circ=0.4)

@@ -45,7 +45,8 @@ def test_replay_cpu_backend_matches_golden_exactly():
 
 
 @pytest.mark.gpu
-def test_reference_kernels_on_gpu_vs_product(built):
+@pytest.mark.parametrize("d_exp", [None, 2.37])
+def test_reference_kernels_on_gpu_vs_product(built, d_exp):
     """GPU-vs-GPU: the reference's own kernels (cubin) and the product agree on every score to 1e-9
     relative (same libdevice powf/log10) over a replayed trajectory."""
     import os
@@ -66,7 +67,10 @@ def test_reference_kernels_on_gpu_vs_product(built):
         for impl in (ref, mine):
             impl.set_state(st)
             impl.set_valid(g["step_valid_before"][t])
-            impl.set_params(g["step_params_before"][t])
+            p8 = np.array(g["step_params_before"][t], dtype=np.float32)
+            if d_exp is not None:
+                p8[4] = d_exp   # expf branch of rippe_contacts
+            impl.set_params(p8)
         a = ref.step(int(g["step_A"][t]), cands)
         b = mine.step(int(g["step_A"][t]), cands)
         sa, sb = np.asarray(a["scores"]), np.asarray(b["scores"])
