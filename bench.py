@@ -103,8 +103,9 @@ def measured_peak():
 def measured_traffic(workload, kernel):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the
     committed `ncu --set full` capture of the same workload (profiles/r1_ncu_*.txt), or None."""
-    table = {("T", "k_score"): 1.118208e6 + 0.0, ("G", "k_score"): 118.486784e6 + 4.7104e6,
-             ("G", "k_full_lnz"): 679.342336e6 + 4.3264e6}
+    table = {("T", "k_score"): 0.475904e6 + 0.0,                    # profiles/r1_ncu_k_score_T.txt (benchmark state)
+             ("G", "k_score"): 171.874048e6 + 9.34016e6,            # profiles/r1_ncu_k_score_G.txt (fully assembled start)
+             ("G", "k_full_lnz"): 679.342336e6 + 4.3264e6}          # profiles/r1_ncu_k_full_lnz_G.txt
     return table.get((workload, kernel))
 
 
@@ -315,7 +316,7 @@ def run_ours(args):
                                      "alg_bytes_per_launch": kern[k][1] / max(kern[k][2], 1),
                                      "achieved_GBs": ach[k]} for k in kern},
                      "terms_per_launch": stp["contacts_selected"] * (stp["proposals"] / max(stp["steps"], 1) / 5.0) / max(stp["steps"], 1),
-                     "note": "instruction-bound, not HBM-bound: <=24 x (powf + f64 log10) per 8-byte contact (DESIGN.md)"},
+                     "note": "instruction/latency-bound, not HBM-bound: per 8-byte contact up to 24 float32 coordinate comparisons and, where a term changes, powf + f64 log10 (DESIGN.md 4a)"},
         "kernel_us_per_step": {k: v / max(n_launch_score, 1) * 1e3 for k, v in ktimes.items()},
         "clocks": clk.summary(),
         "setup_s": {"generate": t_gen, "burn_in": t_burn},

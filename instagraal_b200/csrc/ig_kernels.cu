@@ -1607,6 +1607,7 @@ struct ig_handle {
     long long nnz;
     cudaStream_t stream, side, pf;
     cudaEvent_t ev_coords, ev_lnz, ev_fork, ev_sel, ev_out, ev_cuts, ev_cls;
+    bool rows_small;  // affected-row list in one launch (small levels)
     bool prefetch;  // the level's arrays fit the L2 comfortably: prefetch them at the start of a step
     FragRec *live, *init_live;
     SubRec* sub;
@@ -1738,6 +1739,8 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
         if (dev_alloc(h, &h->exz, (size_t)ns + 1) || dev_alloc(h, &h->exz_test, (size_t)ns + 1)) return -2;
         h->n_chunks = (ns + IG_ROW_CHUNK - 1) / IG_ROW_CHUNK;
         if (dev_alloc(h, &h->chunk_cnt, (size_t)IG_MAX_CANDS * h->n_chunks)) return -2;
+        h->rows_small = h->n_chunks <= IG_ROWS_SMALL_CHUNKS;
+        if (const char* e = getenv("IG_ROWS_SMALL")) h->rows_small = h->rows_small && atoi(e) != 0;   // tests: force the two-pass list
         if (dev_alloc(h, &h->rows, (size_t)IG_MAX_CANDS * ns) || dev_alloc(h, &h->row_cnt, (size_t)IG_MAX_CANDS * ns)) return -2;
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, cfg->device));
@@ -1967,7 +1970,7 @@ static int score_candidates(ig_handle* h, int a, const int32_t* cands, int n, in
     k_find_cuts<<<dim3((h->nf + 255) / 256, n), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc, h->clstab);
     k_classes<<<n, IG_N_OPS * 32, 0, h->stream>>>(h->sc, h->desc, h->clstab, h->rigid, h->cfg.mean_sub_len_kb);
     if (overlap) cudaStreamWaitEvent(h->stream, h->ev_coords, 0);
-    if (h->n_chunks <= IG_ROWS_SMALL_CHUNKS) {
+    if (h->rows_small) {
         k_rows_small<<<n, IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->n_chunks, h->rows, h->rowidx, h->row_cnt, h->ns,
                                                         h->clstab, h->row_ptr, h->rinfo);
     } else {
@@ -2077,7 +2080,7 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands, int cycle = 0)
     cudaEventRecord(h->ev_cls, h->pf);
     cudaStreamWaitEvent(h->stream, h->ev_coords, 0);
     IG_MARK(2);
-    if (h->n_chunks <= IG_ROWS_SMALL_CHUNKS) {
+    if (h->rows_small) {
         IG_MARK(3);
         k_rows_small<<<n, IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->n_chunks, h->rows, h->rowidx, h->row_cnt, h->ns,
                                                         h->clstab, h->row_ptr, h->rinfo);
@@ -2170,7 +2173,7 @@ extern "C" int ig_step(ig_handle* h, int32_t id_frag, const int32_t* cands, int3
     }
     cudaEventRecord(h->ev[1], h->stream);
     CK(cudaStreamSynchronize(h->stream));
-    h->n_launches += (full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR) - (h->rigid ? 1 : 0) + (h->prefetch ? 1 : 0) - (h->n_chunks <= IG_ROWS_SMALL_CHUNKS ? 1 : 0);
+    h->n_launches += (full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR) - (h->rigid ? 1 : 0) + (h->prefetch ? 1 : 0) - (h->rows_small ? 1 : 0);
     h->steps_since_full = full ? 1 : h->steps_since_full + 1;
     h->n_full += full;
     h->incr_valid = true;
@@ -2223,7 +2226,7 @@ static int run_plan(ig_handle* h, int n_steps, GridN grid_n, ig_cycle_step* out)
         h->steps_since_full = full ? 1 : h->steps_since_full + 1;
         h->n_full += full;
         h->incr_valid = true;
-        h->n_launches += (full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR) - (h->rigid ? 1 : 0) + (h->prefetch ? 1 : 0) - (h->n_chunks <= IG_ROWS_SMALL_CHUNKS ? 1 : 0);
+        h->n_launches += (full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR) - (h->rigid ? 1 : 0) + (h->prefetch ? 1 : 0) - (h->rows_small ? 1 : 0);
     }
     cudaEventRecord(h->ev[1], h->stream);
     std::vector<CycleOut> res(n_steps);

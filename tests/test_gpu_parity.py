@@ -501,3 +501,15 @@ def test_yeast_toy_config0_lockstep(built):
     assert (level.n_frags, level.n_sub_frags) == (1015, 2857)
     ties = _lockstep(level, P8_RIPPE, 40, seed=2)
     assert ties <= 8
+
+
+@pytest.mark.parametrize("env", [{"IG_ROWS_SMALL": "0"}, {"IG_PREFETCH": "1"}, {"IG_ROWS_SMALL": "0", "IG_FORCE_SPLIT": "24,1"}])
+def test_large_level_code_paths_on_a_small_level(built, env, monkeypatch):
+    """The two-pass affected-row list (levels above 16 Ki sub-fragments), the optional L2 prefetch and the
+    whole-row work split only run on large levels by default; forced here on the toy level, in lockstep with
+    the oracle."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    level = make_level(WORKLOADS["toy"])
+    ties = _lockstep(level, P8_RIPPE, 80, seed=6, bomb=True)
+    assert ties <= 40
