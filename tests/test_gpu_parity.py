@@ -513,3 +513,15 @@ def test_large_level_code_paths_on_a_small_level(built, env, monkeypatch):
     level = make_level(WORKLOADS["toy"])
     ties = _lockstep(level, P8_RIPPE, 80, seed=6, bomb=True)
     assert ties <= 40
+
+
+def test_medium_level_with_long_contigs_takes_the_large_level_paths_naturally(built):
+    """6000 fragments / 18k sub-fragments in 12 long contigs: above 16 Ki sub-fragments the affected-row list is
+    built in two passes, candidates have > 1000 affected rows so each work item covers all 24 mutations of a
+    whole row (chunk-ahead fetch), and most contacts of a 500-fragment contig do not change under a mutation, so
+    the (contact, mutation) pairs are dealt sparsely to the lanes -- the operating point of the 1 Gb workload,
+    at a size the oracle still finishes in seconds per step.  Lockstep with the oracle."""
+    level = make_level(SynthSpec(n_frags=6000, n_contigs=12, n_chrom=2, max_offset=300, lambda1=30.0, trans_per_row=2.0, seed=11))
+    assert level.n_sub_frags > 16 * 1024
+    ties = _lockstep(level, P8_RIPPE, 30, seed=3)
+    assert ties <= 6
