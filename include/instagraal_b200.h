@@ -138,6 +138,16 @@ int ig_distance_histogram(ig_handle* h, double bin_kb, double max_kb, int32_t n_
  * in the displayed order given by sub_rank[NS] */
 int ig_contact_thumbnail(ig_handle* h, const int32_t* sub_rank, int32_t K, uint32_t* out);
 
+/* Diagnostics (builds with -DIG_TIMELINE only; -1 otherwise): per step of the last cycle run, per kernel, the earliest
+ * block start and latest block end in %globaltimer ns: out[n_steps][16][2]. */
+int ig_timeline_reset(ig_handle* h);
+int ig_timeline_get(ig_handle* h, int32_t n_steps, uint64_t* out);
+/* per block of the LAST k_score launch: start ns, end ns, SM id, work items: out[n_blocks][4] */
+int ig_timeline_blocks(ig_handle* h, int32_t n_blocks, uint64_t* out);
+/* k_score phase profile: SM cycles of warp 0 of every block, summed per phase (prologue, item set-up, contact loop,
+ * final flush + reductions, wait at the block barrier) since the last reset */
+int ig_timeline_phases(ig_handle* h, uint64_t* out8, int32_t reset);
+
 /* diagonal of (M + M^T) at level L-1 (self contacts): only the p(s) histogram sees it (CL:2257-2288) */
 int ig_set_sym_diag(ig_handle* h, const int32_t* diag);
 

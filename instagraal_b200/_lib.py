@@ -22,7 +22,7 @@ EXPORTS = (
     "ig_set_state", "ig_get_valid_insert", "ig_set_valid_insert", "ig_bomb", "ig_step", "ig_eval_scores",
     "ig_apply", "ig_full_likelihood", "ig_distance_histogram", "ig_set_sym_diag", "ig_device_state_ptr",
     "ig_set_profiling", "ig_get_stats", "ig_set_options", "ig_get_full_refresh_count", "ig_get_kernel_times", "ig_run_cycle", "ig_contact_thumbnail", "ig_set_neighbour_weights",
-           "ig_run_cycle_device", "ig_get_cycle_plan",
+           "ig_run_cycle_device", "ig_get_cycle_plan", "ig_timeline_reset", "ig_timeline_get", "ig_timeline_blocks", "ig_timeline_phases",
 )
 
 
@@ -94,6 +94,10 @@ def lib():
         L.ig_set_neighbour_weights.argtypes = [vp, vp, vp, vp, vp]
         L.ig_run_cycle_device.argtypes = [vp, i32, vp, i32, C.c_uint64, C.c_uint32, vp]
         L.ig_get_cycle_plan.argtypes = [vp, i32, vp]
+        L.ig_timeline_reset.argtypes = [vp]
+        L.ig_timeline_get.argtypes = [vp, i32, vp]
+        L.ig_timeline_blocks.argtypes = [vp, i32, vp]
+        L.ig_timeline_phases.argtypes = [vp, vp, i32]
         L.ig_get_full_refresh_count.argtypes = [vp, C.POINTER(i64)]
         for name in EXPORTS:
             if name not in ("ig_destroy", "ig_last_error"):

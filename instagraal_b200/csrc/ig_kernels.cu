@@ -28,7 +28,10 @@
 #include "../../include/instagraal_b200.h"
 #include "ig_moves.cuh"
 
+#ifndef IG_WARPS_PER_BLOCK
 #define IG_WARPS_PER_BLOCK 8
+#endif
+#define IG_SCORE_CTAS_PER_SM (24 / IG_WARPS_PER_BLOCK)
 #define IG_THREADS (IG_WARPS_PER_BLOCK * 32)
 #define IG_ROW_CHUNK 1024
 #define IG_ROWS_SMALL_CHUNKS 16  // levels of up to 16 Ki sub-fragments build the affected-row list in one launch
@@ -86,6 +89,64 @@ struct CycleOut {  // compact per-step record of ig_run_cycle (128 B)
     int n_uniq[IG_MAX_CANDS], n_sub[IG_MAX_CANDS];
     int pad[8];
 };
+
+// ------------------------------------------------------------------------------------------------
+// Optional on-device timeline (build with -DIG_TIMELINE, scripts/gpu_timeline.sh): every kernel of the step
+// records the earliest block start and the latest block end in %globaltimer nanoseconds, per step of a cycle
+// run -- the only way to see the real kernel durations AND the gaps between dependent launches inside a CUDA
+// graph replay with warm caches (ncu serialises and flushes; nsys is not available here).
+#define IG_TL_KERNELS 16
+#define IG_TL_STEPS 4096
+#ifdef IG_TIMELINE
+__device__ unsigned long long g_tl[IG_TL_STEPS][IG_TL_KERNELS][2];
+__device__ int g_tl_step;
+struct TlScope {
+    int id;
+    __device__ __forceinline__ TlScope(int i) : id(i) {
+        if (threadIdx.x == 0) {
+            unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            atomicMin(&g_tl[*(volatile int*)&g_tl_step & (IG_TL_STEPS - 1)][id][0], t);
+        }
+    }
+    __device__ __forceinline__ ~TlScope() {
+        if (threadIdx.x == 0) {
+            unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            atomicMax(&g_tl[*(volatile int*)&g_tl_step & (IG_TL_STEPS - 1)][id][1], t);
+        }
+    }
+};
+#define TL(id) TlScope tl_scope_(id)
+// per-block trace of the scoring kernel (last launch wins): start, end, SM id, items processed
+#define IG_TL_BLOCKS 8192
+__device__ unsigned long long g_tlb[IG_TL_BLOCKS][4];
+struct TlBlock {
+    int idx; unsigned long long t0; int items;
+    __device__ __forceinline__ TlBlock() : items(0) {
+        idx = blockIdx.y * gridDim.x + blockIdx.x;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    }
+    __device__ __forceinline__ ~TlBlock() {
+        if (threadIdx.x == 0 && idx < IG_TL_BLOCKS) {
+            unsigned long long t1; unsigned sm;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+            g_tlb[idx][0] = t0; g_tlb[idx][1] = t1; g_tlb[idx][2] = sm; g_tlb[idx][3] = (unsigned long long)items;
+        }
+    }
+};
+#define TLB() TlBlock tl_block_
+#define TLB_ITEM() tl_block_.items++
+// phase profile of the scoring kernel: cycles of warp 0 of every block, summed per phase
+__device__ unsigned long long g_tlp[8];
+#define TLP_DECL() long long tlp_t_ = clock64()
+#define TLP(ph) do { if (threadIdx.x == 0) { const long long n_ = clock64(); atomicAdd(&g_tlp[ph], (unsigned long long)(n_ - tlp_t_)); tlp_t_ = n_; } } while (0)
+#else
+#define TLB()
+#define TLB_ITEM()
+#define TLP_DECL()
+#define TLP(ph)
+#define TL(id)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // device math: textual twins of KA:111-124, 153-163, 200-225, 251-270
@@ -209,6 +270,7 @@ __global__ void __launch_bounds__(IG_THREADS)
 k_coords(const FragRec* __restrict__ live, const SubRec* __restrict__ sub, CoordRec* __restrict__ coord,
          int* __restrict__ clen, int ns, const DevScalars* __restrict__ sc, float mbar, int use_test,
          double* __restrict__ part_z, int* __restrict__ part_n, int write_coords, SubX* __restrict__ subx) {
+    TL(13);
     __shared__ double sm[32];
     __shared__ int sn;
     const Params p = use_test ? sc->p_test : sc->p;
@@ -241,6 +303,7 @@ __global__ void __launch_bounds__(IG_THREADS)
 k_full_lnz(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, const CoordRec* __restrict__ coord,
            const int* __restrict__ clen, int ns, const DevScalars* __restrict__ sc, float mbar, int use_test,
            const float* __restrict__ exz_tab, double* __restrict__ part) {
+    TL(14);
     __shared__ double sm[32];
     const Params p = use_test ? sc->p_test : sc->p;
     const double l10v = use_test ? sc->log10_vinter_test : sc->log10_vinter;
@@ -298,6 +361,7 @@ __global__ void k_set_params(DevScalars* sc, Params p, int test) {
 //     of candidate k reads the list_valid_insert left by get_bounds of candidate k-1 (quirk Q3).
 __global__ void k_cand_setup(const FragRec* __restrict__ live, DevScalars* sc, IgDescriptor* desc, int n_bounds,
                              int first_flip_eject, const int* __restrict__ cyc_in) {
+    TL(0);
     if (cyc_in) {  // cycle mode: this step's {n_cands, fragment, candidates} come from the uploaded cycle plan
         const int* src = cyc_in + (size_t)sc->step_idx * (2 + IG_MAX_CANDS);
         if (threadIdx.x < 2 + IG_MAX_CANDS) (&sc->n_cands)[threadIdx.x] = src[threadIdx.x];
@@ -344,6 +408,7 @@ __global__ void k_cand_setup(const FragRec* __restrict__ live, DevScalars* sc, I
 //     candidate then evaluates every pivot of its descriptor (one thread).
 __global__ void __launch_bounds__(256)
 k_find_cuts(const FragRec* __restrict__ live, int nf, DevScalars* sc, IgDescriptor* desc, IgClassTab* __restrict__ clstab) {
+    TL(1);
     const int k = blockIdx.y;
     if (k >= sc->n_cands) return;
     __shared__ int is_last;
@@ -385,6 +450,7 @@ k_find_cuts(const FragRec* __restrict__ live, int nf, DevScalars* sc, IgDescript
 //     stream (only k_score needs the result).
 __global__ void __launch_bounds__(IG_N_OPS * 32)
 k_classes(const DevScalars* __restrict__ sc, const IgDescriptor* __restrict__ desc, IgClassTab* __restrict__ clstab, int rigid, float mbar) {
+    TL(2);
     const int k = blockIdx.x;
     if (k >= sc->n_cands) return;
     __shared__ IgDescriptor d;
@@ -459,6 +525,7 @@ k_classes(const DevScalars* __restrict__ sc, const IgDescriptor* __restrict__ de
 __device__ __forceinline__ bool row_affected(const CoordRec& c, const CandInfo& ci) { return c.id_c == ci.id_a || c.id_c == ci.id_b; }
 __global__ void __launch_bounds__(IG_ROW_CHUNK)
 k_rows_count(const CoordRec* __restrict__ coord, int ns, DevScalars* sc, int* __restrict__ chunk_cnt, int n_chunks) {
+    TL(3);
     const int k = blockIdx.y;
     if (k >= sc->n_cands) return;
     __shared__ int is_last, carry;
@@ -505,6 +572,7 @@ __global__ void __launch_bounds__(IG_ROW_CHUNK)
 k_rows_write(const CoordRec* __restrict__ coord, int ns, const DevScalars* __restrict__ sc, const int* __restrict__ chunk_off,
              int n_chunks, int* __restrict__ rows, int* __restrict__ rowidx, int* __restrict__ row_cnt, int rows_stride,
              const IgClassTab* __restrict__ clstab, const long long* __restrict__ row_ptr, RowInfo* __restrict__ rinfo) {
+    TL(4);
     const int k = blockIdx.y;
     if (k >= sc->n_cands) return;
     __shared__ int wsum[32];
@@ -543,6 +611,7 @@ __global__ void __launch_bounds__(IG_ROW_CHUNK)
 k_rows_small(const CoordRec* __restrict__ coord, int ns, DevScalars* sc, int n_chunks, int* __restrict__ rows,
              int* __restrict__ rowidx, int* __restrict__ row_cnt, int rows_stride, const IgClassTab* __restrict__ clstab,
              const long long* __restrict__ row_ptr, RowInfo* __restrict__ rinfo) {
+    TL(3);
     const int k = blockIdx.x;
     if (k >= sc->n_cands) return;
     __shared__ int wsum[32];
@@ -612,6 +681,7 @@ k_precompute(const CoordRec* __restrict__ coord, const int* __restrict__ clen, c
              double* __restrict__ part_z,  // [cand][25][gridDim.x]
              int* __restrict__ part_i)     // [cand][25][gridDim.x]
 {
+    TL(5);
     const int k = blockIdx.y;
     const int n_rows = sc->ci[k].n_rows;
     if (k >= sc->n_cands) return;
@@ -681,6 +751,7 @@ k_precompute(const CoordRec* __restrict__ coord, const int* __restrict__ clen, c
 // between steps, -3 % when steps run back to back (warm L2, the production case) -- hence off by default.
 struct PfList { const char* p[12]; unsigned long long n[12]; int cnt; };
 __global__ void k_prefetch_l2(PfList L) {
+    TL(12);
     for (int a = 0; a < L.cnt; a++) {
         const unsigned long long lines = (L.n[a] + 127ull) >> 7;
         for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < lines; i += (unsigned long long)gridDim.x * blockDim.x)
@@ -806,7 +877,7 @@ __device__ __forceinline__ void queue_push(bool push, float s, int dp, unsigned 
 //     the ROW end is warp-uniform and staged from the k_precompute table into shared memory once per item.
 //   * A pair whose (same-contig flag, s, sub-fragment separation) is bit-identical to the current state is
 //     skipped; the rest is either a cheap constant (other contig / outside (0, d_max)) or goes to the queue.
-__global__ void __launch_bounds__(IG_THREADS, 3)
+__global__ void __launch_bounds__(IG_THREADS, IG_SCORE_CTAS_PER_SM)
 k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, const CoordRec* __restrict__ coord,
         const int* __restrict__ clen, const DevScalars* __restrict__ sc, const IgDescriptor* __restrict__ desc_g,
         const int* __restrict__ rows, const int* __restrict__ rowidx, int ns, int* __restrict__ row_cnt,
@@ -817,6 +888,9 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
         const IgClassTab* __restrict__ clstab, const SubX* __restrict__ subx, const RowInfo* __restrict__ rinfo,
         int sparse_div)                 // deal (contact, mutation) pairs to the lanes when fewer than 32/sparse_div lanes are busy
 {
+    TL(6);
+    TLB();
+    TLP_DECL();
     const int k = blockIdx.y;
     if (k >= sc->n_cands) return;
     extern __shared__ double acc_s[];                 // [IG_N_OPS][IG_THREADS]
@@ -878,7 +952,9 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
     int* myoff = s_off[w];
     // constant term of a contact whose endpoints lie in different contigs (KA:4348-4352) minus the ob part
     const double inter_const = (double)p.v_inter * LOG10E_F;
+    TLP(0);   // block prologue
     for (int it = it0; it < n_items; it += it_step) {
+        TLB_ITEM();
         const int rg = it / parts, part = it - rg * parts;
         const int ri = rg / ng, g = rg - ri * ng;
         const int q_off = block_mode ? 32 * w : 32 * part, q_step = block_mode ? 32 * IG_WARPS_PER_BLOCK : 32 * parts;
@@ -894,6 +970,7 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
         __syncwarp();
         if (u0 + lane < u1) myrow[lane] = tab[(size_t)(u0 + lane) * ns + ri];
         __syncwarp();
+        TLP(1);   // item set-up (row record, row-end table entries)
         int row_sel = 0;
         int qn = 0;  // warp-uniform queue fill
         unsigned touched = 0;  // slots (relative to u0) that received a term in this item
@@ -1005,6 +1082,7 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
             queue_push((x.flags & 2) && chg, x.cur_s, x.cur_dp, chg | IG_QSUB, x.val, myq, qn, my_acc, p, l10v, exz_tab);
             touched |= __reduce_or_sync(0xffffffffu, chg);
         }
+        TLP(2);   // contact loop
         if (qn > 0) { eval_queue(myq, qn, my_acc, p, l10v, exz_tab); }
         __syncwarp();
         // fixed-order accumulation into this warp's slot sums (work items are visited in a fixed order); only
@@ -1025,7 +1103,9 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
             }
         }
     }
+    TLP(3);   // last queue flush + slot reductions of the items
     __syncthreads();
+    TLP(4);   // waiting for the slowest warp of the block
     if (threadIdx.x < 25) {
         double v = 0.0;
         for (int ww = 0; ww < IG_WARPS_PER_BLOCK; ww++) v += red[ww][threadIdx.x];
@@ -1051,6 +1131,8 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
            float mbar, const float* __restrict__ exz_tab, const double* __restrict__ part_nz, const int* __restrict__ part_c,
            int n_part, const double* __restrict__ part_z, const int* __restrict__ part_i, int n_part_z, double n_pix,
            int compat_last_block, int* __restrict__ n_uniq_out, int* __restrict__ n_sub_out, int do_select) {
+    TL(7);
+    TLP_DECL();
     const int k = blockIdx.x;
     if (k >= sc->n_cands) return;
     __shared__ double s_nz[25], s_z[25], s_corr[IG_N_OPS];
@@ -1058,7 +1140,8 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
     __shared__ double t_val[IG_N_OPS][64];
     __shared__ int2 t_cv[64];
     __shared__ int t_ri[64];
-    __shared__ int t_cnt, t_need, t_ri_cur;
+    __shared__ int t_cnt, t_need, tr_n;
+    __shared__ int tr_ri[64], tr_skip[64], tr_off[64];
     __shared__ int t_wsum[32];
     const IgDescriptor& d = desc_g[k];
     const Params p = sc->p;
@@ -1074,12 +1157,12 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
             const double* src = slot < 25 ? &part_nz[PART_IDX(k, 25, slot, n_part, 0)] : &part_z[PART_IDX(k, 25, slot - 25, n_part_z, 0)];
             const int n = slot < 25 ? n_part : n_part_z;
             double v = 0.0;
-            for (int i0 = 0; i0 < n; i0 += 32 * 8) {
-                double x[8];
+            for (int i0 = 0; i0 < n; i0 += 32 * 16) {
+                double x[16];
 #pragma unroll
-                for (int j = 0; j < 8; j++) { const int i = i0 + j * 32 + lane; x[j] = i < n ? src[i] : 0.0; }
+                for (int j = 0; j < 16; j++) { const int i = i0 + j * 32 + lane; x[j] = i < n ? src[i] : 0.0; }
 #pragma unroll
-                for (int j = 0; j < 8; j++) v += x[j];
+                for (int j = 0; j < 16; j++) v += x[j];
             }
             v = warp_sum(v);
             if (lane == 0) { if (slot < 25) s_nz[slot] = v; else s_z[slot - 25] = v; }
@@ -1087,12 +1170,12 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
             const int* src = slot < 75 ? &part_i[PART_IDX(k, 25, slot - 50, n_part_z, 0)] : &part_c[PART_IDX(k, 2, slot - 75, n_part, 0)];
             const int n = slot < 75 ? n_part_z : n_part;
             int v = 0;
-            for (int i0 = 0; i0 < n; i0 += 32 * 8) {
-                int x[8];
+            for (int i0 = 0; i0 < n; i0 += 32 * 16) {
+                int x[16];
 #pragma unroll
-                for (int j = 0; j < 8; j++) { const int i = i0 + j * 32 + lane; x[j] = i < n ? src[i] : 0; }
+                for (int j = 0; j < 16; j++) { const int i = i0 + j * 32 + lane; x[j] = i < n ? src[i] : 0; }
 #pragma unroll
-                for (int j = 0; j < 8; j++) v += x[j];
+                for (int j = 0; j < 16; j++) v += x[j];
             }
             v = __reduce_add_sync(0xffffffffu, v);
             if (lane == 0) { if (slot < 75) s_i[slot - 50] = v; else s_c[slot - 75] = v; }
@@ -1100,6 +1183,7 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
     }
     if (threadIdx.x < IG_N_OPS) s_corr[threadIdx.x] = 0.0;
     __syncthreads();
+    TLP(5);
     const int n_sub = s_c[0];
     const int t = n_sub % 64;
     const RowMut* tab = table + (size_t)k * IG_N_OPS * ns;
@@ -1109,28 +1193,42 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
         // ordered (hence deterministic) collection of the last t selected contacts of the row-sorted slice:
         // rows from the last one backwards, the whole block scans a row's contacts with a block-wide
         // exclusive scan of the selection flags, keeping the row's last `take` selected contacts in order
-        if (threadIdx.x == 0) { t_cnt = 0; t_need = t; t_ri_cur = ci_k.n_rows - 1; }
+        // 1. the tail rows, found in parallel: windows of blockDim rows from the end of the affected-row list,
+        //    block-wide scan of their selected-contact counts (thread order = descending row)
+        const int* rc_k = row_cnt + (size_t)k * ns;
+        if (threadIdx.x == 0) { tr_n = 0; t_need = 0; }
         __syncthreads();
-        while (true) {
-            // advance to the next row (backwards) that has selected contacts
-            if (threadIdx.x == 0) {
-                int ri = t_ri_cur;
-                while (ri >= 0 && row_cnt[(size_t)k * ns + ri] == 0) ri--;
-                t_ri_cur = ri;
+        for (int hi = ci_k.n_rows; hi > 0; hi -= (int)blockDim.x) {
+            const int carry = t_need;   // selected contacts in the rows behind this window
+            if (carry >= t) break;
+            const int ri = hi - 1 - (int)threadIdx.x;
+            const int c = ri >= 0 ? rc_k[ri] : 0;
+            int x = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            if (lane == 31) t_wsum[w] = x;
+            __syncthreads();
+            int before = 0, total = 0;
+            for (int ww = 0; ww < nwarp; ww++) { const int v = t_wsum[ww]; if (ww < w) before += v; total += v; }
+            const int excl = carry + before + x - c;   // tail contacts in later rows
+            if (c > 0 && excl < t) {
+                const int take = min(c, t - excl);
+                const int slot = atomicAdd(&tr_n, 1);  // < 64 rows: each holds at least one tail contact
+                tr_ri[slot] = ri; tr_skip[slot] = c - take; tr_off[slot] = t - (excl + take);
             }
             __syncthreads();
-            const int ri = t_ri_cur, need = t_need;
-            if (ri < 0 || need <= 0) break;
-            const int rc = row_cnt[(size_t)k * ns + ri];
-            const int take = min(rc, need);
-            const int skip = rc - take;  // selected contacts of this row that stay outside the tail
+            if (threadIdx.x == 0) t_need = carry + total;
+            __syncthreads();
+        }
+        // 2. one warp per tail row: its last `take` selected contacts, in column order, to their place in the tail
+        for (int j = w; j < tr_n; j += nwarp) {
+            const int ri = tr_ri[j], skip = tr_skip[j], off = tr_off[j];
             const int r = rows[(size_t)k * ns + ri];
             const CoordRec ci = coord[r];
             const long long b0 = row_ptr[r], e0 = row_ptr[r + 1];
-            const int base_slot = t_cnt;
-            int running = 0;  // selected contacts of this row seen so far (uniform across the block)
-            for (long long q0 = b0; q0 < e0; q0 += blockDim.x) {
-                const long long q = q0 + threadIdx.x;
+            int running = 0;
+            for (long long q0 = b0; q0 < e0; q0 += 32) {
+                const long long q = q0 + lane;
                 int2 c = make_int2(0, 0);
                 bool sel = false;
                 if (q < e0) {
@@ -1138,20 +1236,13 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
                     const CoordRec cj = coord[c.x];
                     sel = (cj.id_c == ci_k.id_a || cj.id_c == ci_k.id_b) && contact_selected(ci, cj, c.y, ci_k);
                 }
-                // block-wide exclusive scan of sel
                 const unsigned bal = __ballot_sync(0xffffffffu, sel);
-                if (lane == 0) t_wsum[w] = __popc(bal);
-                __syncthreads();
-                int before = 0, total = 0;
-                for (int ww = 0; ww < nwarp; ww++) { const int x = t_wsum[ww]; if (ww < w) before += x; total += x; }
-                const int idx = running + before + __popc(bal & ((1u << lane) - 1));
-                if (sel && idx >= skip) { const int slot = base_slot + (idx - skip); t_cv[slot] = c; t_ri[slot] = ri; }
-                running += total;
-                __syncthreads();
+                const int idx = running + __popc(bal & ((1u << lane) - 1));
+                if (sel && idx >= skip) { const int slot = off + (idx - skip); t_cv[slot] = c; t_ri[slot] = ri; }
+                running += __popc(bal);
             }
-            if (threadIdx.x == 0) { t_cnt = base_slot + take; t_need = need - take; t_ri_cur = ri - 1; }
-            __syncthreads();
         }
+        if (threadIdx.x == 0) t_cnt = t;
         __syncthreads();
         const int n_items = t_cnt * (n_uniq - t);
         for (int idx = threadIdx.x; idx < n_items; idx += blockDim.x) {
@@ -1174,6 +1265,7 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
         }
         __syncthreads();
     }
+    TLP(6);
     // ---- scores
     if (threadIdx.x < IG_N_OPS) sc->scores[k * IG_N_OPS + threadIdx.x] = 0.0;
     __syncthreads();
@@ -1203,6 +1295,7 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
         atomicAdd(&sc->st_selected, (unsigned long long)n_sub);
         atomicAdd(&sc->st_proposals, (unsigned long long)n_uniq);
     }
+    TLP(7);
     if (!do_select) return;
     // move selection by the LAST candidate block to finish (saves a dependent launch)
     __threadfence();
@@ -1280,6 +1373,7 @@ k_lnz_outside(const long long* __restrict__ row_ptr, const int2* __restrict__ cv
               const int* __restrict__ clen, DevScalars* sc, const int* __restrict__ rows, const int* __restrict__ rowidx, int ns,
               const RowMut* __restrict__ table, const int* __restrict__ table_len, float mbar, const float* __restrict__ exz_tab,
               double* __restrict__ part) {
+    TL(8);
     if (!sc->prev_windowed) return;
     __shared__ double sm[32];
     __shared__ int is_last;
@@ -1337,6 +1431,7 @@ __global__ void __launch_bounds__(256)
 k_commit_coords(CoordRec* __restrict__ coord, int* __restrict__ clen, DevScalars* sc, const int* __restrict__ rows, int ns,
                 const RowMut* __restrict__ table, const int* __restrict__ table_len, const FragRec* __restrict__ live,
                 const SubRec* __restrict__ sub, SubX* __restrict__ subx) {
+    TL(11);
     const int k = sc->prev_k, u = sc->prev_u, n = sc->prev_n_rows;
     const int* my_rows = rows + (size_t)k * ns;
     const RowMut* tab = table + ((size_t)k * IG_N_OPS + u) * ns;
@@ -1359,6 +1454,7 @@ k_commit_coords(CoordRec* __restrict__ coord, int* __restrict__ clen, DevScalars
 // K11: apply the winning move to every fragment (test_copy_struct + copy_struct, CL:2094-2151)
 __global__ void __launch_bounds__(256)
 k_apply(FragRec* __restrict__ live, int nf, DevScalars* sc, const IgDescriptor* __restrict__ desc_g, int forced_cand, int forced_op) {
+    TL(9);
     __shared__ IgDescriptor d;
     const int kc = forced_cand >= 0 ? forced_cand : sc->win_cand;
     const int op = forced_op >= 0 ? forced_op : sc->win_op;
@@ -1400,6 +1496,7 @@ __global__ void __launch_bounds__(256)
 k_post(const FragRec* __restrict__ live, int nf, const int* __restrict__ init_prev, const int* __restrict__ init_next,
        const int* __restrict__ orientable, DevScalars* sc, CycleOut* __restrict__ cyc_out, const int* __restrict__ d_nuniq,
        const int* __restrict__ d_nsub) {
+    TL(10);
     __shared__ int s_heads;
     __shared__ long long s_len, s_half;
     if (threadIdx.x == 0) { s_heads = 0; s_len = 0; s_half = 0; }
@@ -1455,6 +1552,9 @@ k_post(const FragRec* __restrict__ live, int nf, const int* __restrict__ init_pr
                 for (int i = 0; i < IG_MAX_CANDS; i++) { o.n_uniq[i] = d_nuniq[i]; o.n_sub[i] = d_nsub[i]; o.pad[i] = 0; }
                 cyc_out[sc->step_idx] = o;
                 sc->step_idx += 1;
+#ifdef IG_TIMELINE
+                g_tl_step += 1;
+#endif
             }
         }
     }
@@ -1636,7 +1736,7 @@ struct ig_handle {
     bool params_set, coords_fresh, coords_ever;
     bool incr_valid; int refresh_every; long long steps_since_full;
     double* part_out;
-    int gs_div, sparse_div;
+    int gs_div, sparse_div, grid_split;
     long long last_n_full;
     cudaGraphExec_t graph[4][IG_MAX_CANDS + 1];   // [full + 2 * cycle][candidates in the grid]
     int* cyc_in; CycleOut* cyc_out; int cyc_cap; bool graph_failed, capturing, use_graph; long long n_full;
@@ -1704,6 +1804,8 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
     h->incr_valid = false; h->refresh_every = 4096; h->steps_since_full = 0;
     h->gs_div = 4;
     h->sparse_div = 4;
+    h->grid_split = 0;
+    if (const char* e = getenv("IG_GRID_SPLIT")) h->grid_split = atoi(e);   // 0: the full grid per candidate (experiments)
     if (const char* e = getenv("IG_SPARSE_DIV")) h->sparse_div = atoi(e) & 0xffff;
     if (const char* e = getenv("IG_FORCE_SPLIT")) {  // "gs,parts" (experiments)
         int g = 0, pp = 0;
@@ -1745,7 +1847,7 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, cfg->device));
         const int sms = prop.multiProcessorCount;
-        h->grid_score = sms * 3;  // 3 resident CTAs of 8 warps per SM (launch bounds, 48 KB dynamic smem each)
+        h->grid_score = sms * IG_SCORE_CTAS_PER_SM;  // 24 resident warps per SM (80 registers per thread; 6 KB of accumulators per warp)
         CK(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IG_SCORE_SMEM));
         h->grid_pre = sms * 2;   // 2 resident CTAs of 25 warps per SM
         {
@@ -1956,6 +2058,13 @@ static int refresh_current(ig_handle* h, cudaStream_t st, bool fork) {
     return launch_ok(h, "refresh_current");
 }
 
+// k_score grid: the candidates of a step run side by side, so the resident capacity (3 CTAs per SM) is shared
+// between them -- one wave for the whole step instead of one (mostly latency) wave per candidate
+static int score_grid_x(const ig_handle* h, int n) {
+    if (h->grid_split <= 0) return h->grid_score;
+    return std::max(h->grid_score / std::max(n, 1), h->grid_score / 8) * h->grid_split;
+}
+
 static int score_candidates(ig_handle* h, int a, const int32_t* cands, int n, int first_flip_eject, bool overlap) {
     if (n <= 0 || n > IG_MAX_CANDS) { h->err = "n_cands out of range"; return -1; }
     if (a < 0 || a >= h->nf) { h->err = "id_frag out of range"; return -1; }
@@ -1981,14 +2090,15 @@ static int score_candidates(ig_handle* h, int a, const int32_t* cands, int n, in
     k_precompute<<<dim3(h->grid_pre, n), IG_PRE_THREADS, 0, h->stream>>>(h->coord, h->clen, live, h->sub, h->sc, h->desc, h->rows, h->ns,
                                                                     h->table, h->table_len, mbar, h->part_z, h->part_i);
     if (h->profile) cudaEventRecord(h->ev[4], h->stream);
-    k_score<<<dim3(h->grid_score, n), IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
+    const int gsx = score_grid_x(h, n);
+    k_score<<<dim3(gsx, n), IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
                                                                  h->ns, h->row_cnt, h->table, h->table_len, mbar, h->exz, h->part_nz,
                                                                  h->part_c, h->gs_div, h->clstab, h->subx, h->rinfo, h->sparse_div);
     if (h->profile) cudaEventRecord(h->ev[5], h->stream);
     h->n_launches += 7;
     if (overlap) cudaStreamWaitEvent(h->stream, h->ev_lnz, 0);
     k_finalize<<<n, 1024, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->sc, h->desc, h->rows, h->rowidx, h->ns, h->row_cnt, h->table,
-                                         h->table_len, mbar, h->exz, h->part_nz, h->part_c, h->grid_score, h->part_z, h->part_i,
+                                         h->table_len, mbar, h->exz, h->part_nz, h->part_c, gsx, h->part_z, h->part_i,
                                          h->grid_pre, h->cfg.n_pix, h->cfg.compat_last_block, h->d_nuniq, h->d_nsub, 0);
     return launch_ok(h, "score_candidates");
 }
@@ -2096,14 +2206,15 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands, int cycle = 0)
     if (h->profile && !h->capturing) cudaEventRecord(h->ev[4], h->stream);
     cudaStreamWaitEvent(h->stream, h->ev_cls, 0);
     IG_MARK(5);
-    k_score<<<dim3(h->grid_score, n), IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
+    const int gsx = score_grid_x(h, n);
+    k_score<<<dim3(gsx, n), IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
                                                                  h->ns, h->row_cnt, h->table, h->table_len, mbar, h->exz, h->part_nz,
                                                                  h->part_c, h->gs_div, h->clstab, h->subx, h->rinfo, h->sparse_div);
     if (h->profile && !h->capturing) cudaEventRecord(h->ev[5], h->stream);
     cudaStreamWaitEvent(h->stream, h->ev_lnz, 0);
     IG_MARK(6);
     k_finalize<<<n, 1024, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->sc, h->desc, h->rows, h->rowidx, h->ns, h->row_cnt, h->table,
-                                         h->table_len, mbar, h->exz, h->part_nz, h->part_c, h->grid_score, h->part_z, h->part_i,
+                                         h->table_len, mbar, h->exz, h->part_nz, h->part_c, gsx, h->part_z, h->part_i,
                                          h->grid_pre, h->cfg.n_pix, h->cfg.compat_last_block, h->d_nuniq, h->d_nsub, 1);
     IG_MARK(7);
     IG_MARK(8);
@@ -2482,4 +2593,57 @@ extern "C" int ig_contact_thumbnail(ig_handle* h, const int32_t* sub_rank, int32
     CK(cudaStreamSynchronize(h->stream));
     cudaFree(d_rank); cudaFree(d_img);
     return 0;
+}
+
+// timeline of the last cycle run (IG_TIMELINE builds only): out[n_steps][IG_TL_KERNELS][2] = earliest block start /
+// latest block end of each kernel in %globaltimer ns (~0 / 0 when the kernel did not run in that step)
+extern "C" int ig_timeline_reset(ig_handle* h) {
+    if (use(h)) return -1;
+#ifdef IG_TIMELINE
+    std::vector<unsigned long long> init((size_t)IG_TL_STEPS * IG_TL_KERNELS * 2);
+    for (size_t i = 0; i < init.size(); i += 2) { init[i] = ~0ull; init[i + 1] = 0ull; }
+    CK(cudaMemcpyToSymbol(g_tl, init.data(), init.size() * sizeof(unsigned long long)));
+    int zero = 0;
+    CK(cudaMemcpyToSymbol(g_tl_step, &zero, sizeof zero));
+    return 0;
+#else
+    h->err = "library built without -DIG_TIMELINE";
+    return -1;
+#endif
+}
+extern "C" int ig_timeline_blocks(ig_handle* h, int32_t n_blocks, uint64_t* out) {
+    if (use(h)) return -1;
+#ifdef IG_TIMELINE
+    if (n_blocks > IG_TL_BLOCKS) n_blocks = IG_TL_BLOCKS;
+    CK(cudaMemcpyFromSymbol(out, g_tlb, (size_t)n_blocks * 4 * sizeof(unsigned long long)));
+    return 0;
+#else
+    (void)n_blocks; (void)out;
+    h->err = "library built without -DIG_TIMELINE";
+    return -1;
+#endif
+}
+extern "C" int ig_timeline_phases(ig_handle* h, uint64_t* out8, int32_t reset) {
+    if (use(h)) return -1;
+#ifdef IG_TIMELINE
+    CK(cudaMemcpyFromSymbol(out8, g_tlp, 8 * sizeof(unsigned long long)));
+    if (reset) { unsigned long long z[8] = {0}; CK(cudaMemcpyToSymbol(g_tlp, z, sizeof z)); }
+    return 0;
+#else
+    (void)out8; (void)reset;
+    h->err = "library built without -DIG_TIMELINE";
+    return -1;
+#endif
+}
+extern "C" int ig_timeline_get(ig_handle* h, int32_t n_steps, uint64_t* out) {
+    if (use(h)) return -1;
+#ifdef IG_TIMELINE
+    if (n_steps > IG_TL_STEPS) n_steps = IG_TL_STEPS;
+    CK(cudaMemcpyFromSymbol(out, g_tl, (size_t)n_steps * IG_TL_KERNELS * 2 * sizeof(unsigned long long)));
+    return 0;
+#else
+    (void)n_steps; (void)out;
+    h->err = "library built without -DIG_TIMELINE";
+    return -1;
+#endif
 }
