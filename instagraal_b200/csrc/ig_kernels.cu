@@ -34,6 +34,7 @@
 #define IG_SCORE_CTAS_PER_SM (24 / IG_WARPS_PER_BLOCK)
 #define IG_THREADS (IG_WARPS_PER_BLOCK * 32)
 #define IG_ROW_CHUNK 1024
+#define IG_FLAT_MAX_NNZ 1500000   // levels up to 1.5 M stored contacts take the flat scoring path (list: 64 B x nnz x 8)
 #define IG_ROWS_SMALL_CHUNKS 16  // levels of up to 16 Ki sub-fragments build the affected-row list in one launch
 #define IG_LANE_CUR 24  // lane that owns the current-state zero term in the score kernel
 
@@ -43,7 +44,7 @@ struct CoordRec { float dist; int id_c; int pos; float s_tot; };          // 16 
 struct __align__(16) SubX { int start_bp; int len_ori; float watson; float crick; };  // 16 B: what a rigid motion needs to
                                                                           // recompute a sub-fragment's coordinate (len_ori = len_bp * ori)
 
-struct __align__(16) RowInfo { int r; int cls; int n; int pad; long long b; long long pad2; CoordRec ci; };  // 48 B: all
+struct __align__(16) RowInfo { int r; int cls; int n; int pad; long long b; long long seg; CoordRec ci; };  // 48 B: all
                                    // k_score needs to start on an affected row, in one round trip
 struct CandInfo {  // per-candidate slice description (slice_sp_mat prologue, KA:526-551)
     int id_a, id_b, same, is_circ;
@@ -80,6 +81,9 @@ struct DevScalars {
     unsigned int ticket_cuts[IG_MAX_CANDS], ticket_rows[IG_MAX_CANDS], ticket_fin;  // last-block-done counters
     // measurement: algorithmic traffic of the scoring kernel, accumulated over steps
     unsigned long long st_contacts, st_rows, st_frags, st_selected, st_proposals;
+    // flat scoring path (small levels): per candidate, contacts selected / read / to evaluate
+    int flat_nsub[IG_MAX_CANDS], flat_nread[IG_MAX_CANDS], flat_total[IG_MAX_CANDS], flat_segtotal[IG_MAX_CANDS];
+    unsigned int ticket_pick[IG_MAX_CANDS];
 };
 
 struct CycleOut {  // compact per-step record of ig_run_cycle (128 B)
@@ -137,7 +141,7 @@ struct TlBlock {
 #define TLB() TlBlock tl_block_
 #define TLB_ITEM() tl_block_.items++
 // phase profile of the scoring kernel: cycles of warp 0 of every block, summed per phase
-__device__ unsigned long long g_tlp[8];
+__device__ unsigned long long g_tlp[16];
 #define TLP_DECL() long long tlp_t_ = clock64()
 #define TLP(ph) do { if (threadIdx.x == 0) { const long long n_ = clock64(); atomicAdd(&g_tlp[ph], (unsigned long long)(n_ - tlp_t_)); tlp_t_ = n_; } } while (0)
 #else
@@ -394,7 +398,8 @@ __global__ void k_cand_setup(const FragRec* __restrict__ live, DevScalars* sc, I
         c.up_a = max(0, pfa - n_bounds - A.sub_len); c.down_a = min(A.sub_l_cont - 1, pfa + n_bounds + A.sub_len);
         c.up_b = max(0, pfb - B.sub_len); c.down_b = min(B.sub_l_cont - 1, pfb + B.sub_len);
         c.n_rows = 0; c.n_sub = 0; c.row_hi = -1;
-        sc->ticket_cuts[k] = 0; sc->ticket_rows[k] = 0;
+        sc->ticket_cuts[k] = 0; sc->ticket_rows[k] = 0; sc->ticket_pick[k] = 0;
+        sc->flat_nsub[k] = 0; sc->flat_nread[k] = 0; sc->flat_total[k] = 0;
     }
     __syncthreads();
     if (k < n) {
@@ -599,7 +604,7 @@ k_rows_write(const CoordRec* __restrict__ coord, int ns, const DevScalars* __res
         const int cls = ig_class_of(s_bp, s_bp + IG_MAX_BP, s_bp[IG_MAX_BP + 2], s_bp[IG_MAX_BP + 3], cr.id_c, cr.pos);
         rowidx[(size_t)k * rows_stride + r] = off | (cls << IG_CLS_SHIFT);
         const long long b = row_ptr[r];
-        RowInfo ri; ri.r = r; ri.cls = cls; ri.n = (int)(row_ptr[r + 1] - b); ri.pad = 0; ri.b = b; ri.pad2 = 0; ri.ci = cr;
+        RowInfo ri; ri.r = r; ri.cls = cls; ri.n = (int)(row_ptr[r + 1] - b); ri.pad = 0; ri.b = b; ri.seg = 0; ri.ci = cr;
         rinfo[(size_t)k * rows_stride + off] = ri;
         row_cnt[(size_t)k * rows_stride + off] = 0;  // k_score (block mode) accumulates into it
     }
@@ -614,26 +619,37 @@ k_rows_small(const CoordRec* __restrict__ coord, int ns, DevScalars* sc, int n_c
     TL(3);
     const int k = blockIdx.x;
     if (k >= sc->n_cands) return;
-    __shared__ int wsum[32];
+    __shared__ int wsum[32], wlen[32];
     __shared__ int s_bp[IG_MAX_BP + 4];
     if (threadIdx.x < IG_MAX_BP + 4) s_bp[threadIdx.x] = reinterpret_cast<const int*>(clstab + k)[threadIdx.x];
     const CandInfo ci_k = sc->ci[k];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int base = 0;
+    int base = 0, seg_base = 0;   // rows so far / stored contacts of those rows (segment offsets of the flat list)
     for (int ch = 0; ch < n_chunks; ch++) {
         const int r = ch * IG_ROW_CHUNK + threadIdx.x;
         CoordRec cr;
         if (r < ns) cr = coord[r];
         const bool f = r < ns && row_affected(cr, ci_k);
         const unsigned b = __ballot_sync(0xffffffffu, f);
-        __syncthreads();   // wsum of the previous chunk fully consumed
+        long long rb = 0;
+        int rn = 0;
+        if (f) { rb = row_ptr[r]; rn = (int)(row_ptr[r + 1] - rb); }
+        const int rn_pad = (rn + 31) & ~31;   // rows own whole 32-contact chunks of the flat list
+        int lx = rn_pad;   // inclusive warp scan of the padded row lengths
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, lx, o); if (lane >= o) lx += y; }
+        __syncthreads();   // wsum / wlen of the previous chunk fully consumed
         if (lane == 0) wsum[w] = __popc(b);
+        if (lane == 31) wlen[w] = lx;
         __syncthreads();
         if (w == 0) {
-            int s = wsum[lane];
+            int s = wsum[lane], l = wlen[lane];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
-            wsum[lane] = s;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, s, o), z = __shfl_up_sync(0xffffffffu, l, o);
+                if (lane >= o) { s += y; l += z; }
+            }
+            wsum[lane] = s; wlen[lane] = l;
         }
         __syncthreads();
         if (f) {
@@ -641,14 +657,14 @@ k_rows_small(const CoordRec* __restrict__ coord, int ns, DevScalars* sc, int n_c
             rows[(size_t)k * rows_stride + off] = r;
             const int cls = ig_class_of(s_bp, s_bp + IG_MAX_BP, s_bp[IG_MAX_BP + 2], s_bp[IG_MAX_BP + 3], cr.id_c, cr.pos);
             rowidx[(size_t)k * rows_stride + r] = off | (cls << IG_CLS_SHIFT);
-            const long long rb = row_ptr[r];
-            RowInfo ri; ri.r = r; ri.cls = cls; ri.n = (int)(row_ptr[r + 1] - rb); ri.pad = 0; ri.b = rb; ri.pad2 = 0; ri.ci = cr;
+            RowInfo ri; ri.r = r; ri.cls = cls; ri.n = rn; ri.pad = 0; ri.b = rb; ri.ci = cr;
+            ri.seg = (long long)(seg_base + (w ? wlen[w - 1] : 0) + lx - rn_pad);
             rinfo[(size_t)k * rows_stride + off] = ri;
             row_cnt[(size_t)k * rows_stride + off] = 0;
         }
-        base += wsum[31];
+        base += wsum[31]; seg_base += wlen[31];
     }
-    if (threadIdx.x == 0) sc->ci[k].n_rows = base;
+    if (threadIdx.x == 0) { sc->ci[k].n_rows = base; sc->flat_segtotal[k] = seg_base; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -779,28 +795,33 @@ __global__ void k_prefetch_l2(PfList L) {
 // added to the executing lane's accumulator (only the sum over lanes matters; the order is fixed,
 // hence deterministic).
 struct __align__(16) QEnt { float s; int dp; unsigned mask; int val; };  // 16 B; mask bit 31: subtract
-#define IG_QCAP 64
+#define IG_QCAP 96   // a flush is triggered at 64 entries; at most 32 more arrive before it
 #define IG_QSUB 0x80000000u
 
 // term of a linear-contig contact at 0 < s < d_max WITHOUT the part that depends on the observed count only
 // (it cancels in t_mut - t_cur)
-#ifdef IG_EVALQ_INLINE
-__device__ __forceinline__
-#else
-__device__ __noinline__
-#endif
-void eval_queue(const QEnt* __restrict__ q, int n, double* __restrict__ my_acc, const Params& p,
-                                           double l10v, const float* __restrict__ exz_tab) {
+__device__ __forceinline__ double queued_term(const QEnt& e, const Params& p, double l10v, float exz) {
+    const float exf = fmaxf((p.d == 2.0f) ? (p.c1 * powf(e.s, p.slope)) * p.fact
+                                          : (p.c1 * powf(e.s, p.slope) * expf((p.d - 2) / (powf(e.s * p.lm / p.kuhn, 2.0f) + p.d))) * p.fact,
+                            p.v_inter);  // rippe_contacts for 0 < s < d_max (KA:153-163)
+    const double t = pxl_term(exf, (double)e.val, 0.0, l10v, p.v_inter) + (double)exz * LOG10E_F;
+    return (e.mask & IG_QSUB) ? -t : t;
+}
+// Evaluates the first n (<= 64) queue entries: every lane takes entries `lane` and `lane + 32`, two independent
+// dependency chains of powf + f64 log10 that the scheduler interleaves (the chains are long and serial, so a
+// second one per lane is almost free).
+__device__ __noinline__ void eval_queue(const QEnt* __restrict__ q, int n, double* __restrict__ my_acc, const Params& p,
+                                        double l10v, const float* __restrict__ exz_tab) {
     const int lane = threadIdx.x & 31;
-    if (lane < n) {
-        const QEnt e = q[lane];
-        const float exf = fmaxf((p.d == 2.0f) ? (p.c1 * powf(e.s, p.slope)) * p.fact
-                                              : (p.c1 * powf(e.s, p.slope) * expf((p.d - 2) / (powf(e.s * p.lm / p.kuhn, 2.0f) + p.d))) * p.fact,
-                                p.v_inter);  // rippe_contacts for 0 < s < d_max (KA:153-163)
-        double t = pxl_term(exf, (double)e.val, 0.0, l10v, p.v_inter) + (double)exz_tab[e.dp] * LOG10E_F;
-        if (e.mask & IG_QSUB) t = -t;
-        for (unsigned m = e.mask & 0xffffffu; m; m &= m - 1) my_acc[(__ffs(m) - 1) * IG_THREADS] += t;
-    }
+    const bool v0 = lane < n, v1 = lane + 32 < n;
+    QEnt e0 = {1.0f, 0, 0u, 0}, e1 = {1.0f, 0, 0u, 0};
+    if (v0) e0 = q[lane];
+    if (v1) e1 = q[lane + 32];
+    const float z0 = exz_tab[e0.dp], z1 = exz_tab[e1.dp];
+    const double t0 = queued_term(e0, p, l10v, z0);
+    const double t1 = queued_term(e1, p, l10v, z1);
+    for (unsigned m = e0.mask & 0xffffffu; m; m &= m - 1) my_acc[(__ffs(m) - 1) * IG_THREADS] += t0;
+    for (unsigned m = e1.mask & 0xffffffu; m; m &= m - 1) my_acc[(__ffs(m) - 1) * IG_THREADS] += t1;
 }
 
 // one selected contact as the slot loop needs it (column end + current state)
@@ -845,7 +866,7 @@ __device__ __forceinline__ bool eval_pair(const Ctc& x, int u, const RowMut a, c
     return true;
 }
 
-// warp-collective append to the warp's queue of expensive evaluations; a full batch of 32 is evaluated at once
+// warp-collective append to the warp's queue of expensive evaluations; a batch of 64 is evaluated at once
 __device__ __forceinline__ void queue_push(bool push, float s, int dp, unsigned mask, int val, QEnt* __restrict__ myq, int& qn,
                                            double* __restrict__ my_acc, const Params& p, double l10v, const float* __restrict__ exz_tab) {
     const unsigned pm = __ballot_sync(0xffffffffu, push);
@@ -857,11 +878,11 @@ __device__ __forceinline__ void queue_push(bool push, float s, int dp, unsigned 
     }
     qn += __popc(pm);
     __syncwarp();
-    if (qn >= 32) {
-        eval_queue(myq, 32, my_acc, p, l10v, exz_tab);
+    if (qn >= 64) {
+        eval_queue(myq, 64, my_acc, p, l10v, exz_tab);
         __syncwarp();
-        if (lane < qn - 32) { const QEnt mv = myq[32 + lane]; myq[lane] = mv; }
-        qn -= 32;
+        if (lane < qn - 64) { const QEnt mv = myq[64 + lane]; myq[lane] = mv; }
+        qn -= 64;
         __syncwarp();
     }
 }
@@ -1083,7 +1104,7 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
             touched |= __reduce_or_sync(0xffffffffu, chg);
         }
         TLP(2);   // contact loop
-        if (qn > 0) { eval_queue(myq, qn, my_acc, p, l10v, exz_tab); }
+        if (qn > 0) { eval_queue(myq, qn, my_acc, p, l10v, exz_tab); }   // qn < 64 here
         __syncwarp();
         // fixed-order accumulation into this warp's slot sums (work items are visited in a fixed order); only
         // the slots that received a term are reduced, and their accumulators are put back to zero
@@ -1119,6 +1140,228 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
 }
 #define IG_SCORE_SMEM (IG_N_OPS * IG_THREADS * sizeof(double))
 
+// ------------------------------------------------------------------------------------------------
+// FLAT scoring path for small levels (yeast scale: a candidate touches a few hundred rows of ~100 contacts).
+// There the row-per-warp kernel above is all latency: one tiny work item per warp, each a chain of dependent
+// gathers plus a partly filled evaluation queue, and half of the lanes hold contacts outside the slice.  Instead:
+//   k_pick      one warp per 32-contact chunk of an affected row (rows own whole chunks of a per-candidate list,
+//               offsets = running sum of the padded row lengths from k_rows_small): slice membership, class-pair
+//               mask, current-state term; the contacts that need a look under at least one mutation are written
+//               compactly (ballot prefix) at the start of their chunk (+ the count), so the list order is fixed;
+//   k_eval_flat work item = (one chunk's packed contacts, group of uniq slots): no selection, no gathers by
+//               column, no per-row set-up; loop over the group's mutations exactly like the dense schedule of
+//               k_score (same eval_pair / queue code), one accumulator reduction per block.
+// Results are the same sums in a different (still fixed) order.
+#define IG_PICK_PARTS 4
+struct __align__(16) FlatRec {   // 64 B
+    int pos, start_bp, len_ori; float watson; float crick; int val; float cur_s; int cur_dp;
+    int rjc, flags; double t_cur; int ri; unsigned m; int pad[2];
+};                               // flags: 1 same contig now, 2 current term deferred, 4 the row's contig is circular
+
+__global__ void __launch_bounds__(IG_THREADS, IG_SCORE_CTAS_PER_SM)
+k_pick(const int2* __restrict__ cv, const CoordRec* __restrict__ coord, const int* __restrict__ clen, DevScalars* sc,
+       const IgDescriptor* __restrict__ desc_g, const int* __restrict__ rowidx, int ns, int* __restrict__ row_cnt,
+       int* __restrict__ flat_cnt, size_t chunk_stride, int* __restrict__ part_c, FlatRec* __restrict__ flat, size_t flat_stride,
+       float mbar, const float* __restrict__ exz_tab, const IgClassTab* __restrict__ clstab, const SubX* __restrict__ subx,
+       const RowInfo* __restrict__ rinfo) {
+    TL(15);
+    TLP_DECL();
+    const int k = blockIdx.y;
+    if (k >= sc->n_cands) return;
+    __shared__ int s_sel, s_read;
+    const CandInfo ci_k = sc->ci[k];
+    const int n_items = ci_k.n_rows * IG_PICK_PARTS;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int wg = blockIdx.x * IG_WARPS_PER_BLOCK + w, nw = gridDim.x * IG_WARPS_PER_BLOCK;
+    if (threadIdx.x == 0) { s_sel = 0; s_read = 0; }
+    __syncthreads();
+    if ((int)blockIdx.x * IG_WARPS_PER_BLOCK < n_items) {
+        const Params p = sc->p;
+        const double l10v = sc->log10_vinter;
+        const double inter_const = (double)p.v_inter * LOG10E_F;
+        const unsigned allmask = (1u << desc_g[k].n_uniq) - 1u;
+        const unsigned* g_mask = clstab[k].mask;
+        const unsigned* g_farok = clstab[k].farok;
+        const float far_s = clstab[k].far_s;
+        const int far_dp = clstab[k].far_dp;
+        const int* my_idx = rowidx + (size_t)k * ns;
+        FlatRec* my_flat = flat + (size_t)k * flat_stride;
+        int* my_cnt = flat_cnt + (size_t)k * chunk_stride;
+        TLP(8);   // prologue
+        int sel_w = 0, read_w = 0;
+        for (int it = wg; it < n_items; it += nw) {
+            const int ri = it / IG_PICK_PARTS, part = it - ri * IG_PICK_PARTS;
+            const RowInfo info = rinfo[(size_t)k * ns + ri];
+            const CoordRec ci = info.ci;
+            const unsigned* mrow = g_mask + info.cls * IG_MAX_CLS;
+            const long long b = info.b, e = info.b + info.n;
+            int row_sel = 0;
+            for (long long q0 = b + 32 * part; q0 < e; q0 += 32 * IG_PICK_PARTS) {
+                const long long q = q0 + lane;
+                FlatRec x;
+                x.m = 0;
+                if (q < e) {
+                    const int2 c = __ldg(&cv[q]);
+                    const CoordRec cj = coord[c.x];
+                    if ((cj.id_c == ci_k.id_a || cj.id_c == ci_k.id_b) && contact_selected(ci, cj, c.y, ci_k)) {
+                        row_sel++;
+                        x.rjc = my_idx[c.x];
+                        x.pos = cj.pos; x.val = c.y; x.ri = ri;
+                        x.cur_s = fabsf(ci.dist - cj.dist);
+                        x.cur_dp = abs(ci.pos - cj.pos);
+                        const bool cur_same = ci.id_c == cj.id_c;
+                        unsigned m = __ldg(&mrow[x.rjc >> IG_CLS_SHIFT]) & allmask;
+                        if (m && cur_same && ci.s_tot == 0 && x.cur_s >= far_s && x.cur_dp >= far_dp)
+                            m &= ~__ldg(&g_farok[info.cls * IG_MAX_CLS + (x.rjc >> IG_CLS_SHIFT)]);
+                        if (m) {
+                            const SubX sx = subx[c.x];
+                            x.start_bp = sx.start_bp; x.len_ori = sx.len_ori; x.watson = sx.watson; x.crick = sx.crick;
+                            const double ob = (double)c.y;
+                            x.flags = (cur_same ? 1 : 0) | (ci.s_tot != 0 ? 4 : 0);
+                            x.t_cur = 0.0;
+                            if (!cur_same) x.t_cur = pxl_term(p.v_inter, ob, 0.0, l10v, p.v_inter) + inter_const;
+                            else if (ci.s_tot != 0) x.t_cur = contact_term(ci, cj, clen[c.x], ob, 0.0, p, l10v, mbar, exz_tab);
+                            else if (!((x.cur_s > 0.0f) && (x.cur_s < p.d_max))) x.t_cur = pxl_term(p.v_inter, ob, 0.0, l10v, p.v_inter) + (double)exz_tab[x.cur_dp] * LOG10E_F;
+                            else x.flags |= 2;
+                            x.pad[0] = 0; x.pad[1] = 0;
+                        }
+                        x.m = m;
+                    }
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, x.m != 0);
+                const long long slot0 = info.seg + (q0 - b);   // this chunk's 32 list slots
+                if (x.m) my_flat[slot0 + __popc(bal & ((1u << lane) - 1))] = x;
+                if (lane == 0) my_cnt[slot0 >> 5] = __popc(bal);
+            }
+            row_sel = __reduce_add_sync(0xffffffffu, row_sel);
+            if (lane == 0 && row_sel) atomicAdd(&row_cnt[(size_t)k * ns + ri], row_sel);   // zeroed by k_rows_small
+            sel_w += row_sel;
+            if (part == 0) read_w += info.n;
+        }
+        TLP(9);   // chunk loop
+        if (lane == 0 && (sel_w | read_w)) { atomicAdd(&s_sel, sel_w); atomicAdd(&s_read, read_w); }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        part_c[PART_IDX(k, 2, 0, gridDim.x, blockIdx.x)] = s_sel;
+        part_c[PART_IDX(k, 2, 1, gridDim.x, blockIdx.x)] = s_read;
+    }
+}
+
+__global__ void __launch_bounds__(IG_THREADS, IG_SCORE_CTAS_PER_SM)
+k_eval_flat(const DevScalars* __restrict__ sc, const IgDescriptor* __restrict__ desc_g, int ns, const int* __restrict__ flat_cnt,
+            size_t chunk_stride, const FlatRec* __restrict__ flat, size_t flat_stride, const RowMut* __restrict__ table,
+            const int* __restrict__ table_len, float mbar, const float* __restrict__ exz_tab, double* __restrict__ part_nz,
+            const IgClassTab* __restrict__ clstab) {
+    TL(6);
+    TLP_DECL();
+    extern __shared__ double acc_s[];                 // [IG_N_OPS][IG_THREADS]
+    __shared__ double red[IG_WARPS_PER_BLOCK][IG_N_OPS];
+    __shared__ QEnt queue[IG_WARPS_PER_BLOCK][IG_QCAP];
+    // The blocks of ONE grid are dealt to the candidates in proportion to their number of chunks (a candidate in
+    // two long contigs has many times the contacts of one in two short ones: equal shares would wait for the
+    // largest); inside a candidate the items = (chunk, group of gs uniq slots) are strided over its warps.
+    const int n_cands = sc->n_cands;
+    int tiles_all = 0, n_nonempty = 0;
+    for (int c = 0; c < n_cands; c++) { const int t = sc->flat_segtotal[c] >> 5; tiles_all += t; n_nonempty += t > 0; }
+    int k = -1, b_first = 0, n_blocks_k = 0, tiles_k = 0;
+    {
+        const int spare = (int)gridDim.x - n_nonempty;
+        int b0 = 0;
+        for (int c = 0; c < n_cands; c++) {
+            const int t = sc->flat_segtotal[c] >> 5;
+            if (t == 0) continue;
+            const int nb = 1 + (int)(((long long)spare * t) / tiles_all);
+            if ((int)blockIdx.x >= b0 && (int)blockIdx.x < b0 + nb) { k = c; b_first = b0; n_blocks_k = nb; tiles_k = t; }
+            b0 += nb;
+        }
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int i = lane; i < IG_N_OPS; i += 32) red[w][i] = 0.0;
+    __syncwarp();
+    if (k >= 0) {
+    const int nw = n_blocks_k * IG_WARPS_PER_BLOCK;
+    int gs = IG_N_OPS;
+    while (gs > 3 && tiles_k * (IG_N_OPS / gs) < 2 * nw) gs >>= 1;
+    const int ng = IG_N_OPS / gs;
+    const int n_items = tiles_k * ng;
+    const int wg = ((int)blockIdx.x - b_first) * IG_WARPS_PER_BLOCK + w;
+    for (int u = 0; u < IG_N_OPS; u++) acc_s[u * IG_THREADS + threadIdx.x] = 0.0;
+    const Params p = sc->p;
+    const double l10v = sc->log10_vinter;
+    const double inter_const = (double)p.v_inter * LOG10E_F;
+    double* my_acc = acc_s + threadIdx.x;
+    QEnt* myq = queue[w];
+    int qn = 0;
+    unsigned touched = 0;
+    const int n_uniq = desc_g[k].n_uniq;
+    const int* cnt = flat_cnt + (size_t)k * chunk_stride;
+    const FlatRec* my_flat = flat + (size_t)k * flat_stride;
+    const RowMut* tab = table + (size_t)k * IG_N_OPS * ns;
+    const int* tlen = table_len + (size_t)k * IG_N_OPS * ns;
+    const IgMotion* g_mot = clstab[k].mot;
+    TLP(12);  // prologue
+    for (int it = wg; it < n_items; it += nw) {
+        const int tile = it / ng, grp = it - tile * ng;
+        const int u0 = grp * gs;
+        if (u0 >= n_uniq) continue;
+        const unsigned gmask = ((1u << gs) - 1u) << u0;
+        unsigned m = 0;
+        Ctc x;
+        x.pos = 0; x.start_bp = 0; x.len_ori = 0; x.watson = 0.f; x.crick = 0.f; x.val = 0; x.cur_s = 0.f; x.cur_dp = 0;
+        x.rjc = 0; x.t_cur = 0.0; x.flags = 0;
+        int ri = 0;
+        float row_s_tot = 0.f;
+        if (lane < __ldg(&cnt[tile])) {
+            const FlatRec r = my_flat[((size_t)tile << 5) + lane];
+            x.pos = r.pos; x.start_bp = r.start_bp; x.len_ori = r.len_ori; x.watson = r.watson; x.crick = r.crick; x.val = r.val;
+            x.cur_s = r.cur_s; x.cur_dp = r.cur_dp; x.rjc = r.rjc; x.t_cur = r.t_cur; x.flags = r.flags;
+            ri = r.ri;
+            m = r.m & gmask;
+            row_s_tot = (r.flags & 4) ? 1.0f : 0.0f;   // eval_pair only asks whether the row's contig is circular
+        }
+        const unsigned um = __reduce_or_sync(0xffffffffu, m);
+        if (!um) continue;
+        unsigned chg = 0;
+        RowMut a_nxt = tab[(size_t)(__ffs(um) - 1) * ns + ri];   // row-end entry, fetched one mutation ahead
+#pragma unroll 1
+        for (unsigned uw = um; uw; uw &= uw - 1) {
+            const int u = __ffs(uw) - 1;
+            const RowMut a = a_nxt;
+            const unsigned rest = uw & (uw - 1);
+            if (rest) a_nxt = tab[(size_t)(__ffs(rest) - 1) * ns + ri];
+            float s_m = 0.f; int dp_m = 0; bool push = false;
+            if ((m >> u) & 1u) {
+                double add;
+                if (eval_pair(x, u, a, g_mot, row_s_tot, p, l10v, inter_const, mbar, exz_tab, tab, tlen, ns, s_m, dp_m, push, add)) {
+                    chg |= 1u << u;
+                    my_acc[u * IG_THREADS] += add;
+                }
+            }
+            queue_push(push, s_m, dp_m, 1u << u, x.val, myq, qn, my_acc, p, l10v, exz_tab);
+        }
+        queue_push((x.flags & 2) && chg, x.cur_s, x.cur_dp, chg | IG_QSUB, x.val, myq, qn, my_acc, p, l10v, exz_tab);
+        touched |= __reduce_or_sync(0xffffffffu, chg);
+    }
+    TLP(13);  // items
+    if (qn > 0) { eval_queue(myq, qn, my_acc, p, l10v, exz_tab); }
+    __syncwarp();
+    for (unsigned tw = touched; tw; tw &= tw - 1) {
+        const int us = __ffs(tw) - 1;
+        const double v = warp_sum(my_acc[us * IG_THREADS]);
+        if (lane == 0) red[w][us] = v;
+    }
+    TLP(14);  // final flush + reductions
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_cands * 25; i += blockDim.x) {
+        const int c = i / 25, u = i - c * 25;
+        double v = 0.0;
+        if (c == k && u < IG_N_OPS) for (int ww = 0; ww < IG_WARPS_PER_BLOCK; ww++) v += red[ww][u];
+        part_nz[PART_IDX(c, 25, u, gridDim.x, blockIdx.x)] = v;
+    }
+}
+
 __device__ void select_step(DevScalars* sc, const IgDescriptor* __restrict__ desc_g);
 
 // K9: per-candidate finalisation: fixed-order parallel reduction of the block partials, the
@@ -1130,7 +1373,7 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
            int ns, const int* __restrict__ row_cnt, const RowMut* __restrict__ table, const int* __restrict__ table_len,
            float mbar, const float* __restrict__ exz_tab, const double* __restrict__ part_nz, const int* __restrict__ part_c,
            int n_part, const double* __restrict__ part_z, const int* __restrict__ part_i, int n_part_z, double n_pix,
-           int compat_last_block, int* __restrict__ n_uniq_out, int* __restrict__ n_sub_out, int do_select) {
+           int compat_last_block, int* __restrict__ n_uniq_out, int* __restrict__ n_sub_out, int do_select, int n_part_c) {
     TL(7);
     TLP_DECL();
     const int k = blockIdx.x;
@@ -1167,8 +1410,9 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
             v = warp_sum(v);
             if (lane == 0) { if (slot < 25) s_nz[slot] = v; else s_z[slot - 25] = v; }
         } else {
-            const int* src = slot < 75 ? &part_i[PART_IDX(k, 25, slot - 50, n_part_z, 0)] : &part_c[PART_IDX(k, 2, slot - 75, n_part, 0)];
-            const int n = slot < 75 ? n_part_z : n_part;
+            // (the selection counters may come from another kernel than the likelihood partials: own block count)
+            const int* src = slot < 75 ? &part_i[PART_IDX(k, 25, slot - 50, n_part_z, 0)] : &part_c[PART_IDX(k, 2, slot - 75, n_part_c, 0)];
+            const int n = slot < 75 ? n_part_z : n_part_c;
             int v = 0;
             for (int i0 = 0; i0 < n; i0 += 32 * 16) {
                 int x[16];
@@ -1708,6 +1952,8 @@ struct ig_handle {
     cudaStream_t stream, side, pf;
     cudaEvent_t ev_coords, ev_lnz, ev_fork, ev_sel, ev_out, ev_cuts, ev_cls;
     bool rows_small;  // affected-row list in one launch (small levels)
+    bool flat;        // flat scoring path (k_pick + k_eval_flat) for small levels
+    int grid_pick, grid_flat; int *flat_cnt, *flat_off; FlatRec* flat_list; size_t flat_stride, chunk_stride;
     bool prefetch;  // the level's arrays fit the L2 comfortably: prefetch them at the start of a step
     FragRec *live, *init_live;
     SubRec* sub;
@@ -1843,12 +2089,23 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
         if (dev_alloc(h, &h->chunk_cnt, (size_t)IG_MAX_CANDS * h->n_chunks)) return -2;
         h->rows_small = h->n_chunks <= IG_ROWS_SMALL_CHUNKS;
         if (const char* e = getenv("IG_ROWS_SMALL")) h->rows_small = h->rows_small && atoi(e) != 0;   // tests: force the two-pass list
+        h->flat = h->rows_small && h->nnz <= IG_FLAT_MAX_NNZ;
+        if (const char* e = getenv("IG_FLAT")) h->flat = h->flat && atoi(e) != 0;
+        if (getenv("IG_FORCE_SPLIT")) h->flat = false;   // experiments / tests of the row-per-warp kernel
+        h->flat_cnt = nullptr; h->flat_off = nullptr; h->flat_list = nullptr; h->flat_stride = (size_t)h->nnz + 32 * (size_t)ns + 32;   // rows own whole 32-contact chunks
+        h->chunk_stride = h->flat_stride / 32 + 1;
+        if (h->flat) {
+            if (dev_alloc(h, &h->flat_cnt, (size_t)IG_MAX_CANDS * h->chunk_stride) ||
+                dev_alloc(h, &h->flat_list, (size_t)IG_MAX_CANDS * h->flat_stride)) return -2;
+        }
         if (dev_alloc(h, &h->rows, (size_t)IG_MAX_CANDS * ns) || dev_alloc(h, &h->row_cnt, (size_t)IG_MAX_CANDS * ns)) return -2;
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, cfg->device));
         const int sms = prop.multiProcessorCount;
         h->grid_score = sms * IG_SCORE_CTAS_PER_SM;  // 24 resident warps per SM (80 registers per thread; 6 KB of accumulators per warp)
         CK(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IG_SCORE_SMEM));
+        CK(cudaFuncSetAttribute(k_eval_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IG_SCORE_SMEM));
+        h->grid_flat = (sms * IG_SCORE_CTAS_PER_SM) / 5; h->grid_pick = h->grid_flat;   // a step's (usually 5) candidates fill the GPU once
         h->grid_pre = sms * 2;   // 2 resident CTAs of 25 warps per SM
         {
             const char* e = getenv("IG_PREFETCH");
@@ -1924,7 +2181,7 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
 extern "C" void ig_destroy(ig_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
-    void* ptrs[] = {h->clstab, h->subx, h->rinfo, h->nb_ptr, h->nb_idx, h->nb_cdf, h->nb_nnz, h->cyc_frags, h->live, h->part_out, h->part_c, h->table, h->table_len, h->rowidx, h->init_live, h->sub, h->coord, h->clen, h->row_ptr, h->cv, h->sym_diag,
+    void* ptrs[] = {h->flat_cnt, h->flat_off, h->flat_list, h->clstab, h->subx, h->rinfo, h->nb_ptr, h->nb_idx, h->nb_cdf, h->nb_nnz, h->cyc_frags, h->live, h->part_out, h->part_c, h->table, h->table_len, h->rowidx, h->init_live, h->sub, h->coord, h->clen, h->row_ptr, h->cv, h->sym_diag,
                     h->init_prev, h->init_next, h->orientable, h->sc, h->desc, h->exz, h->exz_test, h->chunk_cnt,
                     h->rows, h->row_cnt, h->part_nz, h->part_z, h->part_i, h->part_full, h->part_zc, h->part_nc,
                     h->d_nuniq, h->d_nsub, h->d_perm, h->d_hist};
@@ -2090,7 +2347,14 @@ static int score_candidates(ig_handle* h, int a, const int32_t* cands, int n, in
     k_precompute<<<dim3(h->grid_pre, n), IG_PRE_THREADS, 0, h->stream>>>(h->coord, h->clen, live, h->sub, h->sc, h->desc, h->rows, h->ns,
                                                                     h->table, h->table_len, mbar, h->part_z, h->part_i);
     if (h->profile) cudaEventRecord(h->ev[4], h->stream);
-    const int gsx = score_grid_x(h, n);
+    const int gsx = h->flat ? h->grid_flat : score_grid_x(h, n);
+    if (h->flat) {
+        k_pick<<<dim3(gsx, n), IG_THREADS, 0, h->stream>>>(h->cv, h->coord, h->clen, h->sc, h->desc, h->rowidx, h->ns, h->row_cnt,
+                                                                    h->flat_cnt, h->chunk_stride, h->part_c, h->flat_list, h->flat_stride, mbar, h->exz,
+                                                                    h->clstab, h->subx, h->rinfo);
+        k_eval_flat<<<h->grid_score, IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->sc, h->desc, h->ns, h->flat_cnt, h->chunk_stride, h->flat_list,
+                                                                            h->flat_stride, h->table, h->table_len, mbar, h->exz, h->part_nz, h->clstab);
+    } else
     k_score<<<dim3(gsx, n), IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
                                                                  h->ns, h->row_cnt, h->table, h->table_len, mbar, h->exz, h->part_nz,
                                                                  h->part_c, h->gs_div, h->clstab, h->subx, h->rinfo, h->sparse_div);
@@ -2098,8 +2362,8 @@ static int score_candidates(ig_handle* h, int a, const int32_t* cands, int n, in
     h->n_launches += 7;
     if (overlap) cudaStreamWaitEvent(h->stream, h->ev_lnz, 0);
     k_finalize<<<n, 1024, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->sc, h->desc, h->rows, h->rowidx, h->ns, h->row_cnt, h->table,
-                                         h->table_len, mbar, h->exz, h->part_nz, h->part_c, gsx, h->part_z, h->part_i,
-                                         h->grid_pre, h->cfg.n_pix, h->cfg.compat_last_block, h->d_nuniq, h->d_nsub, 0);
+                                         h->table_len, mbar, h->exz, h->part_nz, h->part_c, h->flat ? h->grid_score : gsx, h->part_z, h->part_i,
+                                         h->grid_pre, h->cfg.n_pix, h->cfg.compat_last_block, h->d_nuniq, h->d_nsub, 0, gsx);
     return launch_ok(h, "score_candidates");
 }
 
@@ -2206,7 +2470,14 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands, int cycle = 0)
     if (h->profile && !h->capturing) cudaEventRecord(h->ev[4], h->stream);
     cudaStreamWaitEvent(h->stream, h->ev_cls, 0);
     IG_MARK(5);
-    const int gsx = score_grid_x(h, n);
+    const int gsx = h->flat ? h->grid_flat : score_grid_x(h, n);
+    if (h->flat) {
+        k_pick<<<dim3(gsx, n), IG_THREADS, 0, h->stream>>>(h->cv, h->coord, h->clen, h->sc, h->desc, h->rowidx, h->ns, h->row_cnt,
+                                                                    h->flat_cnt, h->chunk_stride, h->part_c, h->flat_list, h->flat_stride, mbar, h->exz,
+                                                                    h->clstab, h->subx, h->rinfo);
+        k_eval_flat<<<h->grid_score, IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->sc, h->desc, h->ns, h->flat_cnt, h->chunk_stride, h->flat_list,
+                                                                            h->flat_stride, h->table, h->table_len, mbar, h->exz, h->part_nz, h->clstab);
+    } else
     k_score<<<dim3(gsx, n), IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
                                                                  h->ns, h->row_cnt, h->table, h->table_len, mbar, h->exz, h->part_nz,
                                                                  h->part_c, h->gs_div, h->clstab, h->subx, h->rinfo, h->sparse_div);
@@ -2214,8 +2485,8 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands, int cycle = 0)
     cudaStreamWaitEvent(h->stream, h->ev_lnz, 0);
     IG_MARK(6);
     k_finalize<<<n, 1024, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->sc, h->desc, h->rows, h->rowidx, h->ns, h->row_cnt, h->table,
-                                         h->table_len, mbar, h->exz, h->part_nz, h->part_c, gsx, h->part_z, h->part_i,
-                                         h->grid_pre, h->cfg.n_pix, h->cfg.compat_last_block, h->d_nuniq, h->d_nsub, 1);
+                                         h->table_len, mbar, h->exz, h->part_nz, h->part_c, h->flat ? h->grid_score : gsx, h->part_z, h->part_i,
+                                         h->grid_pre, h->cfg.n_pix, h->cfg.compat_last_block, h->d_nuniq, h->d_nsub, 1, gsx);
     IG_MARK(7);
     IG_MARK(8);
     // independent of apply/post: runs beside them on the side stream, joined before the result copy
@@ -2284,7 +2555,7 @@ extern "C" int ig_step(ig_handle* h, int32_t id_frag, const int32_t* cands, int3
     }
     cudaEventRecord(h->ev[1], h->stream);
     CK(cudaStreamSynchronize(h->stream));
-    h->n_launches += (full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR) - (h->rigid ? 1 : 0) + (h->prefetch ? 1 : 0) - (h->rows_small ? 1 : 0);
+    h->n_launches += (full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR) - (h->rigid ? 1 : 0) + (h->prefetch ? 1 : 0) - (h->rows_small ? 1 : 0) + (h->flat ? 1 : 0);
     h->steps_since_full = full ? 1 : h->steps_since_full + 1;
     h->n_full += full;
     h->incr_valid = true;
@@ -2337,7 +2608,7 @@ static int run_plan(ig_handle* h, int n_steps, GridN grid_n, ig_cycle_step* out)
         h->steps_since_full = full ? 1 : h->steps_since_full + 1;
         h->n_full += full;
         h->incr_valid = true;
-        h->n_launches += (full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR) - (h->rigid ? 1 : 0) + (h->prefetch ? 1 : 0) - (h->rows_small ? 1 : 0);
+        h->n_launches += (full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR) - (h->rigid ? 1 : 0) + (h->prefetch ? 1 : 0) - (h->rows_small ? 1 : 0) + (h->flat ? 1 : 0);
     }
     cudaEventRecord(h->ev[1], h->stream);
     std::vector<CycleOut> res(n_steps);
@@ -2626,8 +2897,8 @@ extern "C" int ig_timeline_blocks(ig_handle* h, int32_t n_blocks, uint64_t* out)
 extern "C" int ig_timeline_phases(ig_handle* h, uint64_t* out8, int32_t reset) {
     if (use(h)) return -1;
 #ifdef IG_TIMELINE
-    CK(cudaMemcpyFromSymbol(out8, g_tlp, 8 * sizeof(unsigned long long)));
-    if (reset) { unsigned long long z[8] = {0}; CK(cudaMemcpyToSymbol(g_tlp, z, sizeof z)); }
+    CK(cudaMemcpyFromSymbol(out8, g_tlp, 16 * sizeof(unsigned long long)));
+    if (reset) { unsigned long long z[16] = {0}; CK(cudaMemcpyToSymbol(g_tlp, z, sizeof z)); }
     return 0;
 #else
     (void)out8; (void)reset;

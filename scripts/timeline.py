@@ -13,8 +13,8 @@ from instagraal_b200.cuda_lib_gl_single import sampler  # noqa: E402
 from instagraal_b200.synth import make_workload  # noqa: E402
 
 NAMES = ["cand_setup", "find_cuts", "classes", "rows", "rows_write", "precompute", "score", "finalize", "lnz_outside", "apply",
-         "post", "commit_coords", "prefetch", "coords", "full_lnz", "-"]
-MAIN = ["commit_coords", "cand_setup", "find_cuts", "rows", "rows_write", "precompute", "score", "finalize", "apply", "post"]
+         "post", "commit_coords", "prefetch", "coords", "full_lnz", "pick"]
+MAIN = ["commit_coords", "cand_setup", "find_cuts", "rows", "rows_write", "precompute", "pick", "score", "finalize", "apply", "post"]
 
 
 def main():
@@ -31,7 +31,7 @@ def main():
         s.run_cycle_device(rng.permutation(level.n_frags), 5, seed=1, cycle=c)
     frs = np.concatenate([rng.permutation(level.n_frags) for _ in range(1 + n // level.n_frags)])[:n]
     L.check(s._h, L.lib().ig_timeline_reset(s._h), "ig_timeline_reset")
-    ph = np.zeros(8, dtype=np.uint64)
+    ph = np.zeros(16, dtype=np.uint64)
     L.check(s._h, L.lib().ig_timeline_phases(s._h, ph.ctypes.data, 1), "ig_timeline_phases")
     s.run_cycle_device(frs, 5, seed=1, cycle=7)
     L.check(s._h, L.lib().ig_timeline_phases(s._h, ph.ctypes.data, 0), "ig_timeline_phases")
@@ -66,9 +66,15 @@ def main():
         print("  %-28s %6.2f us" % (k, v))
     print("  sum of gaps %.1f us; inter-step gap (post end -> next step first start): %.2f us" %
           (sum(v for _, v in gaps), np.mean((t0[1:] - t1[:-1]) / 1e3)))
-    tot = float(ph[:5].sum())
+    tot = max(float(ph[:5].sum()), 1.0)
     print("k_score phases (cycles of warp 0 of every block, share): prologue %.1f%%, item set-up %.1f%%, contact loop %.1f%%, final flush + reductions %.1f%%, block barrier wait %.1f%%; mean cycles per block %.0f" %
           tuple([100 * float(x) / tot for x in ph[:5]] + [tot / max(n, 1) / 2220.0]))
+    if ph[8:15].sum() > 0:
+        tp, te = float(ph[8:12].sum()), float(ph[12:15].sum())
+        print("k_pick phases (thread 0 of every block, share of %.0f cycles per step): prologue %.1f%%, chunk loop %.1f%%, barrier+ticket %.1f%%, offsets scan (last block) %.1f%%" %
+              ((tp / n,) + tuple(100 * float(x) / tp for x in ph[8:12])))
+        print("k_eval_flat phases (share of %.0f cycles per step): prologue %.1f%%, items %.1f%%, final flush + reductions %.1f%%" %
+              ((te / n,) + tuple(100 * float(x) / te for x in ph[12:15])))
     tf = float(ph[5:8].sum())
     print("k_finalize phases (thread 0 of every block): partial reductions %.1f%%, last-block quirk %.1f%%, scores %.1f%%; mean cycles per block %.0f" %
           (100 * float(ph[5]) / tf, 100 * float(ph[6]) / tf, 100 * float(ph[7]) / tf, tf / max(n, 1) / 5.0))
