@@ -795,34 +795,26 @@ __global__ void k_prefetch_l2(PfList L) {
 // added to the executing lane's accumulator (only the sum over lanes matters; the order is fixed,
 // hence deterministic).
 struct __align__(16) QEnt { float s; int dp; unsigned mask; int val; };  // 16 B; mask bit 31: subtract
-#define IG_QCAP 96   // a flush is triggered at 64 entries; at most 32 more arrive before it
+#define IG_QCAP 64
 #define IG_QSUB 0x80000000u
 
 // term of a linear-contig contact at 0 < s < d_max WITHOUT the part that depends on the observed count only
 // (it cancels in t_mut - t_cur)
-__device__ __forceinline__ double queued_term(const QEnt& e, const Params& p, double l10v, float exz) {
-    const float exf = fmaxf((p.d == 2.0f) ? (p.c1 * powf(e.s, p.slope)) * p.fact
-                                          : (p.c1 * powf(e.s, p.slope) * expf((p.d - 2) / (powf(e.s * p.lm / p.kuhn, 2.0f) + p.d))) * p.fact,
-                            p.v_inter);  // rippe_contacts for 0 < s < d_max (KA:153-163)
-    const double t = pxl_term(exf, (double)e.val, 0.0, l10v, p.v_inter) + (double)exz * LOG10E_F;
-    return (e.mask & IG_QSUB) ? -t : t;
-}
-// Evaluates the first n (<= 64) queue entries: every lane takes entries `lane` and `lane + 32`, two independent
-// dependency chains of powf + f64 log10 that the scheduler interleaves (the chains are long and serial, so a
-// second one per lane is almost free).
 __device__ __noinline__ void eval_queue(const QEnt* __restrict__ q, int n, double* __restrict__ my_acc, const Params& p,
                                         double l10v, const float* __restrict__ exz_tab) {
     const int lane = threadIdx.x & 31;
-    const bool v0 = lane < n, v1 = lane + 32 < n;
-    QEnt e0 = {1.0f, 0, 0u, 0}, e1 = {1.0f, 0, 0u, 0};
-    if (v0) e0 = q[lane];
-    if (v1) e1 = q[lane + 32];
-    const float z0 = exz_tab[e0.dp], z1 = exz_tab[e1.dp];
-    const double t0 = queued_term(e0, p, l10v, z0);
-    const double t1 = queued_term(e1, p, l10v, z1);
-    for (unsigned m = e0.mask & 0xffffffu; m; m &= m - 1) my_acc[(__ffs(m) - 1) * IG_THREADS] += t0;
-    for (unsigned m = e1.mask & 0xffffffu; m; m &= m - 1) my_acc[(__ffs(m) - 1) * IG_THREADS] += t1;
+    if (lane < n) {
+        const QEnt e = q[lane];
+        const float exf = fmaxf((p.d == 2.0f) ? (p.c1 * powf(e.s, p.slope)) * p.fact
+                                              : (p.c1 * powf(e.s, p.slope) * expf((p.d - 2) / (powf(e.s * p.lm / p.kuhn, 2.0f) + p.d))) * p.fact,
+                                p.v_inter);  // rippe_contacts for 0 < s < d_max (KA:153-163)
+        double t = pxl_term(exf, (double)e.val, 0.0, l10v, p.v_inter) + (double)exz_tab[e.dp] * LOG10E_F;
+        if (e.mask & IG_QSUB) t = -t;
+        for (unsigned m = e.mask & 0xffffffu; m; m &= m - 1) my_acc[(__ffs(m) - 1) * IG_THREADS] += t;
+    }
 }
+// (evaluating two entries per lane in batches of 64 -- two interleaved powf/log10 chains -- was tried: no gain on
+//  small levels, 12 % slower on the 1 Gb workload through register pressure)
 
 // one selected contact as the slot loop needs it (column end + current state)
 struct Ctc { int pos, start_bp, len_ori; float watson, crick; int val; float cur_s; int cur_dp; int rjc; double t_cur; int flags; };
@@ -866,7 +858,7 @@ __device__ __forceinline__ bool eval_pair(const Ctc& x, int u, const RowMut a, c
     return true;
 }
 
-// warp-collective append to the warp's queue of expensive evaluations; a batch of 64 is evaluated at once
+// warp-collective append to the warp's queue of expensive evaluations; a full batch of 32 is evaluated at once
 __device__ __forceinline__ void queue_push(bool push, float s, int dp, unsigned mask, int val, QEnt* __restrict__ myq, int& qn,
                                            double* __restrict__ my_acc, const Params& p, double l10v, const float* __restrict__ exz_tab) {
     const unsigned pm = __ballot_sync(0xffffffffu, push);
@@ -878,11 +870,11 @@ __device__ __forceinline__ void queue_push(bool push, float s, int dp, unsigned 
     }
     qn += __popc(pm);
     __syncwarp();
-    if (qn >= 64) {
-        eval_queue(myq, 64, my_acc, p, l10v, exz_tab);
+    if (qn >= 32) {
+        eval_queue(myq, 32, my_acc, p, l10v, exz_tab);
         __syncwarp();
-        if (lane < qn - 64) { const QEnt mv = myq[64 + lane]; myq[lane] = mv; }
-        qn -= 64;
+        if (lane < qn - 32) { const QEnt mv = myq[32 + lane]; myq[lane] = mv; }
+        qn -= 32;
         __syncwarp();
     }
 }
@@ -1104,7 +1096,7 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
             touched |= __reduce_or_sync(0xffffffffu, chg);
         }
         TLP(2);   // contact loop
-        if (qn > 0) { eval_queue(myq, qn, my_acc, p, l10v, exz_tab); }   // qn < 64 here
+        if (qn > 0) { eval_queue(myq, qn, my_acc, p, l10v, exz_tab); }
         __syncwarp();
         // fixed-order accumulation into this warp's slot sums (work items are visited in a fixed order); only
         // the slots that received a term are reduced, and their accumulators are put back to zero
@@ -1252,7 +1244,7 @@ __global__ void __launch_bounds__(IG_THREADS, IG_SCORE_CTAS_PER_SM)
 k_eval_flat(const DevScalars* __restrict__ sc, const IgDescriptor* __restrict__ desc_g, int ns, const int* __restrict__ flat_cnt,
             size_t chunk_stride, const FlatRec* __restrict__ flat, size_t flat_stride, const RowMut* __restrict__ table,
             const int* __restrict__ table_len, float mbar, const float* __restrict__ exz_tab, double* __restrict__ part_nz,
-            const IgClassTab* __restrict__ clstab) {
+            const IgClassTab* __restrict__ clstab, int items_per_warp) {
     TL(6);
     TLP_DECL();
     extern __shared__ double acc_s[];                 // [IG_N_OPS][IG_THREADS]
@@ -1282,7 +1274,7 @@ k_eval_flat(const DevScalars* __restrict__ sc, const IgDescriptor* __restrict__ 
     if (k >= 0) {
     const int nw = n_blocks_k * IG_WARPS_PER_BLOCK;
     int gs = IG_N_OPS;
-    while (gs > 3 && tiles_k * (IG_N_OPS / gs) < 2 * nw) gs >>= 1;
+    while (gs > 3 && tiles_k * (IG_N_OPS / gs) < items_per_warp * nw) gs >>= 1;
     const int ng = IG_N_OPS / gs;
     const int n_items = tiles_k * ng;
     const int wg = ((int)blockIdx.x - b_first) * IG_WARPS_PER_BLOCK + w;
@@ -1953,7 +1945,7 @@ struct ig_handle {
     cudaEvent_t ev_coords, ev_lnz, ev_fork, ev_sel, ev_out, ev_cuts, ev_cls;
     bool rows_small;  // affected-row list in one launch (small levels)
     bool flat;        // flat scoring path (k_pick + k_eval_flat) for small levels
-    int grid_pick, grid_flat; int *flat_cnt, *flat_off; FlatRec* flat_list; size_t flat_stride, chunk_stride;
+    int grid_pick, grid_flat, flat_items; int *flat_cnt, *flat_off; FlatRec* flat_list; size_t flat_stride, chunk_stride;
     bool prefetch;  // the level's arrays fit the L2 comfortably: prefetch them at the start of a step
     FragRec *live, *init_live;
     SubRec* sub;
@@ -2105,7 +2097,9 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
         h->grid_score = sms * IG_SCORE_CTAS_PER_SM;  // 24 resident warps per SM (80 registers per thread; 6 KB of accumulators per warp)
         CK(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IG_SCORE_SMEM));
         CK(cudaFuncSetAttribute(k_eval_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IG_SCORE_SMEM));
-        h->grid_flat = (sms * IG_SCORE_CTAS_PER_SM) / 5; h->grid_pick = h->grid_flat;   // a step's (usually 5) candidates fill the GPU once
+        h->grid_flat = (sms * IG_SCORE_CTAS_PER_SM) / 5; h->grid_pick = h->grid_flat;
+        h->flat_items = 2;
+        if (const char* e = getenv("IG_FLAT_ITEMS")) h->flat_items = std::max(1, atoi(e));   // a step's (usually 5) candidates fill the GPU once
         h->grid_pre = sms * 2;   // 2 resident CTAs of 25 warps per SM
         {
             const char* e = getenv("IG_PREFETCH");
@@ -2353,7 +2347,7 @@ static int score_candidates(ig_handle* h, int a, const int32_t* cands, int n, in
                                                                     h->flat_cnt, h->chunk_stride, h->part_c, h->flat_list, h->flat_stride, mbar, h->exz,
                                                                     h->clstab, h->subx, h->rinfo);
         k_eval_flat<<<h->grid_score, IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->sc, h->desc, h->ns, h->flat_cnt, h->chunk_stride, h->flat_list,
-                                                                            h->flat_stride, h->table, h->table_len, mbar, h->exz, h->part_nz, h->clstab);
+                                                                            h->flat_stride, h->table, h->table_len, mbar, h->exz, h->part_nz, h->clstab, h->flat_items);
     } else
     k_score<<<dim3(gsx, n), IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
                                                                  h->ns, h->row_cnt, h->table, h->table_len, mbar, h->exz, h->part_nz,
@@ -2476,7 +2470,7 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands, int cycle = 0)
                                                                     h->flat_cnt, h->chunk_stride, h->part_c, h->flat_list, h->flat_stride, mbar, h->exz,
                                                                     h->clstab, h->subx, h->rinfo);
         k_eval_flat<<<h->grid_score, IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->sc, h->desc, h->ns, h->flat_cnt, h->chunk_stride, h->flat_list,
-                                                                            h->flat_stride, h->table, h->table_len, mbar, h->exz, h->part_nz, h->clstab);
+                                                                            h->flat_stride, h->table, h->table_len, mbar, h->exz, h->part_nz, h->clstab, h->flat_items);
     } else
     k_score<<<dim3(gsx, n), IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
                                                                  h->ns, h->row_cnt, h->table, h->table_len, mbar, h->exz, h->part_nz,
