@@ -1145,6 +1145,29 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
 //               k_score (same eval_pair / queue code), one accumulator reduction per block.
 // Results are the same sums in a different (still fixed) order.
 #define IG_PICK_PARTS 4
+// blocks [first, first + count) of the k_eval_flat grid that work for a candidate: one block per non-empty
+// candidate + the rest in proportion to the number of chunks
+// (k >= 0: the range of candidate k; k < 0: the candidate whose range holds block `blk`, -1 in *cand if none)
+__device__ __forceinline__ void flat_block_range(const DevScalars* __restrict__ sc, int n_cands, int grid, int k, int blk,
+                                                 int* first, int* count, int* tiles, int* cand) {
+    int t[IG_MAX_CANDS];
+#pragma unroll
+    for (int c = 0; c < IG_MAX_CANDS; c++) t[c] = sc->flat_segtotal[c] >> 5;   // independent loads, issued together
+    int tiles_all = 0, n_nonempty = 0;
+#pragma unroll
+    for (int c = 0; c < IG_MAX_CANDS; c++) { if (c >= n_cands) t[c] = 0; tiles_all += t[c]; n_nonempty += t[c] > 0; }
+    const int spare = grid - n_nonempty;
+    int b0 = 0;
+    *first = 0; *count = 0; *tiles = 0; *cand = -1;
+#pragma unroll
+    for (int c = 0; c < IG_MAX_CANDS; c++) {
+        if (t[c] == 0) continue;
+        const int nb = 1 + (int)(((long long)spare * t[c]) / tiles_all);
+        const bool hit = k >= 0 ? (c == k) : (blk >= b0 && blk < b0 + nb);
+        if (hit) { *first = b0; *count = nb; *tiles = t[c]; *cand = c; }
+        b0 += nb;
+    }
+}
 struct __align__(16) FlatRec {   // 64 B
     int pos, start_bp, len_ori; float watson; float crick; int val; float cur_s; int cur_dp;
     int rjc, flags; double t_cur; int ri; unsigned m; int pad[2];
@@ -1254,20 +1277,8 @@ k_eval_flat(const DevScalars* __restrict__ sc, const IgDescriptor* __restrict__ 
     // two long contigs has many times the contacts of one in two short ones: equal shares would wait for the
     // largest); inside a candidate the items = (chunk, group of gs uniq slots) are strided over its warps.
     const int n_cands = sc->n_cands;
-    int tiles_all = 0, n_nonempty = 0;
-    for (int c = 0; c < n_cands; c++) { const int t = sc->flat_segtotal[c] >> 5; tiles_all += t; n_nonempty += t > 0; }
     int k = -1, b_first = 0, n_blocks_k = 0, tiles_k = 0;
-    {
-        const int spare = (int)gridDim.x - n_nonempty;
-        int b0 = 0;
-        for (int c = 0; c < n_cands; c++) {
-            const int t = sc->flat_segtotal[c] >> 5;
-            if (t == 0) continue;
-            const int nb = 1 + (int)(((long long)spare * t) / tiles_all);
-            if ((int)blockIdx.x >= b0 && (int)blockIdx.x < b0 + nb) { k = c; b_first = b0; n_blocks_k = nb; tiles_k = t; }
-            b0 += nb;
-        }
-    }
+    flat_block_range(sc, n_cands, (int)gridDim.x, -1, (int)blockIdx.x, &b_first, &n_blocks_k, &tiles_k, &k);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int i = lane; i < IG_N_OPS; i += 32) red[w][i] = 0.0;
     __syncwarp();
@@ -1346,11 +1357,10 @@ k_eval_flat(const DevScalars* __restrict__ sc, const IgDescriptor* __restrict__ 
     TLP(14);  // final flush + reductions
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n_cands * 25; i += blockDim.x) {
-        const int c = i / 25, u = i - c * 25;
+    if (k >= 0 && threadIdx.x < 25) {   // k_finalize reads candidate k's partials from its own block range only
         double v = 0.0;
-        if (c == k && u < IG_N_OPS) for (int ww = 0; ww < IG_WARPS_PER_BLOCK; ww++) v += red[ww][u];
-        part_nz[PART_IDX(c, 25, u, gridDim.x, blockIdx.x)] = v;
+        if (threadIdx.x < IG_N_OPS) for (int ww = 0; ww < IG_WARPS_PER_BLOCK; ww++) v += red[ww][threadIdx.x];
+        part_nz[PART_IDX(k, 25, threadIdx.x, gridDim.x, blockIdx.x)] = v;
     }
 }
 
@@ -1365,7 +1375,7 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
            int ns, const int* __restrict__ row_cnt, const RowMut* __restrict__ table, const int* __restrict__ table_len,
            float mbar, const float* __restrict__ exz_tab, const double* __restrict__ part_nz, const int* __restrict__ part_c,
            int n_part, const double* __restrict__ part_z, const int* __restrict__ part_i, int n_part_z, double n_pix,
-           int compat_last_block, int* __restrict__ n_uniq_out, int* __restrict__ n_sub_out, int do_select, int n_part_c) {
+           int compat_last_block, int* __restrict__ n_uniq_out, int* __restrict__ n_sub_out, int do_select, int n_part_c, int flat) {
     TL(7);
     TLP_DECL();
     const int k = blockIdx.x;
@@ -1387,10 +1397,12 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
     // 25 + 25 + 25 + 2 slots, one warp per slot, lanes stride the partial blocks, fixed shuffle tree
     // 32 warps, one slot each per round; every lane first issues all of its loads (independent, in
     // flight together), then adds them in index order; fixed shuffle tree => deterministic
+    int nz_first = 0, nz_count = n_part;
+    if (flat) { int t_, c_; flat_block_range(sc, sc->n_cands, n_part, k, 0, &nz_first, &nz_count, &t_, &c_); }   // k_eval_flat's blocks for k
     for (int slot = w; slot < 77; slot += nwarp) {
         if (slot < 50) {
-            const double* src = slot < 25 ? &part_nz[PART_IDX(k, 25, slot, n_part, 0)] : &part_z[PART_IDX(k, 25, slot - 25, n_part_z, 0)];
-            const int n = slot < 25 ? n_part : n_part_z;
+            const double* src = slot < 25 ? &part_nz[PART_IDX(k, 25, slot, n_part, nz_first)] : &part_z[PART_IDX(k, 25, slot - 25, n_part_z, 0)];
+            const int n = slot < 25 ? nz_count : n_part_z;
             double v = 0.0;
             for (int i0 = 0; i0 < n; i0 += 32 * 16) {
                 double x[16];
@@ -2100,7 +2112,7 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
         h->grid_flat = (sms * IG_SCORE_CTAS_PER_SM) / 5; h->grid_pick = h->grid_flat;
         h->flat_items = 2;
         if (const char* e = getenv("IG_FLAT_ITEMS")) h->flat_items = std::max(1, atoi(e));   // a step's (usually 5) candidates fill the GPU once
-        h->grid_pre = sms * 2;   // 2 resident CTAs of 25 warps per SM
+        h->grid_pre = std::min(sms * 2, (ns + 31) / 32);   // 2 resident CTAs of 25 warps per SM; one tile of 32 rows per block at most
         {
             const char* e = getenv("IG_PREFETCH");
             const size_t bytes = sizeof(int2) * (size_t)h->nnz + 64 * (size_t)ns + 80 * (size_t)nf;
@@ -2357,7 +2369,7 @@ static int score_candidates(ig_handle* h, int a, const int32_t* cands, int n, in
     if (overlap) cudaStreamWaitEvent(h->stream, h->ev_lnz, 0);
     k_finalize<<<n, 1024, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->sc, h->desc, h->rows, h->rowidx, h->ns, h->row_cnt, h->table,
                                          h->table_len, mbar, h->exz, h->part_nz, h->part_c, h->flat ? h->grid_score : gsx, h->part_z, h->part_i,
-                                         h->grid_pre, h->cfg.n_pix, h->cfg.compat_last_block, h->d_nuniq, h->d_nsub, 0, gsx);
+                                         h->grid_pre, h->cfg.n_pix, h->cfg.compat_last_block, h->d_nuniq, h->d_nsub, 0, gsx, h->flat ? 1 : 0);
     return launch_ok(h, "score_candidates");
 }
 
@@ -2480,7 +2492,7 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands, int cycle = 0)
     IG_MARK(6);
     k_finalize<<<n, 1024, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->sc, h->desc, h->rows, h->rowidx, h->ns, h->row_cnt, h->table,
                                          h->table_len, mbar, h->exz, h->part_nz, h->part_c, h->flat ? h->grid_score : gsx, h->part_z, h->part_i,
-                                         h->grid_pre, h->cfg.n_pix, h->cfg.compat_last_block, h->d_nuniq, h->d_nsub, 1, gsx);
+                                         h->grid_pre, h->cfg.n_pix, h->cfg.compat_last_block, h->d_nuniq, h->d_nsub, 1, gsx, h->flat ? 1 : 0);
     IG_MARK(7);
     IG_MARK(8);
     // independent of apply/post: runs beside them on the side stream, joined before the result copy
