@@ -103,7 +103,7 @@ def measured_peak():
 def measured_traffic(workload, kernel):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the
     committed `ncu --set full` capture of the same workload (profiles/r1_ncu_*.txt), or None."""
-    table = {("T", "k_score"): 0.475904e6 + 0.0,                    # profiles/r1_ncu_k_score_T.txt (benchmark state)
+    table = {("T", "k_score"): 1.300992e6 + 0.255232e6,             # profiles/r1_ncu_k_eval_flat_T.txt + r1_ncu_k_pick_T.txt
              ("G", "k_score"): 171.874048e6 + 9.34016e6,            # profiles/r1_ncu_k_score_G.txt (fully assembled start)
              ("G", "k_full_lnz"): 679.342336e6 + 4.3264e6}          # profiles/r1_ncu_k_full_lnz_G.txt
     return table.get((workload, kernel))
@@ -310,7 +310,9 @@ def run_ours(args):
                                  "note": "sampler.run_cycle_device: the host uploads the visiting order only; candidates are "
                                          "drawn on the GPU (Philox4x32-10), steps replay as CUDA graphs"},
         "gpu_launches": int(st["launches"]),
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach[dom], "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": dom, "kernel_launches": ("k_pick + k_eval_flat (flat scoring path of small levels)"
+                                                                         if dom == "k_score" and level.sparse_matrix.nnz <= 1500000 and level.n_sub_frags <= 16384
+                                                                         else dom), "achieved": ach[dom], "peak": peak, "unit": "GB/s",
                      "frac": ach[dom] / peak, "traffic": measured_traffic(args.workload, dom), "peak_source": peak_src,
                      "kernels": {k: {"launches": kern[k][2], "ms_per_launch": kern[k][0] / max(kern[k][2], 1),
                                      "alg_bytes_per_launch": kern[k][1] / max(kern[k][2], 1),
