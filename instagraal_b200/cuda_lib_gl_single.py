@@ -24,6 +24,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib as L
+from . import host_rng
 from . import rippe_fit as opti
 
 FIELDS13 = L.FIELDS13
@@ -306,17 +307,20 @@ class sampler:
                 tmp = np.ones_like(dat, dtype=np.float32)
                 pk = tmp / tmp.sum()
             if len(xk) > 0:
-                self.distri_frags[i] = {"distri": "ok", "xk": xk, "pk": pk}
+                p64, cdf0 = host_rng.prepare(pk)
+                self.distri_frags[i] = {"distri": "ok", "xk": xk, "pk": pk, "p64": p64, "cdf0": cdf0,
+                                        "nnz": int(np.nonzero(pk != 0)[0].shape[0])}
             else:
                 self.distri_frags[i] = {"distri": None}
 
     def return_neighbours(self, id_fA, delta0):
         ori_id = self.gpu_vect_frags.id_d[id_fA]
         delta = delta0
-        if self.distri_frags[ori_id]["distri"] is not None:
-            distri = self.distri_frags[ori_id]["pk"]
-            n_max_candidates = min(delta, np.nonzero(distri != 0)[0].shape[0])
-            init_id = np.random.choice(self.distri_frags[ori_id]["xk"], n_max_candidates, p=distri, replace=False)
+        d = self.distri_frags[ori_id]
+        if d["distri"] is not None:
+            # = np.random.choice(xk, min(delta, #non-zero pk), p=pk, replace=False) (CL:3113-3122): same values, same
+            # generator state afterwards, without NumPy's per-call validation of p (host_rng.py)
+            init_id = host_rng.weighted_choice_no_replace(d["xk"], d["p64"], d["cdf0"], min(delta, d["nnz"]))
         else:
             init_id = np.random.choice(self.n_frags, delta, replace=False)
         out = []
