@@ -193,6 +193,8 @@ def run_ours(args):
         for i, f in enumerate(frag_stream(args.steps)):
             if flush is not None:
                 flush.fill_(i & 0xFF)
+                torch.cuda.current_stream().synchronize()   # the flush runs on torch's stream, the step on the library's:
+                                                            # it must be over (and stays untimed) before the step starts
             s.step_sampler(f, 5, dt)
             if xchg is not None and (i + 1) % args.gather_every == 0:
                 xchg.allgather()
@@ -210,6 +212,7 @@ def run_ours(args):
     for i, f in enumerate(frag_stream(n_prof)):
         if flush is not None:
             flush.fill_(i & 0xFF)
+            torch.cuda.current_stream().synchronize()
         s.step_sampler(f, 5, dt)
     stp = s.get_stats(reset=True)
     ktimes = s.get_kernel_times(reset=True)
