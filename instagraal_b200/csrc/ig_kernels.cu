@@ -81,9 +81,8 @@ struct DevScalars {
     unsigned int ticket_cuts[IG_MAX_CANDS], ticket_rows[IG_MAX_CANDS], ticket_fin;  // last-block-done counters
     // measurement: algorithmic traffic of the scoring kernel, accumulated over steps
     unsigned long long st_contacts, st_rows, st_frags, st_selected, st_proposals;
-    // flat scoring path (small levels): per candidate, contacts selected / read / to evaluate
-    int flat_nsub[IG_MAX_CANDS], flat_nread[IG_MAX_CANDS], flat_total[IG_MAX_CANDS], flat_segtotal[IG_MAX_CANDS];
-    unsigned int ticket_pick[IG_MAX_CANDS];
+    // flat scoring path (small levels): per candidate, list slots owned by the affected rows (padded row lengths)
+    int flat_segtotal[IG_MAX_CANDS];
 };
 
 struct CycleOut {  // compact per-step record of ig_run_cycle (128 B)
@@ -398,8 +397,7 @@ __global__ void k_cand_setup(const FragRec* __restrict__ live, DevScalars* sc, I
         c.up_a = max(0, pfa - n_bounds - A.sub_len); c.down_a = min(A.sub_l_cont - 1, pfa + n_bounds + A.sub_len);
         c.up_b = max(0, pfb - B.sub_len); c.down_b = min(B.sub_l_cont - 1, pfb + B.sub_len);
         c.n_rows = 0; c.n_sub = 0; c.row_hi = -1;
-        sc->ticket_cuts[k] = 0; sc->ticket_rows[k] = 0; sc->ticket_pick[k] = 0;
-        sc->flat_nsub[k] = 0; sc->flat_nread[k] = 0; sc->flat_total[k] = 0;
+        sc->ticket_cuts[k] = 0; sc->ticket_rows[k] = 0;
     }
     __syncthreads();
     if (k < n) {
@@ -1957,7 +1955,7 @@ struct ig_handle {
     cudaEvent_t ev_coords, ev_lnz, ev_fork, ev_sel, ev_out, ev_cuts, ev_cls;
     bool rows_small;  // affected-row list in one launch (small levels)
     bool flat;        // flat scoring path (k_pick + k_eval_flat) for small levels
-    int grid_pick, grid_flat, flat_items; int *flat_cnt, *flat_off; FlatRec* flat_list; size_t flat_stride, chunk_stride;
+    int grid_flat, flat_items; int* flat_cnt; FlatRec* flat_list; size_t flat_stride, chunk_stride;
     bool prefetch;  // the level's arrays fit the L2 comfortably: prefetch them at the start of a step
     FragRec *live, *init_live;
     SubRec* sub;
@@ -2096,7 +2094,7 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
         h->flat = h->rows_small && h->nnz <= IG_FLAT_MAX_NNZ;
         if (const char* e = getenv("IG_FLAT")) h->flat = h->flat && atoi(e) != 0;
         if (getenv("IG_FORCE_SPLIT")) h->flat = false;   // experiments / tests of the row-per-warp kernel
-        h->flat_cnt = nullptr; h->flat_off = nullptr; h->flat_list = nullptr; h->flat_stride = (size_t)h->nnz + 32 * (size_t)ns + 32;   // rows own whole 32-contact chunks
+        h->flat_cnt = nullptr; h->flat_list = nullptr; h->flat_stride = (size_t)h->nnz + 32 * (size_t)ns + 32;   // rows own whole 32-contact chunks
         h->chunk_stride = h->flat_stride / 32 + 1;
         if (h->flat) {
             if (dev_alloc(h, &h->flat_cnt, (size_t)IG_MAX_CANDS * h->chunk_stride) ||
@@ -2109,7 +2107,7 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
         h->grid_score = sms * IG_SCORE_CTAS_PER_SM;  // 24 resident warps per SM (80 registers per thread; 6 KB of accumulators per warp)
         CK(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IG_SCORE_SMEM));
         CK(cudaFuncSetAttribute(k_eval_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IG_SCORE_SMEM));
-        h->grid_flat = (sms * IG_SCORE_CTAS_PER_SM) / 5; h->grid_pick = h->grid_flat;
+        h->grid_flat = (sms * IG_SCORE_CTAS_PER_SM) / 5;   // k_pick grid per candidate: a step's (usually 5) candidates fill the GPU once
         h->flat_items = 2;
         if (const char* e = getenv("IG_FLAT_ITEMS")) h->flat_items = std::max(1, atoi(e));   // a step's (usually 5) candidates fill the GPU once
         h->grid_pre = std::min(sms * 2, (ns + 31) / 32);   // 2 resident CTAs of 25 warps per SM; one tile of 32 rows per block at most
@@ -2187,7 +2185,7 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
 extern "C" void ig_destroy(ig_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
-    void* ptrs[] = {h->flat_cnt, h->flat_off, h->flat_list, h->clstab, h->subx, h->rinfo, h->nb_ptr, h->nb_idx, h->nb_cdf, h->nb_nnz, h->cyc_frags, h->live, h->part_out, h->part_c, h->table, h->table_len, h->rowidx, h->init_live, h->sub, h->coord, h->clen, h->row_ptr, h->cv, h->sym_diag,
+    void* ptrs[] = {h->flat_cnt, h->flat_list, h->clstab, h->subx, h->rinfo, h->nb_ptr, h->nb_idx, h->nb_cdf, h->nb_nnz, h->cyc_frags, h->live, h->part_out, h->part_c, h->table, h->table_len, h->rowidx, h->init_live, h->sub, h->coord, h->clen, h->row_ptr, h->cv, h->sym_diag,
                     h->init_prev, h->init_next, h->orientable, h->sc, h->desc, h->exz, h->exz_test, h->chunk_cnt,
                     h->rows, h->row_cnt, h->part_nz, h->part_z, h->part_i, h->part_full, h->part_zc, h->part_nc,
                     h->d_nuniq, h->d_nsub, h->d_perm, h->d_hist};
