@@ -1,14 +1,20 @@
 // instagraal_b200 -- hand-written CUDA (sm_100a) for the scaffolding-MCMC hot path + its C ABI.
 //
 // One ig_step() = one reference step_sampler() (cuda_lib_gl_single.py:1401-1465, "CL") with the
-// ~700 host<->device crossings collapsed into ~14 stream-ordered launches and ONE blocking D2H of
-// a 1.1 KB result record.  Design (DESIGN.md has the long form):
+// ~700 host<->device crossings collapsed into 11-12 stream-ordered launches (one CUDA-graph replay) and
+// ONE blocking D2H of a 1.1 KB result record; ig_run_cycle / ig_run_cycle_device enqueue a whole sweep.
+// Design (DESIGN.md has the long form):
 //   * contacts: CSR by row sub-fragment of the strict upper triangle, (col,val) interleaved int2;
 //     a candidate touches only the rows of the <=2 affected contigs (ordered row list built on
 //     device), never the whole COO, and never through the host.
-//   * the 24 candidate scaffolds are never materialised: mutated coordinates of both endpoints of a
-//     contact are evaluated on the fly from a 3 KB per-candidate descriptor in shared memory
-//     (ig_moves.cuh).  Row endpoints are evaluated once per row by lanes 0..23 of the warp.
+//   * the 24 candidate scaffolds are never materialised.  Every op moves the fragments between two
+//     breakpoints rigidly (ig_moves.cuh): k_classes evaluates each op once per class; the row end of a
+//     contact comes from a per-(row, mutation) table (k_precompute), the column end is recomputed on
+//     the fly from its class motion with the reference's float32 operations.
+//   * scores are sums of DIFFERENCES to the current state over the contacts whose term changes;
+//     class-pair bit tables say which (contact, mutation) pairs need a look at all.
+//   * two scoring paths: k_score (warp per affected row, large levels) and k_pick + k_eval_flat (packed
+//     per-chunk contact lists, levels up to 1.5 M contacts).
 //   * all sums in double, fixed (deterministic) reduction order: lane -> warp shuffle -> block ->
 //     partial array -> single-block tree.  No floating-point atomics anywhere.
 //   * expected contacts in float32 exactly as the reference kernel writes them (same libdevice
