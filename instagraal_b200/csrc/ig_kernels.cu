@@ -89,6 +89,8 @@ struct DevScalars {
     unsigned long long st_contacts, st_rows, st_frags, st_selected, st_proposals;
     // flat scoring path (small levels): per candidate, list slots owned by the affected rows (padded row lengths)
     int flat_segtotal[IG_MAX_CANDS];
+    // per-candidate counters of the step (written by k_finalize): they travel with this record in ONE copy
+    int res_nuniq[IG_MAX_CANDS], res_nsub[IG_MAX_CANDS];
 };
 
 struct CycleOut {  // compact per-step record of ig_run_cycle (128 B)
@@ -2135,7 +2137,8 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
         if (dev_alloc(h, &h->part_out, h->n_part_full)) return -2;
         h->n_part_zc = sms * 2;
         if (dev_alloc(h, &h->part_zc, h->n_part_zc) || dev_alloc(h, &h->part_nc, h->n_part_zc)) return -2;
-        if (dev_alloc(h, &h->d_nuniq, IG_MAX_CANDS) || dev_alloc(h, &h->d_nsub, IG_MAX_CANDS) || dev_alloc(h, &h->d_perm, nf)) return -2;
+        if (dev_alloc(h, &h->d_perm, nf)) return -2;
+        h->d_nuniq = h->sc->res_nuniq; h->d_nsub = h->sc->res_nsub;   // device addresses inside the result record
         if (dev_alloc(h, &h->d_hist, 1 << 16)) return -2;
         h->sym_diag = nullptr;
         CK(cudaMallocHost((void**)&h->h_sc, sizeof(DevScalars)));
@@ -2194,7 +2197,7 @@ extern "C" void ig_destroy(ig_handle* h) {
     void* ptrs[] = {h->flat_cnt, h->flat_list, h->clstab, h->subx, h->rinfo, h->nb_ptr, h->nb_idx, h->nb_cdf, h->nb_nnz, h->cyc_frags, h->live, h->part_out, h->part_c, h->table, h->table_len, h->rowidx, h->init_live, h->sub, h->coord, h->clen, h->row_ptr, h->cv, h->sym_diag,
                     h->init_prev, h->init_next, h->orientable, h->sc, h->desc, h->exz, h->exz_test, h->chunk_cnt,
                     h->rows, h->row_cnt, h->part_nz, h->part_z, h->part_i, h->part_full, h->part_zc, h->part_nc,
-                    h->d_nuniq, h->d_nsub, h->d_perm, h->d_hist};
+                    h->d_perm, h->d_hist};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_sc) cudaFreeHost(h->h_sc);
     if (h->h_small) cudaFreeHost(h->h_small);
@@ -2390,15 +2393,13 @@ static int apply_and_post(ig_handle* h, int forced_cand, int forced_op) {
 static int fetch_result(ig_handle* h, int n, const int32_t* cands, ig_step_result* out, bool applied, bool copy = true) {
     if (copy) {
         CK(cudaMemcpyAsync(h->h_sc, h->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(h->h_small + 16, h->d_nuniq, IG_MAX_CANDS * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(h->h_small + 32, h->d_nsub, IG_MAX_CANDS * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
     const DevScalars& s = *h->h_sc;
     memset(out, 0, sizeof *out);
     for (int i = 0; i < n * IG_N_OPS; i++) out->scores[i] = s.scores[i];
     out->lnz_full = s.lnz_full;
-    for (int i = 0; i < n; i++) { out->n_uniq[i] = h->h_small[16 + i]; out->n_sub[i] = h->h_small[32 + i]; }
+    for (int i = 0; i < n; i++) { out->n_uniq[i] = s.res_nuniq[i]; out->n_sub[i] = s.res_nsub[i]; }
     out->q4_hits = s.q4_hits;
     if (applied) {
         out->likelihood = s.likelihood;
@@ -2516,8 +2517,6 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands, int cycle = 0)
     cudaStreamWaitEvent(h->stream, h->ev_out, 0);
     if (!cycle) {
         cudaMemcpyAsync(h->h_sc, h->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, h->stream);
-        cudaMemcpyAsync(h->h_small + 16, h->d_nuniq, IG_MAX_CANDS * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
-        cudaMemcpyAsync(h->h_small + 32, h->d_nsub, IG_MAX_CANDS * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
     }
     return launch_ok(h, "enqueue_step");
 }
