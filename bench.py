@@ -302,7 +302,7 @@ def run_ours(args):
         "mcmc_cycle_s": dev_ms_max / 1e3 / args.steps * level.n_frags,
         "proposals_per_step": prop_sum / world / args.steps,
         "wall_s_timed_region": t_wall_max,
-        "e2e": {"value": e2e, "unit": "proposals/s", "h2d_bytes_per_step": 40, "d2h_bytes_per_step": 1096 + 64,
+        "e2e": {"value": e2e, "unit": "proposals/s", "h2d_bytes_per_step": 40, "d2h_bytes_per_step": 6360,  # sizeof(DevScalars): one copy
                 "ms_per_step": t_e2e_max / n_e2e * 1e3},
         "e2e_cycle_api": {"value": cyc_prop / t_cyc, "unit": "proposals/s", "ms_per_step": t_cyc / args.steps * 1e3,
                           "device_ms_per_step": st3["ms_step"] / args.steps,

@@ -2,7 +2,7 @@
 //
 // One ig_step() = one reference step_sampler() (cuda_lib_gl_single.py:1401-1465, "CL") with the
 // ~700 host<->device crossings collapsed into 11-12 stream-ordered launches (one CUDA-graph replay) and
-// ONE blocking D2H of a 1.1 KB result record; ig_run_cycle / ig_run_cycle_device enqueue a whole sweep.
+// ONE blocking D2H of a 6 KB result record; ig_run_cycle / ig_run_cycle_device enqueue a whole sweep.
 // Design (DESIGN.md has the long form):
 //   * contacts: CSR by row sub-fragment of the strict upper triangle, (col,val) interleaved int2;
 //     a candidate touches only the rows of the <=2 affected contigs (ordered row list built on
