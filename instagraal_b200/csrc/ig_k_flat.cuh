@@ -1,0 +1,237 @@
+// instagraal_b200 -- flat scoring path of small levels: k_pick + k_eval_flat.
+// Part of ig_kernels.cu (included there, in this order; not a stand-alone translation unit).
+#pragma once
+
+// ------------------------------------------------------------------------------------------------
+// FLAT scoring path for small levels (yeast scale: a candidate touches a few hundred rows of ~100 contacts).
+// There the row-per-warp kernel above is all latency: one tiny work item per warp, each a chain of dependent
+// gathers plus a partly filled evaluation queue, and half of the lanes hold contacts outside the slice.  Instead:
+//   k_pick      one warp per 32-contact chunk of an affected row (rows own whole chunks of a per-candidate list,
+//               offsets = running sum of the padded row lengths from k_rows_small): slice membership, class-pair
+//               mask, current-state term; the contacts that need a look under at least one mutation are written
+//               compactly (ballot prefix) at the start of their chunk (+ the count), so the list order is fixed;
+//   k_eval_flat work item = (one chunk's packed contacts, group of uniq slots): no selection, no gathers by
+//               column, no per-row set-up; loop over the group's mutations exactly like the dense schedule of
+//               k_score (same eval_pair / queue code), one accumulator reduction per block.
+// Results are the same sums in a different (still fixed) order.
+#define IG_PICK_PARTS 4
+// blocks [first, first + count) of the k_eval_flat grid that work for a candidate: one block per non-empty
+// candidate + the rest in proportion to the number of chunks
+// (k >= 0: the range of candidate k; k < 0: the candidate whose range holds block `blk`, -1 in *cand if none)
+__device__ __forceinline__ void flat_block_range(const DevScalars* __restrict__ sc, int n_cands, int grid, int k, int blk,
+                                                 int* first, int* count, int* tiles, int* cand) {
+    int t[IG_MAX_CANDS];
+#pragma unroll
+    for (int c = 0; c < IG_MAX_CANDS; c++) t[c] = sc->flat_segtotal[c] >> 5;   // independent loads, issued together
+    int tiles_all = 0, n_nonempty = 0;
+#pragma unroll
+    for (int c = 0; c < IG_MAX_CANDS; c++) { if (c >= n_cands) t[c] = 0; tiles_all += t[c]; n_nonempty += t[c] > 0; }
+    const int spare = grid - n_nonempty;
+    int b0 = 0;
+    *first = 0; *count = 0; *tiles = 0; *cand = -1;
+#pragma unroll
+    for (int c = 0; c < IG_MAX_CANDS; c++) {
+        if (t[c] == 0) continue;
+        const int nb = 1 + (int)(((long long)spare * t[c]) / tiles_all);
+        const bool hit = k >= 0 ? (c == k) : (blk >= b0 && blk < b0 + nb);
+        if (hit) { *first = b0; *count = nb; *tiles = t[c]; *cand = c; }
+        b0 += nb;
+    }
+}
+struct __align__(16) FlatRec {   // 64 B
+    int pos, start_bp, len_ori; float watson; float crick; int val; float cur_s; int cur_dp;
+    int rjc, flags; double t_cur; int ri; unsigned m; int pad[2];
+};                               // flags: 1 same contig now, 2 current term deferred, 4 the row's contig is circular
+
+__global__ void __launch_bounds__(IG_THREADS, IG_SCORE_CTAS_PER_SM)
+k_pick(const int2* __restrict__ cv, const CoordRec* __restrict__ coord, const int* __restrict__ clen, DevScalars* sc,
+       const IgDescriptor* __restrict__ desc_g, const int* __restrict__ rowidx, int ns, int* __restrict__ row_cnt,
+       int* __restrict__ flat_cnt, size_t chunk_stride, int* __restrict__ part_c, FlatRec* __restrict__ flat, size_t flat_stride,
+       float mbar, const float* __restrict__ exz_tab, const IgClassTab* __restrict__ clstab, const SubX* __restrict__ subx,
+       const RowInfo* __restrict__ rinfo) {
+    TL(15);
+    TLP_DECL();
+    const int k = blockIdx.y;
+    if (k >= sc->n_cands) return;
+    __shared__ int s_sel, s_read;
+    const CandInfo ci_k = sc->ci[k];
+    const int n_items = ci_k.n_rows * IG_PICK_PARTS;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int wg = blockIdx.x * IG_WARPS_PER_BLOCK + w, nw = gridDim.x * IG_WARPS_PER_BLOCK;
+    if (threadIdx.x == 0) { s_sel = 0; s_read = 0; }
+    __syncthreads();
+    if ((int)blockIdx.x * IG_WARPS_PER_BLOCK < n_items) {
+        const Params p = sc->p;
+        const double l10v = sc->log10_vinter;
+        const double inter_const = (double)p.v_inter * LOG10E_F;
+        const unsigned allmask = (1u << desc_g[k].n_uniq) - 1u;
+        const unsigned* g_mask = clstab[k].mask;
+        const unsigned* g_farok = clstab[k].farok;
+        const float far_s = clstab[k].far_s;
+        const int far_dp = clstab[k].far_dp;
+        const int* my_idx = rowidx + (size_t)k * ns;
+        FlatRec* my_flat = flat + (size_t)k * flat_stride;
+        int* my_cnt = flat_cnt + (size_t)k * chunk_stride;
+        TLP(8);   // prologue
+        int sel_w = 0, read_w = 0;
+        for (int it = wg; it < n_items; it += nw) {
+            const int ri = it / IG_PICK_PARTS, part = it - ri * IG_PICK_PARTS;
+            const RowInfo info = rinfo[(size_t)k * ns + ri];
+            const CoordRec ci = info.ci;
+            const unsigned* mrow = g_mask + info.cls * IG_MAX_CLS;
+            const long long b = info.b, e = info.b + info.n;
+            int row_sel = 0;
+            for (long long q0 = b + 32 * part; q0 < e; q0 += 32 * IG_PICK_PARTS) {
+                const long long q = q0 + lane;
+                FlatRec x;
+                x.m = 0;
+                if (q < e) {
+                    const int2 c = __ldg(&cv[q]);
+                    const CoordRec cj = coord[c.x];
+                    if ((cj.id_c == ci_k.id_a || cj.id_c == ci_k.id_b) && contact_selected(ci, cj, c.y, ci_k)) {
+                        row_sel++;
+                        x.rjc = my_idx[c.x];
+                        x.pos = cj.pos; x.val = c.y; x.ri = ri;
+                        x.cur_s = fabsf(ci.dist - cj.dist);
+                        x.cur_dp = abs(ci.pos - cj.pos);
+                        const bool cur_same = ci.id_c == cj.id_c;
+                        unsigned m = __ldg(&mrow[x.rjc >> IG_CLS_SHIFT]) & allmask;
+                        if (m && cur_same && ci.s_tot == 0 && x.cur_s >= far_s && x.cur_dp >= far_dp)
+                            m &= ~__ldg(&g_farok[info.cls * IG_MAX_CLS + (x.rjc >> IG_CLS_SHIFT)]);
+                        if (m) {
+                            const SubX sx = subx[c.x];
+                            x.start_bp = sx.start_bp; x.len_ori = sx.len_ori; x.watson = sx.watson; x.crick = sx.crick;
+                            const double ob = (double)c.y;
+                            x.flags = (cur_same ? 1 : 0) | (ci.s_tot != 0 ? 4 : 0);
+                            x.t_cur = 0.0;
+                            if (!cur_same) x.t_cur = pxl_term(p.v_inter, ob, 0.0, l10v, p.v_inter) + inter_const;
+                            else if (ci.s_tot != 0) x.t_cur = contact_term(ci, cj, clen[c.x], ob, 0.0, p, l10v, mbar, exz_tab);
+                            else if (!((x.cur_s > 0.0f) && (x.cur_s < p.d_max))) x.t_cur = pxl_term(p.v_inter, ob, 0.0, l10v, p.v_inter) + (double)exz_tab[x.cur_dp] * LOG10E_F;
+                            else x.flags |= 2;
+                            x.pad[0] = 0; x.pad[1] = 0;
+                        }
+                        x.m = m;
+                    }
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, x.m != 0);
+                const long long slot0 = info.seg + (q0 - b);   // this chunk's 32 list slots
+                if (x.m) my_flat[slot0 + __popc(bal & ((1u << lane) - 1))] = x;
+                if (lane == 0) my_cnt[slot0 >> 5] = __popc(bal);
+            }
+            row_sel = __reduce_add_sync(0xffffffffu, row_sel);
+            if (lane == 0 && row_sel) atomicAdd(&row_cnt[(size_t)k * ns + ri], row_sel);   // zeroed by k_rows_small
+            sel_w += row_sel;
+            if (part == 0) read_w += info.n;
+        }
+        TLP(9);   // chunk loop
+        if (lane == 0 && (sel_w | read_w)) { atomicAdd(&s_sel, sel_w); atomicAdd(&s_read, read_w); }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        part_c[PART_IDX(k, 2, 0, gridDim.x, blockIdx.x)] = s_sel;
+        part_c[PART_IDX(k, 2, 1, gridDim.x, blockIdx.x)] = s_read;
+    }
+}
+
+__global__ void __launch_bounds__(IG_THREADS, IG_SCORE_CTAS_PER_SM)
+k_eval_flat(const DevScalars* __restrict__ sc, const IgDescriptor* __restrict__ desc_g, int ns, const int* __restrict__ flat_cnt,
+            size_t chunk_stride, const FlatRec* __restrict__ flat, size_t flat_stride, const RowMut* __restrict__ table,
+            const int* __restrict__ table_len, float mbar, const float* __restrict__ exz_tab, double* __restrict__ part_nz,
+            const IgClassTab* __restrict__ clstab, int items_per_warp) {
+    TL(6);
+    TLP_DECL();
+    extern __shared__ double acc_s[];                 // [IG_N_OPS][IG_THREADS]
+    __shared__ double red[IG_WARPS_PER_BLOCK][IG_N_OPS];
+    __shared__ QEnt queue[IG_WARPS_PER_BLOCK][IG_QCAP];
+    // The blocks of ONE grid are dealt to the candidates in proportion to their number of chunks (a candidate in
+    // two long contigs has many times the contacts of one in two short ones: equal shares would wait for the
+    // largest); inside a candidate the items = (chunk, group of gs uniq slots) are strided over its warps.
+    const int n_cands = sc->n_cands;
+    int k = -1, b_first = 0, n_blocks_k = 0, tiles_k = 0;
+    flat_block_range(sc, n_cands, (int)gridDim.x, -1, (int)blockIdx.x, &b_first, &n_blocks_k, &tiles_k, &k);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int i = lane; i < IG_N_OPS; i += 32) red[w][i] = 0.0;
+    __syncwarp();
+    if (k >= 0) {
+    const int nw = n_blocks_k * IG_WARPS_PER_BLOCK;
+    int gs = IG_N_OPS;
+    while (gs > 3 && tiles_k * (IG_N_OPS / gs) < items_per_warp * nw) gs >>= 1;
+    const int ng = IG_N_OPS / gs;
+    const int n_items = tiles_k * ng;
+    const int wg = ((int)blockIdx.x - b_first) * IG_WARPS_PER_BLOCK + w;
+    for (int u = 0; u < IG_N_OPS; u++) acc_s[u * IG_THREADS + threadIdx.x] = 0.0;
+    const Params p = sc->p;
+    const double l10v = sc->log10_vinter;
+    const double inter_const = (double)p.v_inter * LOG10E_F;
+    double* my_acc = acc_s + threadIdx.x;
+    QEnt* myq = queue[w];
+    int qn = 0;
+    unsigned touched = 0;
+    const int n_uniq = desc_g[k].n_uniq;
+    const int* cnt = flat_cnt + (size_t)k * chunk_stride;
+    const FlatRec* my_flat = flat + (size_t)k * flat_stride;
+    const RowMut* tab = table + (size_t)k * IG_N_OPS * ns;
+    const int* tlen = table_len + (size_t)k * IG_N_OPS * ns;
+    const IgMotion* g_mot = clstab[k].mot;
+    TLP(12);  // prologue
+    for (int it = wg; it < n_items; it += nw) {
+        const int tile = it / ng, grp = it - tile * ng;
+        const int u0 = grp * gs;
+        if (u0 >= n_uniq) continue;
+        const unsigned gmask = ((1u << gs) - 1u) << u0;
+        unsigned m = 0;
+        Ctc x;
+        x.pos = 0; x.start_bp = 0; x.len_ori = 0; x.watson = 0.f; x.crick = 0.f; x.val = 0; x.cur_s = 0.f; x.cur_dp = 0;
+        x.rjc = 0; x.t_cur = 0.0; x.flags = 0;
+        int ri = 0;
+        float row_s_tot = 0.f;
+        if (lane < __ldg(&cnt[tile])) {
+            const FlatRec r = my_flat[((size_t)tile << 5) + lane];
+            x.pos = r.pos; x.start_bp = r.start_bp; x.len_ori = r.len_ori; x.watson = r.watson; x.crick = r.crick; x.val = r.val;
+            x.cur_s = r.cur_s; x.cur_dp = r.cur_dp; x.rjc = r.rjc; x.t_cur = r.t_cur; x.flags = r.flags;
+            ri = r.ri;
+            m = r.m & gmask;
+            row_s_tot = (r.flags & 4) ? 1.0f : 0.0f;   // eval_pair only asks whether the row's contig is circular
+        }
+        const unsigned um = __reduce_or_sync(0xffffffffu, m);
+        if (!um) continue;
+        unsigned chg = 0;
+        RowMut a_nxt = tab[(size_t)(__ffs(um) - 1) * ns + ri];   // row-end entry, fetched one mutation ahead
+#pragma unroll 1
+        for (unsigned uw = um; uw; uw &= uw - 1) {
+            const int u = __ffs(uw) - 1;
+            const RowMut a = a_nxt;
+            const unsigned rest = uw & (uw - 1);
+            if (rest) a_nxt = tab[(size_t)(__ffs(rest) - 1) * ns + ri];
+            float s_m = 0.f; int dp_m = 0; bool push = false;
+            if ((m >> u) & 1u) {
+                double add;
+                if (eval_pair(x, u, a, g_mot, row_s_tot, p, l10v, inter_const, mbar, exz_tab, tab, tlen, ns, s_m, dp_m, push, add)) {
+                    chg |= 1u << u;
+                    my_acc[u * IG_THREADS] += add;
+                }
+            }
+            queue_push(push, s_m, dp_m, 1u << u, x.val, myq, qn, my_acc, p, l10v, exz_tab);
+        }
+        queue_push((x.flags & 2) && chg, x.cur_s, x.cur_dp, chg | IG_QSUB, x.val, myq, qn, my_acc, p, l10v, exz_tab);
+        touched |= __reduce_or_sync(0xffffffffu, chg);
+    }
+    TLP(13);  // items
+    if (qn > 0) { eval_queue(myq, qn, my_acc, p, l10v, exz_tab); }
+    __syncwarp();
+    for (unsigned tw = touched; tw; tw &= tw - 1) {
+        const int us = __ffs(tw) - 1;
+        const double v = warp_sum(my_acc[us * IG_THREADS]);
+        if (lane == 0) red[w][us] = v;
+    }
+    TLP(14);  // final flush + reductions
+    }
+    __syncthreads();
+    if (k >= 0 && threadIdx.x < 25) {   // k_finalize reads candidate k's partials from its own block range only
+        double v = 0.0;
+        if (threadIdx.x < IG_N_OPS) for (int ww = 0; ww < IG_WARPS_PER_BLOCK; ww++) v += red[ww][threadIdx.x];
+        part_nz[PART_IDX(k, 25, threadIdx.x, gridDim.x, blockIdx.x)] = v;
+    }
+}
+
+__device__ void select_step(DevScalars* sc, const IgDescriptor* __restrict__ desc_g);

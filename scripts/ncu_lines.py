@@ -23,31 +23,44 @@ def main(rep, top=32):
                 print("  stall", h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), r[i])
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True,
                          text=True).stdout.splitlines()
+    # one section per source file of the kernel (the kernels live in several included .cuh files)
     idx = [i for i, l in enumerate(src) if l.startswith('"Line No","Source","Address"')]
-    sec = src[idx[0]:(idx[1] - 2 if len(idx) > 1 else len(src))]
-    rows = list(csv.reader(sec))
-    h = rows[0]
-    iS, iI, iT = h.index("# Samples"), h.index("Instructions Executed"), h.index("Thread Instructions Executed")
-    st = [i for i, x in enumerate(h) if x.startswith("stall_") and "Not Issued" not in x]
+    names = [l for l in src if l.startswith('"File Name"')]
     agg = {}
-    for r in rows[1:]:
-        try:
-            ln = int(r[0])
-        except (ValueError, IndexError):
-            continue
-        a = agg.setdefault(ln, [r[1], 0, 0, 0, {}])
-        a[1] += int(r[iS] or 0); a[2] += int(r[iI] or 0); a[3] += int(r[iT] or 0)
-        for i in st:
-            v = int(r[i] or 0)
-            if v:
-                a[4][h[i]] = a[4].get(h[i], 0) + v
+    for n, start in enumerate(idx):
+        end = idx[n + 1] - 2 if n + 1 < len(idx) else len(src)
+        fname = ""
+        for back in range(start, max(start - 4, -1), -1):
+            if src[back].startswith('"File Name"'):
+                fname = src[back].split(",", 1)[1].strip('"').split("/")[-1]
+                break
+        rows = list(csv.reader(src[start:end]))
+        h = rows[0]
+        iS, iI, iT = h.index("# Samples"), h.index("Instructions Executed"), h.index("Thread Instructions Executed")
+        st = [i for i, x in enumerate(h) if x.startswith("stall_") and "Not Issued" not in x]
+        for r in rows[1:]:
+            try:
+                ln = int(r[0])
+            except (ValueError, IndexError):
+                continue
+            def num(x):
+                try:
+                    return int(x)
+                except ValueError:
+                    return 0
+            a = agg.setdefault((fname, ln), [r[1], 0, 0, 0, {}])
+            a[1] += num(r[iS]); a[2] += num(r[iI]); a[3] += num(r[iT])
+            for i in st:
+                v = num(r[i])
+                if v:
+                    a[4][h[i]] = a[4].get(h[i], 0) + v
     ts, ti = sum(a[1] for a in agg.values()), sum(a[2] for a in agg.values())
     print(f"total warp instructions {ti}, samples {ts}")
     keys = set(k for k, _ in sorted(agg.items(), key=lambda kv: -kv[1][2])[:top]) | set(k for k, _ in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top])
     for ln in sorted(keys):
         a = agg[ln]
         ss = ",".join(f"{k.replace('stall_', '')}:{v}" for k, v in sorted(a[4].items(), key=lambda kv: -kv[1])[:2])
-        print(f"{ln:5d} inst={100 * a[2] / ti:5.1f}% samp={100 * a[1] / max(ts, 1):5.1f}% lanes={a[3] / max(a[2], 1):4.1f} [{ss}] | {a[0].strip()[:100]}")
+        print(f"{ln[0][:18]:18s}{ln[1]:5d} inst={100 * a[2] / ti:5.1f}% samp={100 * a[1] / max(ts, 1):5.1f}% lanes={a[3] / max(a[2], 1):4.1f} [{ss}] | {a[0].strip()[:100]}")
 
 
 if __name__ == "__main__":
