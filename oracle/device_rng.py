@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE ONLY -- restatement of the product's production-mode neighbour draws
-(instagraal_b200/csrc/ig_kernels.cu: philox4x32_10, philox_uniform, k_draw_plan) in NumPy/Python.
+(instagraal_b200/csrc/ig_k_rng.cuh: philox4x32_10, philox_uniform, k_draw_plan) in NumPy/Python.
 
 The distribution is the reference's return_neighbours (cuda_lib_gl_single.py:3103-3141: min(delta, #non-zero pk)
 fragments without replacement, probability proportional to pk; `delta` distinct uniform fragments when the
