@@ -33,18 +33,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# p(s) parameters of the simulated data (optim_rippe_curve_update.py:66-70 defaults); fact/v_inter per workload
 def params_for(level):
-    from instagraal_b200 import rippe_fit  # noqa: F401
-    spec = level.spec
-    kuhn, lm, slope = 50.0, 9.6, -1.5
-    c1 = np.float32(0.53 * (lm / kuhn) ** slope * kuhn ** -3)
-    s1 = float(level.S_o_A_sub_frags["len_bp"].mean()) / 1000.0
-    fact = spec.lambda1 / (float(c1) * s1 ** slope)
-    ns = level.n_sub_frags
-    v_inter = max(spec.trans_per_row * 2.0 / ns, 1e-6) / 10.0
-    d_max = (v_inter / (float(c1) * fact)) ** (1.0 / slope)
-    return np.array([kuhn, lm, c1, slope, 2.0, d_max, fact, v_inter], dtype=np.float32)
+    from instagraal_b200.synth import workload_params
+    return workload_params(level)
 
 
 class ClockSampler:

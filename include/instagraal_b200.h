@@ -162,8 +162,16 @@ int ig_get_kernel_times(ig_handle* h, double out11[11], int32_t reset);
  * outside); in between they are maintained incrementally (identical up to f64 summation order).
  * use_graph: replay each step as one CUDA graph. */
 int ig_set_options(ig_handle* h, int32_t refresh_every, int32_t use_graph);
+/* device milliseconds spent inside the full-likelihood kernel by ig_full_likelihood calls (the nuisance step's
+ * eval_likelihood_4_nuisance, CL:1296-1344) and the number of such calls: out2 = { ms, calls } */
+int ig_get_nuisance_stats(ig_handle* h, double out2[2], int32_t reset);
 /* number of full refreshes among the steps covered by the last ig_get_stats call */
 int ig_get_full_refresh_count(ig_handle* h, int64_t* out);
+
+/* self-test of the device math the kernels use in place of libdevice's powf / double log10 (same results: powf_pos is a
+ * transcription of powf's main path, bit-identical for x > 0; log10_f32 agrees to < 4e-16): n samples of x log-uniform in
+ * [x_lo, x_hi], exponent y; out2 = { inputs where powf_pos != powf bit-wise, max |log10_f32 - log10| }. */
+int ig_selftest_math(ig_handle* h, int32_t n, float x_lo, float x_hi, float y, double out2[2]);
 
 /* replica chains (one handle per GPU/process): exchange {likelihood, n_contigs, live id_c/pos/ori...}
  * is done by the host facade over NCCL; the library only exposes the packed best-state buffer. */

@@ -23,6 +23,7 @@ EXPORTS = (
     "ig_apply", "ig_full_likelihood", "ig_distance_histogram", "ig_set_sym_diag", "ig_device_state_ptr",
     "ig_set_profiling", "ig_get_stats", "ig_set_options", "ig_get_full_refresh_count", "ig_get_kernel_times", "ig_run_cycle", "ig_contact_thumbnail", "ig_set_neighbour_weights",
            "ig_run_cycle_device", "ig_get_cycle_plan", "ig_timeline_reset", "ig_timeline_get", "ig_timeline_blocks", "ig_timeline_phases",
+    "ig_selftest_math", "ig_get_nuisance_stats",
 )
 
 
@@ -99,6 +100,8 @@ def lib():
         L.ig_timeline_blocks.argtypes = [vp, i32, vp]
         L.ig_timeline_phases.argtypes = [vp, vp, i32]
         L.ig_get_full_refresh_count.argtypes = [vp, C.POINTER(i64)]
+        L.ig_get_nuisance_stats.argtypes = [vp, vp, i32]
+        L.ig_selftest_math.argtypes = [vp, i32, C.c_float, C.c_float, C.c_float, vp]
         for name in EXPORTS:
             if name not in ("ig_destroy", "ig_last_error"):
                 getattr(L, name).restype = C.c_int

@@ -34,9 +34,17 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
     // 32 warps, one slot each per round; every lane first issues all of its loads (independent, in
     // flight together), then adds them in index order; fixed shuffle tree => deterministic
     int nz_first = 0, nz_count = n_part;
-    if (flat) { int t_, c_; flat_block_range(sc, sc->n_cands, n_part, k, 0, &nz_first, &nz_count, &t_, &c_); }   // k_eval_flat's blocks for k
+    const bool fixed = sc->use_stream[k] != 0;   // streaming path: int64 fixed-point partials from k_eval_flat<true>
+    if (flat || fixed) { int t_, c_; flat_block_range(sc, sc->n_cands, n_part, k, 0, &nz_first, &nz_count, &t_, &c_); }   // k_eval_flat's blocks for k
     for (int slot = w; slot < 77; slot += nwarp) {
-        if (slot < 50) {
+        if (slot < 25 && fixed) {
+            const long long* src = reinterpret_cast<const long long*>(&part_nz[PART_IDX(k, 25, slot, n_part, nz_first)]);
+            long long v = 0;
+            for (int i = lane; i < nz_count; i += 32) v += src[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            if (lane == 0) s_nz[slot] = (double)v * (1.0 / IG_FIX_SCALE);   // exact integer total, whatever the order
+        } else if (slot < 50) {
             const double* src = slot < 25 ? &part_nz[PART_IDX(k, 25, slot, n_part, nz_first)] : &part_z[PART_IDX(k, 25, slot - 25, n_part_z, 0)];
             const int n = slot < 25 ? nz_count : n_part_z;
             double v = 0.0;

@@ -135,17 +135,28 @@ struct __align__(16) QEnt { float s; int dp; unsigned mask; int val; };  // 16 B
 
 // term of a linear-contig contact at 0 < s < d_max WITHOUT the part that depends on the observed count only
 // (it cancels in t_mut - t_cur)
+// Accumulation flavours.  FIXED = false: per-thread double sums, reduced in a fixed order (deterministic because the work
+// of a thread is fixed).  FIXED = true (streaming path of large levels, whose pick list is appended in arbitrary order):
+// every term is rounded to a 2^-32 fixed-point int64 first, so the total is EXACT integer arithmetic and independent of
+// the order -- run-to-run deterministic without fixing who evaluates what (rounding error < 1.2e-10 per term).
+#define IG_FIX_SCALE 4294967296.0
+template <bool FIXED>
+__device__ __forceinline__ void acc_add(double* __restrict__ slot, double t) {
+    if (FIXED) *reinterpret_cast<long long*>(slot) += __double2ll_rn(t * IG_FIX_SCALE);
+    else *slot += t;
+}
+template <bool FIXED>
 __device__ __noinline__ void eval_queue(const QEnt* __restrict__ q, int n, double* __restrict__ my_acc, const Params& p,
                                         double l10v, const float* __restrict__ exz_tab) {
     const int lane = threadIdx.x & 31;
     if (lane < n) {
         const QEnt e = q[lane];
-        const float exf = fmaxf((p.d == 2.0f) ? (p.c1 * powf(e.s, p.slope)) * p.fact
-                                              : (p.c1 * powf(e.s, p.slope) * expf((p.d - 2) / (powf(e.s * p.lm / p.kuhn, 2.0f) + p.d))) * p.fact,
+        const float exf = fmaxf((p.d == 2.0f) ? (p.c1 * IG_POWF(e.s, p.slope)) * p.fact
+                                              : (p.c1 * IG_POWF(e.s, p.slope) * expf((p.d - 2) / (IG_POWF(e.s * p.lm / p.kuhn, 2.0f) + p.d))) * p.fact,
                                 p.v_inter);  // rippe_contacts for 0 < s < d_max (KA:153-163)
         double t = pxl_term(exf, (double)e.val, 0.0, l10v, p.v_inter) + (double)exz_tab[e.dp] * LOG10E_F;
         if (e.mask & IG_QSUB) t = -t;
-        for (unsigned m = e.mask & 0xffffffu; m; m &= m - 1) my_acc[(__ffs(m) - 1) * IG_THREADS] += t;
+        for (unsigned m = e.mask & 0xffffffu; m; m &= m - 1) acc_add<FIXED>(&my_acc[(__ffs(m) - 1) * IG_THREADS], t);
     }
 }
 // (evaluating two entries per lane in batches of 64 -- two interleaved powf/log10 chains -- was tried: no gain on
@@ -194,6 +205,7 @@ __device__ __forceinline__ bool eval_pair(const Ctc& x, int u, const RowMut a, c
 }
 
 // warp-collective append to the warp's queue of expensive evaluations; a full batch of 32 is evaluated at once
+template <bool FIXED = false>
 __device__ __forceinline__ void queue_push(bool push, float s, int dp, unsigned mask, int val, QEnt* __restrict__ myq, int& qn,
                                            double* __restrict__ my_acc, const Params& p, double l10v, const float* __restrict__ exz_tab) {
     const unsigned pm = __ballot_sync(0xffffffffu, push);
@@ -206,7 +218,7 @@ __device__ __forceinline__ void queue_push(bool push, float s, int dp, unsigned 
     qn += __popc(pm);
     __syncwarp();
     if (qn >= 32) {
-        eval_queue(myq, 32, my_acc, p, l10v, exz_tab);
+        eval_queue<FIXED>(myq, 32, my_acc, p, l10v, exz_tab);
         __syncwarp();
         if (lane < qn - 32) { const QEnt mv = myq[32 + lane]; myq[lane] = mv; }
         qn -= 32;
@@ -241,6 +253,7 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
     TLP_DECL();
     const int k = blockIdx.y;
     if (k >= sc->n_cands) return;
+    if (sc->use_stream[k]) return;                    // scored by k_stream + k_eval_flat<true>
     extern __shared__ double acc_s[];                 // [IG_N_OPS][IG_THREADS]
     __shared__ double red[IG_WARPS_PER_BLOCK][25];
     __shared__ int redi[IG_WARPS_PER_BLOCK][2];
@@ -431,7 +444,7 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
             touched |= __reduce_or_sync(0xffffffffu, chg);
         }
         TLP(2);   // contact loop
-        if (qn > 0) { eval_queue(myq, qn, my_acc, p, l10v, exz_tab); }
+        if (qn > 0) { eval_queue<false>(myq, qn, my_acc, p, l10v, exz_tab); }
         __syncwarp();
         // fixed-order accumulation into this warp's slot sums (work items are visited in a fixed order); only
         // the slots that received a term are reduced, and their accumulators are put back to zero

@@ -6,7 +6,7 @@
 // K2: per-candidate setup.  Thread 0 walks the candidates IN ORDER because extract_uniq_mutations
 //     of candidate k reads the list_valid_insert left by get_bounds of candidate k-1 (quirk Q3).
 __global__ void k_cand_setup(const FragRec* __restrict__ live, DevScalars* sc, IgDescriptor* desc, int n_bounds,
-                             int first_flip_eject, const int* __restrict__ cyc_in) {
+                             int first_flip_eject, const int* __restrict__ cyc_in, int stream_mode) {
     TL(0);
     if (cyc_in) {  // cycle mode: this step's {n_cands, fragment, candidates} come from the uploaded cycle plan
         const int* src = cyc_in + (size_t)sc->step_idx * (2 + IG_MAX_CANDS);
@@ -41,7 +41,11 @@ __global__ void k_cand_setup(const FragRec* __restrict__ live, DevScalars* sc, I
         c.up_b = max(0, pfb - B.sub_len); c.down_b = min(B.sub_l_cont - 1, pfb + B.sub_len);
         c.n_rows = 0; c.n_sub = 0; c.row_hi = -1;
         sc->ticket_cuts[k] = 0; sc->ticket_rows[k] = 0;
+        // streaming scoring path: not for circular contigs (every class pair may change there: k_score's generic route)
+        sc->use_stream[k] = (stream_mode && A.circ == 0 && B.circ == 0) ? 1 : 0;
+        if (stream_mode) sc->flat_segtotal[k] = 0;   // pick-list fill
     }
+    if (stream_mode && k >= n && k < IG_MAX_CANDS) { sc->use_stream[k] = 0; sc->flat_segtotal[k] = 0; }
     __syncthreads();
     if (k < n) {
         IgDescriptor& d = desc[k];
@@ -169,6 +173,18 @@ k_classes(const DevScalars* __restrict__ sc, const IgDescriptor* __restrict__ de
 // ------------------------------------------------------------------------------------------------
 // K5-7: ORDERED list of the CSR rows (sub-fragments) that belong to the <=2 affected contigs.
 __device__ __forceinline__ bool row_affected(const CoordRec& c, const CandInfo& ci) { return c.id_c == ci.id_a || c.id_c == ci.id_b; }
+// Position of a sub-fragment relative to the two slice windows of a same-linear-contig candidate (slice_sp_mat,
+// KA:565-586): bit 0 = left of window A (pos < up_a), 1 = right of it (pos > down_a), 2 / 3 = the same for window B.
+// A contact (i, j) is selected when, for one of the windows, the two ends are neither both left nor both right of it:
+//     min(pos) <= down && max(pos) >= up   <=>   (flags_i & flags_j & 3) == 0   (resp. & 12)
+__device__ __forceinline__ unsigned window_flags(int pos, const CandInfo& c) {
+    if (!(c.same && c.is_circ == 0)) return 0u;
+    return (pos < c.up_a ? 1u : 0u) | (pos > c.down_a ? 2u : 0u) | (pos < c.up_b ? 4u : 0u) | (pos > c.down_b ? 8u : 0u);
+}
+__device__ __forceinline__ bool window_selected(unsigned fi, unsigned fj) {
+    const unsigned both = fi & fj;
+    return ((both & 3u) == 0u) || ((both & 12u) == 0u);
+}
 __global__ void __launch_bounds__(IG_ROW_CHUNK)
 k_rows_count(const CoordRec* __restrict__ coord, int ns, DevScalars* sc, int* __restrict__ chunk_cnt, int n_chunks) {
     TL(3);
@@ -217,7 +233,8 @@ k_rows_count(const CoordRec* __restrict__ coord, int ns, DevScalars* sc, int* __
 __global__ void __launch_bounds__(IG_ROW_CHUNK)
 k_rows_write(const CoordRec* __restrict__ coord, int ns, const DevScalars* __restrict__ sc, const int* __restrict__ chunk_off,
              int n_chunks, int* __restrict__ rows, int* __restrict__ rowidx, int* __restrict__ row_cnt, int rows_stride,
-             const IgClassTab* __restrict__ clstab, const long long* __restrict__ row_ptr, RowInfo* __restrict__ rinfo) {
+             const IgClassTab* __restrict__ clstab, const long long* __restrict__ row_ptr, RowInfo* __restrict__ rinfo,
+             unsigned* __restrict__ bitmap, int bitmap_words, unsigned short* __restrict__ cls16) {
     TL(4);
     const int k = blockIdx.y;
     if (k >= sc->n_cands) return;
@@ -231,6 +248,9 @@ k_rows_write(const CoordRec* __restrict__ coord, int ns, const DevScalars* __res
     const unsigned b = __ballot_sync(0xffffffffu, f);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (lane == 0) wsum[w] = __popc(b);
+    // streaming scoring path: membership bitmap of the affected contigs (one bit per sub-fragment, staged in shared
+    // memory by k_stream)
+    if (bitmap && lane == 0 && r < ns) bitmap[(size_t)k * bitmap_words + (r >> 5)] = b;
     __syncthreads();
     if (w == 0) {
         int s = wsum[lane];
@@ -244,6 +264,7 @@ k_rows_write(const CoordRec* __restrict__ coord, int ns, const DevScalars* __res
         rows[(size_t)k * rows_stride + off] = r;
         const int cls = ig_class_of(s_bp, s_bp + IG_MAX_BP, s_bp[IG_MAX_BP + 2], s_bp[IG_MAX_BP + 3], cr.id_c, cr.pos);
         rowidx[(size_t)k * rows_stride + r] = off | (cls << IG_CLS_SHIFT);
+        if (cls16) cls16[(size_t)k * rows_stride + r] = (unsigned short)(cls | (window_flags(cr.pos, sc->ci[k]) << 8));
         const long long b = row_ptr[r];
         RowInfo ri; ri.r = r; ri.cls = cls; ri.n = (int)(row_ptr[r + 1] - b); ri.pad = 0; ri.b = b; ri.seg = 0; ri.ci = cr;
         rinfo[(size_t)k * rows_stride + off] = ri;

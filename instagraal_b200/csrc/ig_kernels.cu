@@ -84,6 +84,7 @@ struct DevScalars {
     int step_idx;
     double full_out[3];
     int full_nintra, pad_;
+    double obc_total;   // sum over every stored contact of the observed-count-only part of its term (k_obc_sum)
     unsigned int ticket_cuts[IG_MAX_CANDS], ticket_rows[IG_MAX_CANDS], ticket_fin;  // last-block-done counters
     // measurement: algorithmic traffic of the scoring kernel, accumulated over steps
     unsigned long long st_contacts, st_rows, st_frags, st_selected, st_proposals;
@@ -91,6 +92,9 @@ struct DevScalars {
     int flat_segtotal[IG_MAX_CANDS];
     // per-candidate counters of the step (written by k_finalize): they travel with this record in ONE copy
     int res_nuniq[IG_MAX_CANDS], res_nsub[IG_MAX_CANDS];
+    // streaming scoring path of large levels: which candidates take it, overflow of a pick list
+    int use_stream[IG_MAX_CANDS];
+    int list_overflow, pad2_;
 };
 
 struct CycleOut {  // compact per-step record of ig_run_cycle (128 B)
@@ -121,6 +125,8 @@ struct ig_handle {
     bool flat;        // flat scoring path (k_pick + k_eval_flat) for small levels
     int grid_flat, flat_items; int* flat_cnt; FlatRec* flat_list; size_t flat_stride, chunk_stride;
     bool prefetch;  // the level's arrays fit the L2 comfortably: prefetch them at the start of a step
+    bool streaming; // streaming scoring path (k_stream + k_eval_flat<true>): large levels with rigid_pruning != 0
+    unsigned* bitmap; int bitmap_words; unsigned short* cls16; FlatRec* pick_list; size_t pick_cap; int stream_smem;
     FragRec *live, *init_live;
     SubRec* sub;
     CoordRec* coord;
@@ -155,7 +161,7 @@ struct ig_handle {
     // measurement (CUDA events on the launching stream)
     cudaEvent_t ev[6];
     cudaEvent_t evk[16]; double ms_k[16];  // per-kernel event timing of the main stream (profiling mode)
-    double ms_step, ms_score, ms_full;
+    double ms_step, ms_score, ms_full, ms_nuis; long long n_nuis;
     long long n_launches, n_steps;
     int profile;
     std::string err;
@@ -243,11 +249,11 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
         CK(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
         for (int i = 0; i < 6; i++) CK(cudaEventCreate(&h->ev[i]));
         for (int i = 0; i < 16; i++) { CK(cudaEventCreate(&h->evk[i])); h->ms_k[i] = 0.0; }
-        h->ms_step = h->ms_score = h->ms_full = 0.0; h->n_launches = 0; h->n_steps = 0; h->profile = 0;
+        h->ms_step = h->ms_score = h->ms_full = 0.0; h->ms_nuis = 0.0; h->n_nuis = 0; h->n_launches = 0; h->n_steps = 0; h->profile = 0;
         const int nf = h->nf, ns = h->ns;
         if (dev_alloc(h, &h->live, nf) || dev_alloc(h, &h->init_live, nf)) return -2;
         if (dev_alloc(h, &h->sub, ns) || dev_alloc(h, &h->coord, ns) || dev_alloc(h, &h->clen, ns)) return -2;
-        if (dev_alloc(h, &h->row_ptr, (size_t)ns + 1) || dev_alloc(h, &h->cv, (size_t)h->nnz)) return -2;
+        if (dev_alloc(h, &h->row_ptr, (size_t)ns + 1) || dev_alloc(h, &h->cv, (size_t)h->nnz + 2)) return -2;
         if (dev_alloc(h, &h->init_prev, nf) || dev_alloc(h, &h->init_next, nf) || dev_alloc(h, &h->orientable, nf)) return -2;
         if (dev_alloc(h, &h->sc, 1) || dev_alloc(h, &h->desc, IG_MAX_CANDS)) return -2;
         if (dev_alloc(h, &h->exz, (size_t)ns + 1) || dev_alloc(h, &h->exz_test, (size_t)ns + 1)) return -2;
@@ -265,12 +271,29 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
                 dev_alloc(h, &h->flat_list, (size_t)IG_MAX_CANDS * h->flat_stride)) return -2;
         }
         if (dev_alloc(h, &h->rows, (size_t)IG_MAX_CANDS * ns) || dev_alloc(h, &h->row_cnt, (size_t)IG_MAX_CANDS * ns)) return -2;
+        h->bitmap = nullptr; h->cls16 = nullptr; h->pick_list = nullptr;
+        h->bitmap_words = (ns + 31) / 32;
+        h->stream_smem = h->bitmap_words * (int)sizeof(unsigned);
+        h->streaming = !h->flat && h->rigid != 0 && h->stream_smem <= 200 * 1024;
+        if (const char* e = getenv("IG_STREAM")) h->streaming = h->streaming && atoi(e) != 0;   // experiments / tests
+        if (getenv("IG_FORCE_STREAM") && h->rigid != 0 && h->stream_smem <= 200 * 1024) {   // tests: small levels through the streaming path
+            h->streaming = true; h->flat = false;
+        }
+        if (h->streaming) {
+            h->rows_small = false;   // the two-pass row list also writes the bitmap and the class words
+            h->pick_cap = std::min<size_t>((size_t)h->nnz + 64, (size_t)4 << 20);
+            if (const char* e = getenv("IG_PICK_CAP")) h->pick_cap = (size_t)std::max(64, atoi(e));
+            if (dev_alloc(h, &h->bitmap, (size_t)IG_MAX_CANDS * h->bitmap_words) || dev_alloc(h, &h->cls16, (size_t)IG_MAX_CANDS * ns) ||
+                dev_alloc(h, &h->pick_list, (size_t)IG_MAX_CANDS * h->pick_cap)) return -2;
+            CK(cudaFuncSetAttribute(k_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, h->stream_smem));
+        }
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, cfg->device));
         const int sms = prop.multiProcessorCount;
         h->grid_score = sms * IG_SCORE_CTAS_PER_SM;  // 24 resident warps per SM (80 registers per thread; 6 KB of accumulators per warp)
         CK(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IG_SCORE_SMEM));
-        CK(cudaFuncSetAttribute(k_eval_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IG_SCORE_SMEM));
+        CK(cudaFuncSetAttribute(k_eval_flat<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IG_SCORE_SMEM));
+        CK(cudaFuncSetAttribute(k_eval_flat<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IG_SCORE_SMEM));
         h->grid_flat = (sms * IG_SCORE_CTAS_PER_SM) / 5;   // k_pick grid per candidate: a step's (usually 5) candidates fill the GPU once
         h->flat_items = 2;
         if (const char* e = getenv("IG_FLAT_ITEMS")) h->flat_items = std::max(1, atoi(e));   // a step's (usually 5) candidates fill the GPU once
@@ -323,6 +346,7 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
                 CK(cudaMemcpy(h->cv + off, buf.data(), n * sizeof(int2), cudaMemcpyHostToDevice));
             }
         }
+        CK(cudaMemset(h->cv + h->nnz, 0, 2 * sizeof(int2)));   // k_full_lnz reads contacts in aligned pairs
         CK(cudaMemcpy(h->init_prev, data->init_prev, sizeof(int) * nf, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(h->init_next, data->init_next, sizeof(int) * nf, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(h->orientable, data->orientable, sizeof(int) * nf, cudaMemcpyHostToDevice));
@@ -335,6 +359,15 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
         CK(cudaStreamSynchronize(h->stream));
         CK(cudaMemcpyToSymbol(c_log10_fact, h16, sizeof h16));
         CK(cudaFree(d16));
+        {   // log10_f32: bucket centres of the float mantissa
+            double2 tab[128];
+            for (int i = 0; i < 128; i++) { const double c = 1.0 + (i + 0.5) / 128.0; tab[i].x = 1.0 / c; tab[i].y = log10(c); }
+            CK(cudaMemcpyToSymbol(g_log10tab, tab, sizeof tab));
+        }
+        // observed-count-only part of the likelihood terms, summed once (it depends on neither scaffold nor parameters)
+        k_obc_sum<<<h->n_part_full, IG_THREADS, 0, h->stream>>>(h->cv, h->nnz, h->part_full);
+        k_reduce<<<1, 256, 0, h->stream>>>(h->part_full, h->n_part_full, &h->sc->obc_total, nullptr, nullptr);
+        CK(cudaStreamSynchronize(h->stream));
         // label counter: labels in the initial scaffold are arbitrary; start above their maximum
         int maxlab = 0;
         for (int i = 0; i < nf; i++) maxlab = std::max(maxlab, data->frags13[(size_t)2 * nf + i]);
@@ -350,7 +383,7 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
 extern "C" void ig_destroy(ig_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
-    void* ptrs[] = {h->flat_cnt, h->flat_list, h->clstab, h->subx, h->rinfo, h->nb_ptr, h->nb_idx, h->nb_cdf, h->nb_nnz, h->cyc_frags, h->live, h->part_out, h->part_c, h->table, h->table_len, h->rowidx, h->init_live, h->sub, h->coord, h->clen, h->row_ptr, h->cv, h->sym_diag,
+    void* ptrs[] = {h->bitmap, h->cls16, h->pick_list, h->flat_cnt, h->flat_list, h->clstab, h->subx, h->rinfo, h->nb_ptr, h->nb_idx, h->nb_cdf, h->nb_nnz, h->cyc_frags, h->live, h->part_out, h->part_c, h->table, h->table_len, h->rowidx, h->init_live, h->sub, h->coord, h->clen, h->row_ptr, h->cv, h->sym_diag,
                     h->init_prev, h->init_next, h->orientable, h->sc, h->desc, h->exz, h->exz_test, h->chunk_cnt,
                     h->rows, h->row_cnt, h->part_nz, h->part_z, h->part_i, h->part_full, h->part_zc, h->part_nc,
                     h->d_perm, h->d_hist};
@@ -491,6 +524,51 @@ static int score_grid_x(const ig_handle* h, int n) {
     return std::max(h->grid_score / std::max(n, 1), h->grid_score / 8) * h->grid_split;
 }
 
+// rows + precompute + scoring kernels of one step (after k_cand_setup / k_find_cuts / k_classes were enqueued);
+// in_step: event joins with the side streams and the profiling marks of enqueue_step
+#define IG_MARK(i) do { if (h->profile && !h->capturing) cudaEventRecord(h->evk[i], h->stream); } while (0)
+static void enqueue_scoring(ig_handle* h, int n, bool in_step) {
+    const float mbar = h->cfg.mean_sub_len_kb;
+    const FragRec* live = h->live;
+    if (h->rows_small) {
+        if (in_step) IG_MARK(3);
+        k_rows_small<<<n, IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->n_chunks, h->rows, h->rowidx, h->row_cnt, h->ns,
+                                                        h->clstab, h->row_ptr, h->rinfo);
+    } else {
+        k_rows_count<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks);
+        if (in_step) IG_MARK(3);
+        k_rows_write<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks, h->rows,
+                                                                           h->rowidx, h->row_cnt, h->ns, h->clstab, h->row_ptr, h->rinfo,
+                                                                           h->bitmap, h->bitmap_words, h->cls16);
+    }
+    if (in_step) IG_MARK(4);
+    k_precompute<<<dim3(h->grid_pre, n), IG_PRE_THREADS, 0, h->stream>>>(h->coord, h->clen, live, h->sub, h->sc, h->desc, h->rows, h->ns,
+                                                                    h->table, h->table_len, mbar, h->part_z, h->part_i);
+    if (h->profile && !h->capturing) cudaEventRecord(h->ev[4], h->stream);
+    if (in_step) { cudaStreamWaitEvent(h->stream, h->ev_cls, 0); IG_MARK(5); }
+    const int gsx = h->flat ? h->grid_flat : score_grid_x(h, n);
+    if (h->flat) {
+        k_pick<<<dim3(gsx, n), IG_THREADS, 0, h->stream>>>(h->cv, h->coord, h->clen, h->sc, h->desc, h->rowidx, h->ns, h->row_cnt,
+                                                                    h->flat_cnt, h->chunk_stride, h->part_c, h->flat_list, h->flat_stride, mbar, h->exz,
+                                                                    h->clstab, h->subx, h->rinfo);
+        k_eval_flat<false><<<h->grid_score, IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->sc, h->desc, h->ns, h->flat_cnt, h->chunk_stride, h->flat_list,
+                                                                            h->flat_stride, h->table, h->table_len, mbar, h->exz, h->part_nz, h->clstab, h->flat_items);
+    } else {
+        if (h->streaming) {
+            k_stream<<<dim3(gsx, n), IG_THREADS, h->stream_smem, h->stream>>>(h->cv, h->coord, h->clen, h->sc, h->desc, h->rowidx, h->ns, h->row_cnt,
+                                                                             h->bitmap, h->bitmap_words, h->cls16, h->part_c, h->pick_list, h->pick_cap,
+                                                                             mbar, h->exz, h->clstab, h->subx, h->rinfo);
+            k_eval_flat<true><<<h->grid_score, IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->sc, h->desc, h->ns, nullptr, 0, h->pick_list, h->pick_cap,
+                                                                               h->table, h->table_len, mbar, h->exz, h->part_nz, h->clstab, h->flat_items);
+        }
+        // (streaming mode: k_score only works for the candidates k_stream leaves to it -- circular contigs)
+        k_score<<<dim3(gsx, n), IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
+                                                                     h->ns, h->row_cnt, h->table, h->table_len, mbar, h->exz, h->part_nz,
+                                                                     h->part_c, h->gs_div, h->clstab, h->subx, h->rinfo, h->sparse_div);
+    }
+    if (h->profile && !h->capturing) cudaEventRecord(h->ev[5], h->stream);
+}
+
 static int score_candidates(ig_handle* h, int a, const int32_t* cands, int n, int first_flip_eject, bool overlap) {
     if (n <= 0 || n > IG_MAX_CANDS) { h->err = "n_cands out of range"; return -1; }
     if (a < 0 || a >= h->nf) { h->err = "id_frag out of range"; return -1; }
@@ -501,33 +579,12 @@ static int score_candidates(ig_handle* h, int a, const int32_t* cands, int n, in
     for (int i = 0; i < IG_MAX_CANDS; i++) hs[2 + i] = i < n ? cands[i] : 0;
     CK(cudaMemcpyAsync(&h->sc->n_cands, hs, (2 + IG_MAX_CANDS) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     const FragRec* live = h->live;
-    k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, first_flip_eject, nullptr);
+    k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, first_flip_eject, nullptr, h->streaming ? 1 : 0);
     k_find_cuts<<<dim3((h->nf + 255) / 256, n), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc, h->clstab);
     k_classes<<<n, IG_N_OPS * 32, 0, h->stream>>>(h->sc, h->desc, h->clstab, h->rigid, h->cfg.mean_sub_len_kb);
     if (overlap) cudaStreamWaitEvent(h->stream, h->ev_coords, 0);
-    if (h->rows_small) {
-        k_rows_small<<<n, IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->n_chunks, h->rows, h->rowidx, h->row_cnt, h->ns,
-                                                        h->clstab, h->row_ptr, h->rinfo);
-    } else {
-        k_rows_count<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks);
-        k_rows_write<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks, h->rows,
-                                                                           h->rowidx, h->row_cnt, h->ns, h->clstab, h->row_ptr, h->rinfo);
-    }
-    k_precompute<<<dim3(h->grid_pre, n), IG_PRE_THREADS, 0, h->stream>>>(h->coord, h->clen, live, h->sub, h->sc, h->desc, h->rows, h->ns,
-                                                                    h->table, h->table_len, mbar, h->part_z, h->part_i);
-    if (h->profile) cudaEventRecord(h->ev[4], h->stream);
+    enqueue_scoring(h, n, false);
     const int gsx = h->flat ? h->grid_flat : score_grid_x(h, n);
-    if (h->flat) {
-        k_pick<<<dim3(gsx, n), IG_THREADS, 0, h->stream>>>(h->cv, h->coord, h->clen, h->sc, h->desc, h->rowidx, h->ns, h->row_cnt,
-                                                                    h->flat_cnt, h->chunk_stride, h->part_c, h->flat_list, h->flat_stride, mbar, h->exz,
-                                                                    h->clstab, h->subx, h->rinfo);
-        k_eval_flat<<<h->grid_score, IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->sc, h->desc, h->ns, h->flat_cnt, h->chunk_stride, h->flat_list,
-                                                                            h->flat_stride, h->table, h->table_len, mbar, h->exz, h->part_nz, h->clstab, h->flat_items);
-    } else
-    k_score<<<dim3(gsx, n), IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
-                                                                 h->ns, h->row_cnt, h->table, h->table_len, mbar, h->exz, h->part_nz,
-                                                                 h->part_c, h->gs_div, h->clstab, h->subx, h->rinfo, h->sparse_div);
-    if (h->profile) cudaEventRecord(h->ev[5], h->stream);
     h->n_launches += 7;
     if (overlap) cudaStreamWaitEvent(h->stream, h->ev_lnz, 0);
     k_finalize<<<n, 1024, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->sc, h->desc, h->rows, h->rowidx, h->ns, h->row_cnt, h->table,
@@ -552,6 +609,7 @@ static int fetch_result(ig_handle* h, int n, const int32_t* cands, ig_step_resul
         CK(cudaStreamSynchronize(h->stream));
     }
     const DevScalars& s = *h->h_sc;
+    if (s.list_overflow) { h->err = "pick list of the streaming scoring path overflowed (IG_PICK_CAP)"; return -4; }
     memset(out, 0, sizeof *out);
     for (int i = 0; i < n * IG_N_OPS; i++) out->scores[i] = s.scores[i];
     out->lnz_full = s.lnz_full;
@@ -610,9 +668,8 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands, int cycle = 0)
         cudaEventRecord(h->ev_lnz, h->side);
     }
     const FragRec* live = h->live;
-#define IG_MARK(i) do { if (h->profile && !h->capturing) cudaEventRecord(h->evk[i], h->stream); } while (0)
     IG_MARK(0);
-    k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, 1, cycle ? h->cyc_in : nullptr);
+    k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, 1, cycle ? h->cyc_in : nullptr, h->streaming ? 1 : 0);
     IG_MARK(1);
     k_find_cuts<<<dim3((h->nf + 255) / 256, n), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc, h->clstab);
     cudaEventRecord(h->ev_cuts, h->stream);
@@ -621,34 +678,8 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands, int cycle = 0)
     cudaEventRecord(h->ev_cls, h->pf);
     cudaStreamWaitEvent(h->stream, h->ev_coords, 0);
     IG_MARK(2);
-    if (h->rows_small) {
-        IG_MARK(3);
-        k_rows_small<<<n, IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->n_chunks, h->rows, h->rowidx, h->row_cnt, h->ns,
-                                                        h->clstab, h->row_ptr, h->rinfo);
-    } else {
-        k_rows_count<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks);
-        IG_MARK(3);
-        k_rows_write<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks, h->rows,
-                                                                           h->rowidx, h->row_cnt, h->ns, h->clstab, h->row_ptr, h->rinfo);
-    }
-    IG_MARK(4);
-    k_precompute<<<dim3(h->grid_pre, n), IG_PRE_THREADS, 0, h->stream>>>(h->coord, h->clen, live, h->sub, h->sc, h->desc, h->rows, h->ns,
-                                                                    h->table, h->table_len, mbar, h->part_z, h->part_i);
-    if (h->profile && !h->capturing) cudaEventRecord(h->ev[4], h->stream);
-    cudaStreamWaitEvent(h->stream, h->ev_cls, 0);
-    IG_MARK(5);
+    enqueue_scoring(h, n, true);
     const int gsx = h->flat ? h->grid_flat : score_grid_x(h, n);
-    if (h->flat) {
-        k_pick<<<dim3(gsx, n), IG_THREADS, 0, h->stream>>>(h->cv, h->coord, h->clen, h->sc, h->desc, h->rowidx, h->ns, h->row_cnt,
-                                                                    h->flat_cnt, h->chunk_stride, h->part_c, h->flat_list, h->flat_stride, mbar, h->exz,
-                                                                    h->clstab, h->subx, h->rinfo);
-        k_eval_flat<<<h->grid_score, IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->sc, h->desc, h->ns, h->flat_cnt, h->chunk_stride, h->flat_list,
-                                                                            h->flat_stride, h->table, h->table_len, mbar, h->exz, h->part_nz, h->clstab, h->flat_items);
-    } else
-    k_score<<<dim3(gsx, n), IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
-                                                                 h->ns, h->row_cnt, h->table, h->table_len, mbar, h->exz, h->part_nz,
-                                                                 h->part_c, h->gs_div, h->clstab, h->subx, h->rinfo, h->sparse_div);
-    if (h->profile && !h->capturing) cudaEventRecord(h->ev[5], h->stream);
     cudaStreamWaitEvent(h->stream, h->ev_lnz, 0);
     IG_MARK(6);
     k_finalize<<<n, 1024, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->sc, h->desc, h->rows, h->rowidx, h->ns, h->row_cnt, h->table,
@@ -720,7 +751,7 @@ extern "C" int ig_step(ig_handle* h, int32_t id_frag, const int32_t* cands, int3
     }
     cudaEventRecord(h->ev[1], h->stream);
     CK(cudaStreamSynchronize(h->stream));
-    h->n_launches += (full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR) - (h->rigid ? 1 : 0) + (h->prefetch ? 1 : 0) - (h->rows_small ? 1 : 0) + (h->flat ? 1 : 0);
+    h->n_launches += (full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR) - (h->rigid ? 1 : 0) + (h->prefetch ? 1 : 0) - (h->rows_small ? 1 : 0) + (h->flat ? 1 : 0) + (h->streaming ? 2 : 0);
     h->steps_since_full = full ? 1 : h->steps_since_full + 1;
     h->n_full += full;
     h->incr_valid = true;
@@ -773,7 +804,7 @@ static int run_plan(ig_handle* h, int n_steps, GridN grid_n, ig_cycle_step* out)
         h->steps_since_full = full ? 1 : h->steps_since_full + 1;
         h->n_full += full;
         h->incr_valid = true;
-        h->n_launches += (full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR) - (h->rigid ? 1 : 0) + (h->prefetch ? 1 : 0) - (h->rows_small ? 1 : 0) + (h->flat ? 1 : 0);
+        h->n_launches += (full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR) - (h->rigid ? 1 : 0) + (h->prefetch ? 1 : 0) - (h->rows_small ? 1 : 0) + (h->flat ? 1 : 0) + (h->streaming ? 2 : 0);
     }
     cudaEventRecord(h->ev[1], h->stream);
     std::vector<CycleOut> res(n_steps);
@@ -906,7 +937,7 @@ extern "C" int ig_apply(ig_handle* h, int32_t id_frag, int32_t id_cand, int32_t 
     CK(cudaMemcpyAsync(saved, h->sc->valid, sizeof saved, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     const FragRec* live = h->live;
-    k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, 0, nullptr);
+    k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, 0, nullptr, 0);
     k_find_cuts<<<dim3((h->nf + 255) / 256, 1), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc, h->clstab);
     // test_copy_struct only re-runs get_bounds for op >= 12 (CL:2121-2126): restore the list otherwise
     CK(cudaMemcpyAsync(h->sc->valid, saved, sizeof saved, cudaMemcpyHostToDevice, h->stream));
@@ -929,12 +960,19 @@ extern "C" int ig_full_likelihood(ig_handle* h, const float p8[8], int32_t use_s
     k_coords<<<h->n_part_zc, IG_THREADS, 0, h->stream>>>(h->live, h->sub, h->coord, h->clen, h->ns, h->sc, mbar, 1,
                                                         h->part_zc, h->part_nc, write, h->subx);
     k_reduce<<<1, 256, 0, h->stream>>>(h->part_zc, h->n_part_zc, &h->sc->full_out[1], h->part_nc, &h->sc->full_nintra);
+    cudaEventRecord(h->ev[2], h->stream);
     k_full_lnz<<<h->n_part_full, IG_THREADS, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->ns, h->sc, mbar, 1,
                                                             h->exz_test, h->part_full);
+    cudaEventRecord(h->ev[3], h->stream);
     k_reduce<<<1, 256, 0, h->stream>>>(h->part_full, h->n_part_full, &h->sc->full_out[0], nullptr, nullptr);
     if (launch_ok(h, "full_likelihood")) return -2;
+    h->n_launches += 6;
     CK(cudaMemcpyAsync(h->h_sc, h->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    {   // device time of the nuisance likelihood (always measured: two events per call)
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) { h->ms_nuis += ms; h->n_nuis++; }
+    }
     out3[0] = h->h_sc->full_out[0];
     out3[1] = h->h_sc->full_out[1];
     out3[2] = (double)h->h_sc->full_nintra;
@@ -992,9 +1030,49 @@ extern "C" int ig_get_stats(ig_handle* h, double out10[10], int32_t reset) {
     }
     return 0;
 }
+// device self-test of the two transcribed math routines against the library ones (tests/test_gpu_math.py):
+// n samples of x log-uniform in [x_lo, x_hi] with exponent y; out[0] = number of inputs where powf_pos differs from powf
+// in any bit, out[1] = max |log10_f32(x) - log10((double)x)|
+__global__ void k_selftest_math(int n, float x_lo, float x_hi, float y, unsigned long long* n_bad, double* max_err) {
+    const float l0 = log2f(x_lo), l1 = log2f(x_hi);
+    unsigned long long bad = 0;
+    double worst = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        unsigned hsh = (unsigned)i * 2654435761u; hsh ^= hsh >> 15; hsh *= 2246822519u; hsh ^= hsh >> 13;
+        const float x = exp2f(l0 + (l1 - l0) * ((float)(hsh >> 8) * (1.0f / 16777216.0f)));
+        if (__float_as_uint(powf_pos(x, y)) != __float_as_uint(powf(x, y))) bad++;
+        worst = fmax(worst, fabs(log10_f32(x) - log10((double)x)));
+    }
+    if (bad) atomicAdd(n_bad, bad);
+    atomicMax((unsigned long long*)max_err, (unsigned long long)__double_as_longlong(worst));   // non-negative doubles order like integers
+}
+extern "C" int ig_selftest_math(ig_handle* h, int32_t n, float x_lo, float x_hi, float y, double out2[2]) {
+    if (use(h)) return -1;
+    unsigned long long* d = nullptr;
+    if (dev_alloc(h, &d, 2)) return -2;
+    CK(cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), h->stream));
+    k_selftest_math<<<296, 256, 0, h->stream>>>(n, x_lo, x_hi, y, d, reinterpret_cast<double*>(d + 1));
+    if (launch_ok(h, "selftest_math")) return -2;
+    unsigned long long r[2];
+    CK(cudaMemcpyAsync(r, d, sizeof r, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(d);
+    out2[0] = (double)r[0];
+    memcpy(&out2[1], &r[1], sizeof(double));
+    return 0;
+}
+
 extern "C" int ig_set_profiling(ig_handle* h, int32_t on) {
     if (!h) return -1;
     h->profile = on ? 1 : 0;
+    return 0;
+}
+
+// device ms spent in the full-likelihood kernel by ig_full_likelihood calls (nuisance step) and their number
+extern "C" int ig_get_nuisance_stats(ig_handle* h, double out2[2], int32_t reset) {
+    if (!h) return -1;
+    out2[0] = h->ms_nuis; out2[1] = (double)h->n_nuis;
+    if (reset) { h->ms_nuis = 0.0; h->n_nuis = 0; }
     return 0;
 }
 

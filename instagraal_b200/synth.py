@@ -342,6 +342,20 @@ def make_level(spec: SynthSpec, geometry=None) -> LevelData:
     )
 
 
+def workload_params(level):
+    """float32[8] param_simu (kuhn, lm, c1, slope, d, d_max, fact, v_inter; KA:91-100) the contacts of `level` were
+    simulated with (optim_rippe_curve_update.py:66-70 defaults; fact / v_inter from the workload's spec)."""
+    spec = level.spec
+    kuhn, lm, slope = 50.0, 9.6, -1.5
+    c1 = np.float32(0.53 * (lm / kuhn) ** slope * kuhn ** -3)
+    s1 = float(level.S_o_A_sub_frags["len_bp"].mean()) / 1000.0
+    fact = spec.lambda1 / (float(c1) * s1 ** slope)
+    ns = level.n_sub_frags
+    v_inter = max(spec.trans_per_row * 2.0 / ns, 1e-6) / 10.0
+    d_max = (v_inter / (float(c1) * fact)) ** (1.0 / slope)
+    return np.array([kuhn, lm, c1, slope, 2.0, d_max, fact, v_inter], dtype=np.float32)
+
+
 # Named workloads (BASELINE.md section 4).  T = toy/yeast-like level 4; Y3 = yeast level 3;
 # G = ~1 Gb synthetic (1e5 fragments, ~3e5 sub-fragments, ~1e8 contacts).
 YEAST_TOY_GEOMETRY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "yeast_toy_geometry.npz")

@@ -525,3 +525,82 @@ def test_medium_level_with_long_contigs_takes_the_large_level_paths_naturally(bu
     assert level.n_sub_frags > 16 * 1024
     ties = _lockstep(level, P8_RIPPE, 30, seed=3)
     assert ties <= 6
+
+
+@pytest.mark.parametrize("workload,steps", [("T", 1200), ("toy", 400)])
+def test_streaming_path_equals_row_per_warp_rigid_path(built, workload, steps, monkeypatch):
+    """The streaming scoring path of large levels (k_stream + k_eval_flat<true>, rigid_pruning=1) forced on small levels:
+    same selected-contact counts, scores equal to the row-per-warp kernel's in rigid mode up to the 2^-32 fixed-point
+    rounding of its order-independent sums, same trajectory (unless two scores are that close), and two runs of the
+    streaming path are bit-identical although its pick list is appended in arbitrary order."""
+    level = make_level(WORKLOADS[workload])
+    p8 = P8_RIPPE if workload == "T" else P8
+    monkeypatch.setenv("IG_FLAT", "0")
+    ref = make_sampler(level, rigid_pruning=True)        # k_score, rigid class-pair table
+    monkeypatch.setenv("IG_FORCE_STREAM", "1")
+    st1 = make_sampler(level, rigid_pruning=True)
+    st2 = make_sampler(level, rigid_pruning=True)
+    ss = [ref, st1, st2]
+    for s in ss:
+        s.set_param_simu(p8)
+        np.random.seed(5)
+        s.bomb_the_genome()
+    rng = np.random.RandomState(10)
+    n_div = 0
+    worst = 0.0
+    for t in range(steps):
+        a = int(rng.randint(level.n_frags))
+        cands = sorted(int(c) for c in rng.choice(level.n_frags, 5, replace=False) if c != a)
+        outs = [s.step_sampler(a, 5, np.float32(0.01), candidates=cands) for s in ss]
+        r, x, y = (s.all_scores.copy() for s in ss)
+        assert np.array_equal(x, y), ("streaming path not deterministic", t)
+        assert outs[1] == outs[2]
+        assert ss[0].n_sub_vals == ss[1].n_sub_vals, (t, ss[0].n_sub_vals, ss[1].n_sub_vals)
+        assert np.array_equal(r != 0, x != 0)
+        nz = r != 0
+        d = float(np.max(np.abs(r[nz] - x[nz])))
+        worst = max(worst, d)
+        assert d < 1e-6, (t, d)
+        if (outs[0][2], outs[0][3]) != (outs[1][2], outs[1][3]):
+            top = np.sort(r[nz])[-2:]
+            assert abs(top[1] - top[0]) <= 2e-6, "diverged without a tie"
+            n_div += 1
+            for s in ss[1:]:
+                s._set_state(ss[0]._get_state())
+                s.set_valid_insert(ss[0].get_valid_insert())
+    assert np.array_equal(ss[0]._get_state(), ss[1]._get_state()) or n_div > 0
+    print("streaming vs row-per-warp (rigid): worst |score difference|", worst, "tie divergences", n_div)
+    for s in ss:
+        s.free_gpu()
+
+
+def test_streaming_path_random_scaffolds_with_circular_contigs(built, monkeypatch):
+    """eval on random scaffolds incl. circular contigs (left to k_score inside a streaming-mode step) and reversed
+    fragments: streaming == row-per-warp in rigid mode."""
+    from oracle.fuzz import random_state
+    level = make_level(WORKLOADS["micro"])
+    monkeypatch.setenv("IG_FLAT", "0")
+    ref = make_sampler(level, rigid_pruning=True)
+    monkeypatch.setenv("IG_FORCE_STREAM", "1")
+    st = make_sampler(level, rigid_pruning=True)
+    for s in (ref, st):
+        s.set_param_simu(P8)
+    rng = np.random.RandomState(3)
+    nf = level.n_frags
+    for it in range(40):
+        state = random_state(nf, rng, p_circ=0.4)
+        for k in ("len_bp", "sub_len"):
+            state[k] = np.asarray(level.S_o_A_frags[k], dtype=np.int32).copy()
+        state = _rebuild_offsets(state)
+        st13 = np.stack([state[k] for k in FIELDS13]).astype(np.int32)
+        a, b = [int(x) for x in rng.choice(nf, 2, replace=False)]
+        valid0 = rng.choice([-1, 1], 12).astype(np.int32)
+        res = []
+        for s in (ref, st):
+            s._set_state(st13)
+            s.set_valid_insert(valid0)
+            res.append((s.eval_all_sub_likelihood(a, b, 1), s.n_sub_vals[0]))
+        assert res[0][1] == res[1][1], (it, a, b)
+        assert np.array_equal(res[0][0] != 0, res[1][0] != 0)
+        assert np.max(np.abs(res[0][0] - res[1][0])) < 1e-6, (it, a, b, np.max(np.abs(res[0][0] - res[1][0])))
+    ref.free_gpu(); st.free_gpu()
