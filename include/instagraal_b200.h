@@ -4,7 +4,7 @@
  * "CL"): every entry point below replaces the pycuda launch sequence of one reference method.
  * Plain C: borrowed, C-contiguous host buffers in, caller-allocated buffers out; nothing returned
  * by pointer outlives the call.  One handle = one chain on one GPU, single host thread, all calls
- * blocking.  Every function returns 0 on success or a negative code (message: ig_last_error).
+ * blocking (except ig_run_cycle_device_async).  Every function returns 0 on success or a negative code (message: ig_last_error).
  * There is no CPU path: ig_create fails when no CUDA device is usable.
  */
 #ifndef INSTAGRAAL_B200_H
@@ -173,8 +173,32 @@ int ig_get_full_refresh_count(ig_handle* h, int64_t* out);
  * [x_lo, x_hi], exponent y; out2 = { inputs where powf_pos != powf bit-wise, max |log10_f32 - log10| }. */
 int ig_selftest_math(ig_handle* h, int32_t n, float x_lo, float x_hi, float y, double out2[2]);
 
-/* replica chains (one handle per GPU/process): exchange {likelihood, n_contigs, live id_c/pos/ori...}
- * is done by the host facade over NCCL; the library only exposes the packed best-state buffer. */
+/* ---- replica chains (a chain is sequential, so the 8-GPU box runs independent chains, one or more per GPU).
+ * The reference has no counterpart: it is single-process, single-GPU (instagraal.py:55 pycuda.autoinit).
+ *
+ * ig_clone: a further chain on the same level and device.  Own scaffold / scratch / streams; the contacts, sub-fragment
+ * table, initial scaffold and neighbour weights are shared with `parent` (freed with the last chain that uses them). */
+int ig_clone(ig_handle* parent, ig_handle** out);
+/* ig_run_cycle_device for n_chains chains of one device at once: steps enqueued round-robin on the chains' streams, one wait
+ * at the end, so the chains run side by side.  frags = [n_chains][n_steps], seeds = [n_chains], out = [n_chains][n_steps]. */
+int ig_run_cycles_device_multi(ig_handle** chains, int32_t n_chains, int32_t n_steps, const int32_t* frags, int32_t n_neighbours,
+                               const uint64_t* seeds, uint32_t cycle, ig_cycle_step* out);
+/* the same, one chain, without waiting: ig_cycle_wait collects the records of the n_steps enqueued steps */
+int ig_run_cycle_device_async(ig_handle* h, int32_t n_steps, const int32_t* frags, int32_t n_neighbours, uint64_t seed, uint32_t cycle);
+int ig_cycle_wait(ig_handle* h, int32_t n_steps, ig_cycle_step* out);
+/* NCCL all-gather of every chain's likelihood + live scaffold, inside the library (libnccl.so.2 is dlopen'ed on first use).
+ * ig_nccl_unique_id: rank 0 creates the id, the launcher distributes it (file, environment, MPI, ...).
+ * ig_nccl_init: one communicator per process / GPU, owned by `lead`; n_ranks == 1 needs no id and no NCCL.
+ * ig_allgather_best: lik / n_contigs = [n_ranks * n_local] (rank-major); best = index of the highest likelihood (lowest index
+ * on ties; the same on every rank); ms = device time of pack + all-gather (CUDA events).
+ * ig_get_gathered_state: scaffold [13][NF] of chain `index` as of the last all-gather. */
+int ig_nccl_unique_id(char id_out[128]);
+int ig_nccl_init(ig_handle* lead, int32_t rank, int32_t n_ranks, int32_t n_local_chains, const char id[128]);
+int ig_allgather_best(ig_handle* lead, ig_handle** local_chains, int32_t n_local, double* lik, int32_t* n_contigs, int32_t* best,
+                      float* ms);
+int ig_get_gathered_state(ig_handle* lead, int32_t index, int32_t* out13xNF);
+int ig_nccl_finalize(ig_handle* lead);
+/* device address of the live scaffold records (64 B per fragment) -- diagnostics */
 int ig_device_state_ptr(ig_handle* h, void** dev_ptr, int64_t* n_bytes);
 
 #ifdef __cplusplus

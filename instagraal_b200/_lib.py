@@ -23,7 +23,8 @@ EXPORTS = (
     "ig_apply", "ig_full_likelihood", "ig_distance_histogram", "ig_set_sym_diag", "ig_device_state_ptr",
     "ig_set_profiling", "ig_get_stats", "ig_set_options", "ig_get_full_refresh_count", "ig_get_kernel_times", "ig_run_cycle", "ig_contact_thumbnail", "ig_set_neighbour_weights",
            "ig_run_cycle_device", "ig_get_cycle_plan", "ig_timeline_reset", "ig_timeline_get", "ig_timeline_blocks", "ig_timeline_phases",
-    "ig_selftest_math", "ig_get_nuisance_stats",
+    "ig_selftest_math", "ig_get_nuisance_stats", "ig_clone", "ig_run_cycles_device_multi", "ig_run_cycle_device_async", "ig_cycle_wait",
+    "ig_nccl_unique_id", "ig_nccl_init", "ig_allgather_best", "ig_get_gathered_state", "ig_nccl_finalize",
 )
 
 
@@ -101,6 +102,15 @@ def lib():
         L.ig_timeline_phases.argtypes = [vp, vp, i32]
         L.ig_get_full_refresh_count.argtypes = [vp, C.POINTER(i64)]
         L.ig_get_nuisance_stats.argtypes = [vp, vp, i32]
+        L.ig_clone.argtypes = [vp, C.POINTER(vp)]
+        L.ig_run_cycles_device_multi.argtypes = [vp, i32, i32, vp, i32, vp, C.c_uint32, vp]
+        L.ig_run_cycle_device_async.argtypes = [vp, i32, vp, i32, C.c_uint64, C.c_uint32]
+        L.ig_cycle_wait.argtypes = [vp, i32, vp]
+        L.ig_nccl_unique_id.argtypes = [vp]
+        L.ig_nccl_init.argtypes = [vp, i32, i32, i32, vp]
+        L.ig_allgather_best.argtypes = [vp, vp, i32, vp, vp, C.POINTER(i32), C.POINTER(C.c_float)]
+        L.ig_get_gathered_state.argtypes = [vp, i32, vp]
+        L.ig_nccl_finalize.argtypes = [vp]
         L.ig_selftest_math.argtypes = [vp, i32, C.c_float, C.c_float, C.c_float, vp]
         for name in EXPORTS:
             if name not in ("ig_destroy", "ig_last_error"):

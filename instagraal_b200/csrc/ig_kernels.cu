@@ -115,8 +115,17 @@ struct CycleOut {  // compact per-step record of ig_run_cycle (128 B)
 
 // ================================================================================================
 // host side
+// the level's read-only arrays: shared by every chain cloned from one handle (ig_clone), freed with the last of them
+struct LevelBlock {
+    int refs;
+    int* sym_diag;
+    long long* nb_ptr; int* nb_idx; double* nb_cdf; int* nb_nnz;
+};
+struct ig_replica_state;
 struct ig_handle {
     ig_config cfg;
+    LevelBlock* lvl;
+    ig_replica_state* rep;   // NCCL communicator + gather buffers (ig_nccl_init), owned by the process's lead handle
     int nf, ns;
     long long nnz;
     cudaStream_t stream, side, pf;
@@ -133,7 +142,6 @@ struct ig_handle {
     int* clen;
     long long* row_ptr;
     int2* cv;
-    int* sym_diag;
     int *init_prev, *init_next, *orientable;
     DevScalars* sc;
     IgDescriptor* desc;
@@ -144,20 +152,21 @@ struct ig_handle {
     int grid_pre;
     RowMut* table; int *table_len, *rowidx;
     IgClassTab* clstab; int rigid; SubX* subx; RowInfo* rinfo;
-    long long* nb_ptr; int* nb_idx; double* nb_cdf; int* nb_nnz; int* cyc_frags;
+    int* cyc_frags;
     double *part_full; int n_part_full;
     double *part_zc; int* part_nc; int n_part_zc;
     int *d_nuniq, *d_nsub, *d_perm;
     unsigned long long* d_hist;
     DevScalars* h_sc;  // pinned mirror
     int* h_small;      // pinned scratch (cands, nuniq, nsub)
-    bool params_set, coords_fresh, coords_ever;
+    bool params_set, coords_fresh, coords_ever; int init_max_label;
     bool incr_valid; int refresh_every; long long steps_since_full;
     double* part_out;
     int gs_div, sparse_div, grid_split;
     long long last_n_full;
     cudaGraphExec_t graph[4][IG_MAX_CANDS + 1];   // [full + 2 * cycle][candidates in the grid]
     int* cyc_in; CycleOut* cyc_out; int cyc_cap; bool graph_failed, capturing, use_graph; long long n_full;
+    int pending_steps;   // steps enqueued by an asynchronous cycle call and not collected yet
     // measurement (CUDA events on the launching stream)
     cudaEvent_t ev[6];
     cudaEvent_t evk[16]; double ms_k[16];  // per-kernel event timing of the main stream (profiling mode)
@@ -204,9 +213,10 @@ static int upload_state(ig_handle* h, const int32_t* in13, FragRec* dst) {
     return 0;
 }
 
-extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_handle** out) {
+// parent != nullptr: a further chain on the same level (ig_clone): the level's read-only arrays are borrowed, not uploaded
+static int create_impl(const ig_config* cfg, const ig_level_data* data, ig_handle* parent, ig_handle** out) {
     ig_handle* h = nullptr;
-    if (!cfg || !data || !out) { g_err = "ig_create: null argument"; return -1; }
+    if (!cfg || (!data && !parent) || !out) { g_err = "ig_create: null argument"; return -1; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
         g_err = "ig_create: no CUDA device available (this library has no CPU path)";
@@ -232,7 +242,7 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
     if (const char* e = getenv("IG_GS_DIV")) h->gs_div = std::max(1, atoi(e));
     if (const char* e = getenv("IG_BLOCK_MODE")) if (atoi(e)) h->gs_div = -h->gs_div;
     memset(h->graph, 0, sizeof h->graph); h->cyc_in = nullptr; h->cyc_out = nullptr; h->cyc_frags = nullptr; h->cyc_cap = 0;
-    h->nb_ptr = nullptr; h->nb_idx = nullptr; h->nb_cdf = nullptr; h->nb_nnz = nullptr; h->graph_failed = false; h->capturing = false; h->use_graph = true; h->n_full = 0;
+    h->graph_failed = false; h->capturing = false; h->use_graph = true; h->n_full = 0; h->pending_steps = 0; h->rep = nullptr;
     cudaError_t e0 = cudaSetDevice(cfg->device);
     if (e0 != cudaSuccess) { g_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e0); delete h; return -2; }
 #define CKC(x) do { int r_ = (x); if (r_) { g_err = h->err; ig_destroy(h); return r_; } } while (0)
@@ -251,10 +261,18 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
         for (int i = 0; i < 16; i++) { CK(cudaEventCreate(&h->evk[i])); h->ms_k[i] = 0.0; }
         h->ms_step = h->ms_score = h->ms_full = 0.0; h->ms_nuis = 0.0; h->n_nuis = 0; h->n_launches = 0; h->n_steps = 0; h->profile = 0;
         const int nf = h->nf, ns = h->ns;
-        if (dev_alloc(h, &h->live, nf) || dev_alloc(h, &h->init_live, nf)) return -2;
-        if (dev_alloc(h, &h->sub, ns) || dev_alloc(h, &h->coord, ns) || dev_alloc(h, &h->clen, ns)) return -2;
-        if (dev_alloc(h, &h->row_ptr, (size_t)ns + 1) || dev_alloc(h, &h->cv, (size_t)h->nnz + 2)) return -2;
-        if (dev_alloc(h, &h->init_prev, nf) || dev_alloc(h, &h->init_next, nf) || dev_alloc(h, &h->orientable, nf)) return -2;
+        if (dev_alloc(h, &h->live, nf) || dev_alloc(h, &h->coord, ns) || dev_alloc(h, &h->clen, ns)) return -2;
+        if (parent) {
+            h->lvl = parent->lvl; h->lvl->refs++;
+            h->init_live = parent->init_live; h->sub = parent->sub; h->row_ptr = parent->row_ptr; h->cv = parent->cv;
+            h->init_prev = parent->init_prev; h->init_next = parent->init_next; h->orientable = parent->orientable;
+        } else {
+            h->lvl = new LevelBlock();
+            memset(h->lvl, 0, sizeof(LevelBlock)); h->lvl->refs = 1;
+            if (dev_alloc(h, &h->init_live, nf) || dev_alloc(h, &h->sub, ns)) return -2;
+            if (dev_alloc(h, &h->row_ptr, (size_t)ns + 1) || dev_alloc(h, &h->cv, (size_t)h->nnz + 2)) return -2;
+            if (dev_alloc(h, &h->init_prev, nf) || dev_alloc(h, &h->init_next, nf) || dev_alloc(h, &h->orientable, nf)) return -2;
+        }
         if (dev_alloc(h, &h->sc, 1) || dev_alloc(h, &h->desc, IG_MAX_CANDS)) return -2;
         if (dev_alloc(h, &h->exz, (size_t)ns + 1) || dev_alloc(h, &h->exz_test, (size_t)ns + 1)) return -2;
         h->n_chunks = (ns + IG_ROW_CHUNK - 1) / IG_ROW_CHUNK;
@@ -319,37 +337,40 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
         if (dev_alloc(h, &h->d_perm, nf)) return -2;
         h->d_nuniq = h->sc->res_nuniq; h->d_nsub = h->sc->res_nsub;   // device addresses inside the result record
         if (dev_alloc(h, &h->d_hist, 1 << 16)) return -2;
-        h->sym_diag = nullptr;
         CK(cudaMallocHost((void**)&h->h_sc, sizeof(DevScalars)));
         CK(cudaMallocHost((void**)&h->h_small, 64 * sizeof(int)));
         CK(cudaMemsetAsync(h->sc, 0, sizeof(DevScalars), h->stream));
         // uploads
-        if (upload_state(h, data->frags13, h->live)) return -2;
-        CK(cudaMemcpy(h->init_live, h->live, sizeof(FragRec) * nf, cudaMemcpyDeviceToDevice));
-        {
-            std::vector<SubRec> s(ns);
-            for (int i = 0; i < ns; i++) {
-                s[i].parent = data->sub_parent[i]; s[i].watson = data->sub_watson[i];
-                s[i].crick = data->sub_crick[i]; s[i].j = data->sub_j[i];
-                if (s[i].parent < 0 || s[i].parent >= nf) { h->err = "ig_create: sub_parent out of range"; return -1; }
+        if (parent) {
+            CK(cudaMemcpyAsync(h->live, h->init_live, sizeof(FragRec) * nf, cudaMemcpyDeviceToDevice, h->stream));
+        } else {
+            if (upload_state(h, data->frags13, h->live)) return -2;
+            CK(cudaMemcpy(h->init_live, h->live, sizeof(FragRec) * nf, cudaMemcpyDeviceToDevice));
+            {
+                std::vector<SubRec> s(ns);
+                for (int i = 0; i < ns; i++) {
+                    s[i].parent = data->sub_parent[i]; s[i].watson = data->sub_watson[i];
+                    s[i].crick = data->sub_crick[i]; s[i].j = data->sub_j[i];
+                    if (s[i].parent < 0 || s[i].parent >= nf) { h->err = "ig_create: sub_parent out of range"; return -1; }
+                }
+                CK(cudaMemcpy(h->sub, s.data(), sizeof(SubRec) * ns, cudaMemcpyHostToDevice));
             }
-            CK(cudaMemcpy(h->sub, s.data(), sizeof(SubRec) * ns, cudaMemcpyHostToDevice));
-        }
-        if (data->row_ptr[0] != 0 || data->row_ptr[ns] != h->nnz) { h->err = "ig_create: row_ptr inconsistent with nnz"; return -1; }
-        CK(cudaMemcpy(h->row_ptr, data->row_ptr, sizeof(long long) * ((size_t)ns + 1), cudaMemcpyHostToDevice));
-        {
-            const size_t chunk = 1 << 24;
-            std::vector<int2> buf(std::min<size_t>(chunk, (size_t)h->nnz));
-            for (size_t off = 0; off < (size_t)h->nnz; off += chunk) {
-                const size_t n = std::min(chunk, (size_t)h->nnz - off);
-                for (size_t i = 0; i < n; i++) { buf[i].x = data->col[off + i]; buf[i].y = data->val[off + i]; }
-                CK(cudaMemcpy(h->cv + off, buf.data(), n * sizeof(int2), cudaMemcpyHostToDevice));
+            if (data->row_ptr[0] != 0 || data->row_ptr[ns] != h->nnz) { h->err = "ig_create: row_ptr inconsistent with nnz"; return -1; }
+            CK(cudaMemcpy(h->row_ptr, data->row_ptr, sizeof(long long) * ((size_t)ns + 1), cudaMemcpyHostToDevice));
+            {
+                const size_t chunk = 1 << 24;
+                std::vector<int2> buf(std::min<size_t>(chunk, (size_t)h->nnz));
+                for (size_t off = 0; off < (size_t)h->nnz; off += chunk) {
+                    const size_t n = std::min(chunk, (size_t)h->nnz - off);
+                    for (size_t i = 0; i < n; i++) { buf[i].x = data->col[off + i]; buf[i].y = data->val[off + i]; }
+                    CK(cudaMemcpy(h->cv + off, buf.data(), n * sizeof(int2), cudaMemcpyHostToDevice));
+                }
             }
+            CK(cudaMemset(h->cv + h->nnz, 0, 2 * sizeof(int2)));   // k_full_lnz reads contacts in aligned pairs
+            CK(cudaMemcpy(h->init_prev, data->init_prev, sizeof(int) * nf, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(h->init_next, data->init_next, sizeof(int) * nf, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(h->orientable, data->orientable, sizeof(int) * nf, cudaMemcpyHostToDevice));
         }
-        CK(cudaMemset(h->cv + h->nnz, 0, 2 * sizeof(int2)));   // k_full_lnz reads contacts in aligned pairs
-        CK(cudaMemcpy(h->init_prev, data->init_prev, sizeof(int) * nf, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(h->init_next, data->init_next, sizeof(int) * nf, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(h->orientable, data->orientable, sizeof(int) * nf, cudaMemcpyHostToDevice));
         // factorial table on the device (same libdevice calls as the reference's factorial())
         double* d16;
         CK(cudaMalloc((void**)&d16, 16 * sizeof(double)));
@@ -365,12 +386,18 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
             CK(cudaMemcpyToSymbol(g_log10tab, tab, sizeof tab));
         }
         // observed-count-only part of the likelihood terms, summed once (it depends on neither scaffold nor parameters)
-        k_obc_sum<<<h->n_part_full, IG_THREADS, 0, h->stream>>>(h->cv, h->nnz, h->part_full);
-        k_reduce<<<1, 256, 0, h->stream>>>(h->part_full, h->n_part_full, &h->sc->obc_total, nullptr, nullptr);
+        if (parent) {
+            CK(cudaMemcpyAsync(&h->sc->obc_total, &parent->sc->obc_total, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        } else {
+            k_obc_sum<<<h->n_part_full, IG_THREADS, 0, h->stream>>>(h->cv, h->nnz, h->part_full);
+            k_reduce<<<1, 256, 0, h->stream>>>(h->part_full, h->n_part_full, &h->sc->obc_total, nullptr, nullptr);
+        }
         CK(cudaStreamSynchronize(h->stream));
         // label counter: labels in the initial scaffold are arbitrary; start above their maximum
         int maxlab = 0;
-        for (int i = 0; i < nf; i++) maxlab = std::max(maxlab, data->frags13[(size_t)2 * nf + i]);
+        if (parent) maxlab = parent->init_max_label;
+        else for (int i = 0; i < nf; i++) maxlab = std::max(maxlab, data->frags13[(size_t)2 * nf + i]);
+        h->init_max_label = maxlab;
         CK(cudaMemcpy(&h->sc->max_label, &maxlab, sizeof(int), cudaMemcpyHostToDevice));
         return 0;
     };
@@ -380,10 +407,33 @@ extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_han
     return 0;
 }
 
+extern "C" int ig_create(const ig_config* cfg, const ig_level_data* data, ig_handle** out) {
+    if (!data) { g_err = "ig_create: null argument"; return -1; }
+    return create_impl(cfg, data, nullptr, out);
+}
+// A further chain on the SAME level and device (replicas with different seeds, several per GPU): own scaffold, scratch,
+// streams and graphs; the contacts, sub-fragment table and initial scaffold (the bulk of the memory: 8 B per contact)
+// are shared with `parent` and freed when the last chain using them is destroyed.  The clone starts from the level's
+// initial scaffold with no parameters set.
+extern "C" int ig_clone(ig_handle* parent, ig_handle** out) {
+    if (!parent || !out) { g_err = "ig_clone: null argument"; return -1; }
+    return create_impl(&parent->cfg, nullptr, parent, out);
+}
+
+static void replica_free(ig_handle* h);
 extern "C" void ig_destroy(ig_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
-    void* ptrs[] = {h->bitmap, h->cls16, h->pick_list, h->flat_cnt, h->flat_list, h->clstab, h->subx, h->rinfo, h->nb_ptr, h->nb_idx, h->nb_cdf, h->nb_nnz, h->cyc_frags, h->live, h->part_out, h->part_c, h->table, h->table_len, h->rowidx, h->init_live, h->sub, h->coord, h->clen, h->row_ptr, h->cv, h->sym_diag,
+    replica_free(h);
+    if (h->lvl && --h->lvl->refs > 0) {   // other chains still use the level's arrays
+        h->init_live = nullptr; h->sub = nullptr; h->row_ptr = nullptr; h->cv = nullptr;
+        h->init_prev = nullptr; h->init_next = nullptr; h->orientable = nullptr;
+    } else if (h->lvl) {
+        for (void* q : {(void*)h->lvl->sym_diag, (void*)h->lvl->nb_ptr, (void*)h->lvl->nb_idx, (void*)h->lvl->nb_cdf, (void*)h->lvl->nb_nnz}) if (q) cudaFree(q);
+        delete h->lvl;
+    }
+    h->lvl = nullptr;
+    void* ptrs[] = {h->bitmap, h->cls16, h->pick_list, h->flat_cnt, h->flat_list, h->clstab, h->subx, h->rinfo, h->cyc_frags, h->live, h->part_out, h->part_c, h->table, h->table_len, h->rowidx, h->init_live, h->sub, h->coord, h->clen, h->row_ptr, h->cv,
                     h->init_prev, h->init_next, h->orientable, h->sc, h->desc, h->exz, h->exz_test, h->chunk_cnt,
                     h->rows, h->row_cnt, h->part_nz, h->part_z, h->part_i, h->part_full, h->part_zc, h->part_nc,
                     h->d_perm, h->d_hist};
@@ -791,28 +841,38 @@ static int cycle_buffers(ig_handle* h, int n_steps) {
 
 // replay n_steps steps from the plan in h->cyc_in (already on the device, or being written by an earlier kernel of
 // the stream); grid_n(t) = number of candidate slots the step's grid is built for
-template <class GridN>
-static int run_plan(ig_handle* h, int n_steps, GridN grid_n, ig_cycle_step* out) {
+// one step of the plan in h->cyc_in enqueued on the handle's stream (CUDA-graph replay); grid_n = number of candidate
+// slots the step's grid is built for
+static int enqueue_plan_step(ig_handle* h, int grid_n) {
+    const int full = (!h->incr_valid || (h->refresh_every > 0 && h->steps_since_full >= h->refresh_every)) ? 1 : 0;
+    cudaGraphExec_t ge = nullptr;
+    if (h->use_graph) get_graph(h, full, &ge, 1, grid_n);
+    if (ge) { CK(cudaGraphLaunch(ge, h->stream)); }
+    else if (enqueue_step(h, full, grid_n, 1)) return -2;
+    h->steps_since_full = full ? 1 : h->steps_since_full + 1;
+    h->n_full += full;
+    h->incr_valid = true;
+    h->n_launches += (full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR) - (h->rigid ? 1 : 0) + (h->prefetch ? 1 : 0) - (h->rows_small ? 1 : 0) + (h->flat ? 1 : 0) + (h->streaming ? 2 : 0);
+    return 0;
+}
+static int begin_plan(ig_handle* h) {
     CK(cudaMemsetAsync(&h->sc->step_idx, 0, sizeof(int), h->stream));
     cudaEventRecord(h->ev[0], h->stream);
-    for (int t = 0; t < n_steps; t++) {
-        const int full = (!h->incr_valid || (h->refresh_every > 0 && h->steps_since_full >= h->refresh_every)) ? 1 : 0;
-        cudaGraphExec_t ge = nullptr;
-        if (h->use_graph) get_graph(h, full, &ge, 1, grid_n(t));
-        if (ge) { CK(cudaGraphLaunch(ge, h->stream)); }
-        else if (enqueue_step(h, full, grid_n(t), 1)) return -2;
-        h->steps_since_full = full ? 1 : h->steps_since_full + 1;
-        h->n_full += full;
-        h->incr_valid = true;
-        h->n_launches += (full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR) - (h->rigid ? 1 : 0) + (h->prefetch ? 1 : 0) - (h->rows_small ? 1 : 0) + (h->flat ? 1 : 0) + (h->streaming ? 2 : 0);
-    }
+    return 0;
+}
+// wait for the n_steps enqueued steps and convert their device records
+static int collect_plan(ig_handle* h, int n_steps, ig_cycle_step* out) {
     cudaEventRecord(h->ev[1], h->stream);
     std::vector<CycleOut> res(n_steps);
     std::vector<int> plan((size_t)n_steps * (2 + IG_MAX_CANDS));
+    int overflow = 0;
     CK(cudaMemcpyAsync(res.data(), h->cyc_out, sizeof(CycleOut) * n_steps, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(plan.data(), h->cyc_in, plan.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&overflow, &h->sc->list_overflow, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->coords_fresh = false; h->coords_ever = true;
+    h->pending_steps = 0;
+    if (overflow) { h->err = "pick list of the streaming scoring path overflowed (IG_PICK_CAP)"; return -4; }
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->ms_step += ms;
     h->n_steps += n_steps;
@@ -828,6 +888,12 @@ static int run_plan(ig_handle* h, int n_steps, GridN grid_n, ig_cycle_step* out)
         for (int i = 0; i < pl[0]; i++) o.n_proposals += r.n_uniq[i];
     }
     return 0;
+}
+template <class GridN>
+static int run_plan(ig_handle* h, int n_steps, GridN grid_n, ig_cycle_step* out) {
+    if (begin_plan(h)) return -2;
+    for (int t = 0; t < n_steps; t++) if (int rc = enqueue_plan_step(h, grid_n(t))) return rc;
+    return collect_plan(h, n_steps, out);
 }
 
 extern "C" int ig_run_cycle(ig_handle* h, int32_t n_steps, const int32_t* frags, const int32_t* cands8, const int32_t* n_cands,
@@ -858,38 +924,85 @@ extern "C" int ig_set_neighbour_weights(ig_handle* h, const int64_t* ptr, const 
     if (use(h)) return -1;
     if (!ptr || !n_nonzero) { h->err = "ig_set_neighbour_weights: null argument"; return -1; }
     const size_t n = (size_t)ptr[h->nf];
-    for (void* q : {(void*)h->nb_ptr, (void*)h->nb_idx, (void*)h->nb_cdf, (void*)h->nb_nnz}) if (q) cudaFree(q);
-    h->nb_ptr = nullptr; h->nb_idx = nullptr; h->nb_cdf = nullptr; h->nb_nnz = nullptr;
-    if (dev_alloc(h, &h->nb_ptr, (size_t)h->nf + 1) || dev_alloc(h, &h->nb_idx, n + 1) || dev_alloc(h, &h->nb_cdf, n + 1) ||
-        dev_alloc(h, &h->nb_nnz, (size_t)h->nf)) return -2;
-    CK(cudaMemcpy(h->nb_ptr, ptr, sizeof(long long) * ((size_t)h->nf + 1), cudaMemcpyHostToDevice));
+    LevelBlock* L = h->lvl;
+    CK(cudaDeviceSynchronize());   // chains sharing the level may still be drawing from the old arrays
+    for (void* q : {(void*)L->nb_ptr, (void*)L->nb_idx, (void*)L->nb_cdf, (void*)L->nb_nnz}) if (q) cudaFree(q);
+    L->nb_ptr = nullptr; L->nb_idx = nullptr; L->nb_cdf = nullptr; L->nb_nnz = nullptr;
+    if (dev_alloc(h, &L->nb_ptr, (size_t)h->nf + 1) || dev_alloc(h, &L->nb_idx, n + 1) || dev_alloc(h, &L->nb_cdf, n + 1) ||
+        dev_alloc(h, &L->nb_nnz, (size_t)h->nf)) return -2;
+    CK(cudaMemcpy(L->nb_ptr, ptr, sizeof(long long) * ((size_t)h->nf + 1), cudaMemcpyHostToDevice));
     if (n) {
-        CK(cudaMemcpy(h->nb_idx, idx, sizeof(int) * n, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(h->nb_cdf, cdf, sizeof(double) * n, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(L->nb_idx, idx, sizeof(int) * n, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(L->nb_cdf, cdf, sizeof(double) * n, cudaMemcpyHostToDevice));
     }
-    CK(cudaMemcpy(h->nb_nnz, n_nonzero, sizeof(int) * (size_t)h->nf, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(L->nb_nnz, n_nonzero, sizeof(int) * (size_t)h->nf, cudaMemcpyHostToDevice));
     return 0;
 }
 
 // One sweep of step_sampler over `frags` with the neighbour draws made ON THE DEVICE (Philox4x32-10 keyed by
 // (seed, cycle, step, draw)): the host uploads the visiting order, one kernel draws every step's candidates,
 // then the steps replay without host synchronisation.  Needs ig_set_neighbour_weights.
-extern "C" int ig_run_cycle_device(ig_handle* h, int32_t n_steps, const int32_t* frags, int32_t n_neighbours, uint64_t seed,
-                                   uint32_t cycle, ig_cycle_step* out) {
-    if (use(h)) return -1;
+static int prepare_device_plan(ig_handle* h, int32_t n_steps, const int32_t* frags, int32_t n_neighbours, uint64_t seed, uint32_t cycle) {
     if (!h->params_set) { h->err = "ig_run_cycle_device: parameters not set"; return -1; }
-    if (!h->nb_ptr) { h->err = "ig_run_cycle_device: neighbour weights not set (ig_set_neighbour_weights)"; return -1; }
+    if (!h->lvl->nb_ptr) { h->err = "ig_run_cycle_device: neighbour weights not set (ig_set_neighbour_weights)"; return -1; }
     if (n_neighbours <= 0 || n_neighbours > IG_MAX_CANDS) { h->err = "ig_run_cycle_device: n_neighbours out of range"; return -1; }
     if (h->nf < 2) { h->err = "ig_run_cycle_device: needs at least two fragments"; return -1; }
-    if (n_steps <= 0) return 0;
+    if (h->pending_steps) { h->err = "ig_run_cycle_device: an asynchronous cycle is still pending (ig_cycle_wait)"; return -1; }
     for (int t = 0; t < n_steps; t++) if (frags[t] < 0 || frags[t] >= h->nf) { h->err = "ig_run_cycle_device: fragment out of range"; return -1; }
     if (cycle_buffers(h, n_steps)) return -2;
     CK(cudaMemcpyAsync(h->cyc_frags, frags, sizeof(int) * (size_t)n_steps, cudaMemcpyHostToDevice, h->stream));
-    k_draw_plan<<<(n_steps + 127) / 128, 128, 0, h->stream>>>(h->cyc_in, h->cyc_frags, n_steps, n_neighbours, h->nf, h->nb_ptr, h->nb_idx,
-                                                            h->nb_cdf, h->nb_nnz, (unsigned)(seed & 0xffffffffu), (unsigned)(seed >> 32), cycle);
+    k_draw_plan<<<(n_steps + 127) / 128, 128, 0, h->stream>>>(h->cyc_in, h->cyc_frags, n_steps, n_neighbours, h->nf, h->lvl->nb_ptr, h->lvl->nb_idx,
+                                                            h->lvl->nb_cdf, h->lvl->nb_nnz, (unsigned)(seed & 0xffffffffu), (unsigned)(seed >> 32), cycle);
     if (launch_ok(h, "draw_plan")) return -2;
     h->n_launches += 1;
+    return 0;
+}
+extern "C" int ig_run_cycle_device(ig_handle* h, int32_t n_steps, const int32_t* frags, int32_t n_neighbours, uint64_t seed,
+                                   uint32_t cycle, ig_cycle_step* out) {
+    if (use(h)) return -1;
+    if (n_steps <= 0) return 0;
+    if (int rc = prepare_device_plan(h, n_steps, frags, n_neighbours, seed, cycle)) return rc;
     return run_plan(h, n_steps, [&](int) { return (int)n_neighbours; }, out);
+}
+
+// Several chains of ONE device advanced together (replica chains, ig_clone): the same as one ig_run_cycle_device call per
+// chain, but the steps are enqueued round-robin on the chains' own streams before anything is waited for, so the GPU runs
+// them side by side -- a yeast-scale chain keeps a B200 under 25 % busy, eight of them fill it.  frags = [n_chains][n_steps]
+// (each chain's visiting order), seeds = [n_chains], out = [n_chains][n_steps].  Every chain's trajectory is bit-identical
+// to what ig_run_cycle_device gives it alone (tests/test_gpu_parity.py).
+extern "C" int ig_run_cycles_device_multi(ig_handle** hs, int32_t n_chains, int32_t n_steps, const int32_t* frags, int32_t n_neighbours,
+                                          const uint64_t* seeds, uint32_t cycle, ig_cycle_step* out) {
+    if (!hs || n_chains <= 0) { g_err = "ig_run_cycles_device_multi: no chains"; return -1; }
+    if (n_steps <= 0) return 0;
+    for (int c = 0; c < n_chains; c++) {
+        ig_handle* h = hs[c];
+        if (use(h)) return -1;
+        if (int rc = prepare_device_plan(h, n_steps, frags + (size_t)c * n_steps, n_neighbours, seeds[c], cycle)) { g_err = h->err; return rc; }
+        if (begin_plan(h)) return -2;
+    }
+    for (int t = 0; t < n_steps; t++)
+        for (int c = 0; c < n_chains; c++)
+            if (int rc = enqueue_plan_step(hs[c], n_neighbours)) { g_err = hs[c]->err; return rc; }
+    int rc_all = 0;
+    for (int c = 0; c < n_chains; c++)
+        if (int rc = collect_plan(hs[c], n_steps, out + (size_t)c * n_steps)) { g_err = hs[c]->err; rc_all = rc; }
+    return rc_all;
+}
+// Asynchronous form for callers that drive the chains themselves: enqueue now, collect later.
+extern "C" int ig_run_cycle_device_async(ig_handle* h, int32_t n_steps, const int32_t* frags, int32_t n_neighbours, uint64_t seed, uint32_t cycle) {
+    if (use(h)) return -1;
+    if (n_steps <= 0) return 0;
+    if (int rc = prepare_device_plan(h, n_steps, frags, n_neighbours, seed, cycle)) return rc;
+    if (begin_plan(h)) return -2;
+    for (int t = 0; t < n_steps; t++) if (int rc = enqueue_plan_step(h, n_neighbours)) return rc;
+    h->pending_steps = n_steps;
+    return 0;
+}
+extern "C" int ig_cycle_wait(ig_handle* h, int32_t n_steps, ig_cycle_step* out) {
+    if (use(h)) return -1;
+    if (n_steps != h->pending_steps) { h->err = "ig_cycle_wait: n_steps does not match the pending cycle"; return -1; }
+    if (n_steps <= 0) return 0;
+    return collect_plan(h, n_steps, out);
 }
 
 // download the plan of the last cycle ([n_steps][2 + IG_MAX_CANDS]: n_cands, fragment, candidates) -- tests / logging
@@ -985,7 +1098,7 @@ extern "C" int ig_distance_histogram(ig_handle* h, double bin_kb, double max_kb,
     if (n_bins <= 0 || n_bins > (1 << 16) - 1) { h->err = "ig_distance_histogram: n_bins out of range"; return -1; }
     if (n_rows > h->ns) n_rows = h->ns;
     CK(cudaMemsetAsync(h->d_hist, 0, sizeof(unsigned long long) * (n_bins + 1), h->stream));
-    k_histogram<<<h->n_part_full, IG_THREADS, 0, h->stream>>>(h->row_ptr, h->cv, h->sym_diag, h->init_live, h->sub, n_rows, bin_kb,
+    k_histogram<<<h->n_part_full, IG_THREADS, 0, h->stream>>>(h->row_ptr, h->cv, h->lvl->sym_diag, h->init_live, h->sub, n_rows, bin_kb,
                                                              max_kb, n_bins, h->d_hist, h->d_hist + n_bins);
     if (launch_ok(h, "histogram")) return -2;
     std::vector<unsigned long long> tmp(n_bins + 1);
@@ -998,8 +1111,9 @@ extern "C" int ig_distance_histogram(ig_handle* h, double bin_kb, double max_kb,
 
 extern "C" int ig_set_sym_diag(ig_handle* h, const int32_t* diag) {
     if (use(h)) return -1;
-    if (!h->sym_diag) { if (dev_alloc(h, &h->sym_diag, h->ns)) return -2; }
-    CK(cudaMemcpy(h->sym_diag, diag, sizeof(int) * h->ns, cudaMemcpyHostToDevice));
+    if (!h->lvl->sym_diag) { if (dev_alloc(h, &h->lvl->sym_diag, h->ns)) return -2; }
+    CK(cudaMemcpyAsync(h->lvl->sym_diag, diag, sizeof(int) * h->ns, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
@@ -1161,3 +1275,5 @@ extern "C" int ig_timeline_get(ig_handle* h, int32_t n_steps, uint64_t* out) {
     return -1;
 #endif
 }
+
+#include "ig_replicas.cuh"   // replica chains across GPUs: NCCL all-gather inside the library

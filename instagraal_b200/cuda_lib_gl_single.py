@@ -175,6 +175,7 @@ class sampler:
             "pop out insert @ right or -1", "transloc_1", "transloc_2", "transloc_3", "transloc_4",
             "local_scramble d1", "local_scramble d2", "local_scramble d3", "local_scramble d4"]
         self.setup_distri_frags()
+        self._nb_state = {}   # shared (by reference) with the clones of this chain: neighbour weights uploaded once per level
         # one result record per handle, read through NumPy views (no per-step ctypes -> list conversions)
         self._res = L.ig_step_result()
         self._res_scores = np.frombuffer(self._res, dtype=np.float64, count=L.IG_MAX_CANDS * L.IG_N_OPS,
@@ -185,6 +186,33 @@ class sampler:
         self._cand_ptr = _ptr(self._cand_buf)
         self._res_ref = C.byref(self._res)
         self._ig_step = L.lib().ig_step
+
+    @classmethod
+    def clone_of(cls, other):
+        """A further chain on the same level and GPU (ig_clone): shares the contacts / sub-fragment table / neighbour
+        weights of ``other`` in device memory; own scaffold (starting from the level's initial one), own RNG-free state.
+        Parameters are copied from ``other``."""
+        import copy
+        s = copy.copy(other)   # host-side attributes (level arrays, neighbour pmfs) are shared read-only
+        h = C.c_void_p()
+        L.check(other._h, L.lib().ig_clone(other._h, C.byref(h)), "ig_clone")
+        s._h = h
+        s.gpu_vect_frags = _VectFrags(s, other.S_o_A_frags)
+        s.candidates = []
+        s.all_scores = np.zeros(0)
+        s.n_proposals_scored = 0
+        s.likelihood_t = None
+        s._res = L.ig_step_result()
+        s._res_scores = np.frombuffer(s._res, dtype=np.float64, count=L.IG_MAX_CANDS * L.IG_N_OPS, offset=L.ig_step_result.scores.offset)
+        s._res_nuniq = np.frombuffer(s._res, dtype=np.int32, count=L.IG_MAX_CANDS, offset=L.ig_step_result.n_uniq.offset)
+        s._res_nsub = np.frombuffer(s._res, dtype=np.int32, count=L.IG_MAX_CANDS, offset=L.ig_step_result.n_sub.offset)
+        s._cand_buf = np.zeros(L.IG_MAX_CANDS, dtype=np.int32)
+        s._cand_ptr = _ptr(s._cand_buf)
+        s._res_ref = C.byref(s._res)
+        if other.param_simu is not None:
+            s.set_param_simu(np.array(list(other.param_simu[0]), dtype=np.float32))
+            s.param_simu_test = s.param_simu
+        return s
 
     # ------------------------------------------------------------------ state plumbing
     def _get_state(self):
@@ -414,23 +442,30 @@ class sampler:
         """Production RNG mode: like run_cycle, but every step's neighbours are drawn ON THE DEVICE (Philox4x32-10
         keyed by (seed, cycle, step, draw); same distribution as return_neighbours, a different random stream than
         NumPy's).  The host only provides the visiting order (np.random.shuffle in full_em, IG:213)."""
-        if not getattr(self, "_nb_uploaded", False):
-            ptr, idx, cdf, nnz = self.neighbour_weights_csr()
-            L.check(self._h, L.lib().ig_set_neighbour_weights(self._h, _ptr(ptr), _ptr(idx), _ptr(cdf), _ptr(nnz)),
-                    "ig_set_neighbour_weights")
-            self._nb_uploaded = True
+        self._upload_neighbour_weights()
         n = len(list_frags)
         frags = np.ascontiguousarray(list_frags, dtype=np.int32)
         out = np.zeros(n, dtype=L.CYCLE_DTYPE)
         L.check(self._h, L.lib().ig_run_cycle_device(self._h, n, _ptr(frags), int(n_neighbours), int(seed), int(cycle), _ptr(out)),
                 "ig_run_cycle_device")
-        if n:
+        self._after_cycle(out)
+        return out
+
+    def _upload_neighbour_weights(self):
+        """setup_distri_frags (CL:3053-3101) to the device once per level (shared by the chains cloned from this one)"""
+        if not self._nb_state.get("uploaded", False):
+            ptr, idx, cdf, nnz = self.neighbour_weights_csr()
+            L.check(self._h, L.lib().ig_set_neighbour_weights(self._h, _ptr(ptr), _ptr(idx), _ptr(cdf), _ptr(nnz)),
+                    "ig_set_neighbour_weights")
+            self._nb_state["uploaded"] = True
+
+    def _after_cycle(self, out):
+        if len(out):
             last = out[-1]
             self.n_contigs = np.int32(last["n_contigs"])
             self.mean_length_contigs = np.float32(last["sum_l_cont"]) / np.float32(last["n_contigs"])
             self.likelihood_t = self.o = np.float64(last["likelihood"])
             self.n_proposals_scored += int(out["n_proposals"].sum())
-        return out
 
     def last_cycle_plan(self, n_steps):
         """(n_cands, fragment, candidates[8]) per step of the last run_cycle / run_cycle_device call."""

@@ -1,74 +1,104 @@
-"""Replica chains across GPUs (a single chain is sequential, so the only natural
-sharding is independent chains / tempering replicas, one or more per GPU).
+"""Replica chains (a single chain is sequential, so the only natural sharding of the 8 x B200 box is
+independent chains with different seeds, one or more per GPU).
 
-One process per GPU (torchrun); each process owns one ``sampler`` (one chain).  Every
-``gather_every`` steps the chains all-gather {likelihood, n_contigs, temperature, live scaffold}
-over NCCL (NVLink/NVSwitch) -- ~64 B x NF per chain, latency-bound -- and every rank takes the same
-deterministic decisions from the gathered table (best chain; optional replica-exchange swaps).
-torch.distributed is plumbing only; the data path has no other collective.
+``ReplicaSet`` owns the chains of ONE process / GPU: the first one is a normal ``sampler`` (uploads the level), the others
+are ``ig_clone``s that share its contacts in device memory.  ``run_cycle`` advances all of them together
+(``ig_run_cycles_device_multi``: steps enqueued round-robin on the chains' streams, so a GPU that one yeast-scale chain
+keeps < 25 % busy is filled by eight); ``allgather`` is the per-cycle exchange of {likelihood, n_contigs, live scaffold}
+across the GPUs: ``ncclAllGather`` INSIDE the library, straight from device memory over NVLink (``ig_allgather_best``).
+No PyTorch here: the launcher only has to hand every rank the 128-byte NCCL id created by rank 0
+(``nccl_unique_id`` -> file / environment / any broadcast).
+The live path of the reference has no temperature (fragment moves are an argmax, CL:1435-1446), so the chains differ by
+their seeds only; every rank takes the same decision (best chain) from the gathered table.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 
-
-class _DevBuf:
-    """Expose a raw device pointer (the handle's live scaffold) through __cuda_array_interface__."""
-
-    def __init__(self, ptr, n_int32):
-        self.__cuda_array_interface__ = {"shape": (int(n_int32),), "typestr": "<i4", "data": (int(ptr), False),
-                                         "version": 2, "strides": None}
+from . import _lib as L
 
 
 def best_chain(likelihoods):
-    """Deterministic on every rank: highest likelihood, lowest rank on ties."""
+    """Deterministic on every rank: highest likelihood, lowest global chain index on ties (what ig_allgather_best returns)."""
     lik = np.asarray(likelihoods, dtype=np.float64)
     return int(np.flatnonzero(lik == lik.max())[0])
 
 
-def exchange_pairs(likelihoods, temperatures, sweep, u):
-    """Replica-exchange (parallel tempering) decisions for neighbouring temperature pairs
-    (even pairs on even sweeps, odd pairs on odd sweeps), Metropolis on
-    (1/T_i - 1/T_j) * (L_j - L_i) with the shared uniform draws ``u`` -- identical on every rank."""
-    lik = np.asarray(likelihoods, dtype=np.float64)
-    T = np.asarray(temperatures, dtype=np.float64)
-    order = np.argsort(T, kind="stable")
-    swaps = []
-    for k in range(sweep % 2, len(order) - 1, 2):
-        i, j = int(order[k]), int(order[k + 1])
-        log_r = (1.0 / T[i] - 1.0 / T[j]) * (lik[j] - lik[i])
-        if np.log(max(u[k], 1e-300)) < log_r:
-            swaps.append((i, j))
-    return swaps
+def nccl_unique_id():
+    """128-byte id for ncclCommInitRank (call on rank 0, distribute to the other ranks)."""
+    buf = (C.c_char * 128)()
+    L.check(None, L.lib().ig_nccl_unique_id(buf), "ig_nccl_unique_id")
+    return bytes(buf)
 
 
-class ReplicaExchange:
-    def __init__(self, sampler, dist, device, temperature=1.0, state_fn=None):
-        import torch
-        self.torch = torch
-        self.s = sampler
-        self.dist = dist
-        self.device = device
-        self.world = dist.get_world_size()
-        self.rank = dist.get_rank()
-        self.temperature = float(temperature)
-        self.state_fn = state_fn or self._device_state
-        n = self.state_fn().numel()
-        self.all_states = torch.empty((self.world, n), dtype=torch.int32, device=device)
-        self.all_meta = torch.empty((self.world, 3), dtype=torch.float64, device=device)
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class ReplicaSet:
+    def __init__(self, first_sampler, n_chains, seeds=None):
+        """first_sampler: a constructed ``sampler`` (parameters already set); n_chains - 1 clones are made from it."""
+        from .cuda_lib_gl_single import sampler
+        self.chains = [first_sampler] + [sampler.clone_of(first_sampler) for _ in range(n_chains - 1)]
+        self.n = n_chains
+        self.seeds = np.ascontiguousarray(seeds if seeds is not None else np.arange(n_chains), dtype=np.uint64)
+        self._handles = (C.c_void_p * n_chains)(*[c._h for c in self.chains])
+        self.rank, self.n_ranks = 0, 1
+        self._nccl = False
+        self.nf = int(first_sampler.n_new_frags)
+        self.gather_ms = 0.0
         self.n_gathers = 0
 
-    def _device_state(self):
-        ptr, nbytes = self.s.device_state()
-        return self.torch.as_tensor(_DevBuf(ptr, nbytes // 4), device=self.device)
+    def init_comm(self, rank=0, n_ranks=1, nccl_id=None):
+        lead = self.chains[0]
+        idbuf = C.create_string_buffer(nccl_id, 128) if nccl_id is not None else None
+        L.check(lead._h, L.lib().ig_nccl_init(lead._h, int(rank), int(n_ranks), self.n, idbuf), "ig_nccl_init")
+        self.rank, self.n_ranks, self._nccl = int(rank), int(n_ranks), True
+
+    def bomb(self, seed0=0):
+        for i, c in enumerate(self.chains):
+            np.random.seed(int(seed0) + i)
+            c.bomb_the_genome()
+
+    def run_cycle(self, frags_per_chain, n_neighbours=5, cycle=0):
+        """frags_per_chain: int32[n_chains, n_steps] visiting orders.  Returns the structured per-step records
+        [n_chains, n_steps] (same fields as sampler.run_cycle_device)."""
+        frags = np.ascontiguousarray(frags_per_chain, dtype=np.int32)
+        assert frags.ndim == 2 and frags.shape[0] == self.n
+        for c in self.chains:
+            c._upload_neighbour_weights()
+        n_steps = frags.shape[1]
+        out = np.zeros((self.n, n_steps), dtype=L.CYCLE_DTYPE)
+        rc = L.lib().ig_run_cycles_device_multi(self._handles, self.n, n_steps, _ptr(frags), int(n_neighbours), _ptr(self.seeds),
+                                                int(cycle), _ptr(out))
+        L.check(None, rc, "ig_run_cycles_device_multi")
+        for i, c in enumerate(self.chains):
+            c._after_cycle(out[i])
+        return out
 
     def allgather(self):
-        """Returns (best rank, likelihoods[world], n_contigs[world]); all_states holds every chain's scaffold."""
-        t = self.torch
-        lik = float(self.s.likelihood_t) if self.s.likelihood_t is not None else float("-inf")
-        meta = t.tensor([lik, float(self.s.n_contigs or 0), self.temperature], dtype=t.float64, device=self.device)
-        self.dist.all_gather([self.all_meta[i] for i in range(self.world)], meta)
-        self.dist.all_gather([self.all_states[i] for i in range(self.world)], self.state_fn().contiguous())
-        m = self.all_meta.cpu().numpy()
+        """-> (best global chain index, likelihood[n_ranks * n], n_contigs[n_ranks * n]); device ms accumulated in gather_ms"""
+        if not self._nccl:
+            self.init_comm()
+        n_all = self.n_ranks * self.n
+        lik = np.zeros(n_all, dtype=np.float64)
+        nc = np.zeros(n_all, dtype=np.int32)
+        best, ms = C.c_int32(0), C.c_float(0.0)
+        lead = self.chains[0]
+        L.check(lead._h, L.lib().ig_allgather_best(lead._h, self._handles, self.n, _ptr(lik), _ptr(nc), C.byref(best), C.byref(ms)),
+                "ig_allgather_best")
+        self.gather_ms += float(ms.value)
         self.n_gathers += 1
-        return best_chain(m[:, 0]), m[:, 0].copy(), m[:, 1].astype(np.int64)
+        return int(best.value), lik, nc
+
+    def gathered_state(self, index):
+        out = np.zeros((13, self.nf), dtype=np.int32)
+        lead = self.chains[0]
+        L.check(lead._h, L.lib().ig_get_gathered_state(lead._h, int(index), _ptr(out)), "ig_get_gathered_state")
+        return out
+
+    def free(self):
+        for c in reversed(self.chains):
+            c.free_gpu()

@@ -1,21 +1,25 @@
-"""Host-side replica logic over torch.distributed with the gloo backend, world_size 2, on CPU."""
+"""Host-side replica logic, world_size 2, on CPU.  The collective of the product is ncclAllGather inside the library
+(ig_allgather_best; GPU tests in test_gpu_replicas.py); what can be checked without a GPU is the launcher-side contract:
+  * every rank derives the same decision (best chain) from the same gathered table (best_chain),
+  * the chain -> (rank, local index) layout is rank-major with n_local chains per rank,
+  * a 128-byte id created by one rank reaches the others unchanged (here over torch.distributed/gloo, which is what
+    bench.py uses for that one broadcast).
+"""
 import os
 import socket
 
 import numpy as np
-import pytest
 
-from instagraal_b200.replicas import ReplicaExchange, best_chain, exchange_pairs
+from instagraal_b200.replicas import best_chain
 
 
-def test_best_chain_and_exchange_are_deterministic():
+def test_best_chain_is_deterministic():
     assert best_chain([-5.0, -3.0, -3.0, -9.0]) == 1
-    sw = exchange_pairs([-10.0, -2.0, -8.0, -1.0], [1.0, 1.3, 1.6, 2.0], 0, np.zeros(4) + 1e-9)
-    assert sw == [(0, 1), (2, 3)]
-    assert exchange_pairs([-1.0, -2.0], [1.0, 2.0], 0, np.ones(2)) == []
+    assert best_chain([-1.0]) == 0
+    assert best_chain(np.array([-2.0, -2.0])) == 0
 
 
-def test_allgather_world_size_2_gloo():
+def test_launcher_contract_world_size_2_gloo():
     import json
     import subprocess
     import sys
@@ -32,5 +36,8 @@ def test_allgather_world_size_2_gloo():
         assert p.returncode == 0, out[-2000:]
         line = [ln for ln in out.splitlines() if ln.startswith("RESULT ")][-1]
         res.append(json.loads(line[7:]))
-    for rank, best, liks, ncs, first in sorted(res):
-        assert best == 1 and liks == [-100.0, -90.0] and ncs == [7, 8] and first == [0, 1000]
+    assert len(res) == 2
+    for rank, best, liks, id_sum in sorted(res):
+        assert best == 5                       # chain 1 of rank 1 (rank-major, 4 chains per rank)
+        assert liks == [-100.0, -99.0, -98.0, -97.0, -90.0, -10.0, -88.0, -87.0]
+        assert id_sum == sum(range(128))       # the id created by rank 0 arrived intact
