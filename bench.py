@@ -32,6 +32,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+DEFAULT_MODE = "exact"
 
 def params_for(level):
     from instagraal_b200.synth import workload_params
@@ -91,37 +92,137 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def measured_traffic(workload, kernel):
-    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the
-    committed `ncu --set full` capture of the same workload (profiles/r1_ncu_*.txt), or None."""
-    table = {("T", "k_score"): 1.300992e6 + 0.255232e6,             # profiles/r1_ncu_k_eval_flat_T.txt + r1_ncu_k_pick_T.txt
-             ("G", "k_score"): 171.874048e6 + 9.34016e6,            # profiles/r1_ncu_k_score_G.txt (fully assembled start)
-             ("G", "k_full_lnz"): 679.342336e6 + 4.3264e6}          # profiles/r1_ncu_k_full_lnz_G.txt
-    return table.get((workload, kernel))
+def measured_traffic(workload, kernel, mode):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture of
+    this workload (profiles/r2_traffic.json, written by scripts/ncu_traffic.py from the .ncu-rep), or None."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    try:
+        return json.load(open(p)).get("%s/%s/%s" % (workload, mode, kernel))
+    except Exception:
+        return None
+
+
+def measure_l2_peak(torch, dev):
+    """L2-resident streaming bandwidth of this box: device copy of a 24 MiB buffer (48 MiB footprint << 126 MB L2),
+    read + write bytes, best of 20, CUDA events.  The roofline denominator of the workloads whose contacts fit the L2."""
+    n = 24 << 20
+    a = torch.empty(n, dtype=torch.uint8, device=dev).fill_(1)
+    b = torch.empty_like(a)
+    for _ in range(5):
+        b.copy_(a)
+    best = 1e9
+    for _ in range(20):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            b.copy_(a)
+        e1.record()
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1) / 10.0)
+    return 2.0 * n / (best * 1e-3) / 1e9
 
 
 def build_level(name):
-    from instagraal_b200.synth import WORKLOADS, make_level, make_workload
+    from instagraal_b200.synth import make_workload
     t0 = time.time()
     level = make_workload(name)
     return level, time.time() - t0
 
 
-def burn_in(s, level, n_cycles, seed):
-    """bomb + n_cycles of MCMC so the timed region runs in the assembled (expensive) regime."""
-    np.random.seed(seed)
-    s.bomb_the_genome()
-    frs = np.arange(level.n_frags)
+def frag_orders(level, n_chains, n_steps, seed):
+    rng = np.random.RandomState(seed)
+    out = np.empty((n_chains, n_steps), dtype=np.int32)
+    for c in range(n_chains):
+        v = []
+        while len(v) < n_steps:
+            v.extend(rng.permutation(level.n_frags).tolist())
+        out[c] = v[:n_steps]
+    return out
+
+
+def nuis_stats(s, reset=True):
+    import ctypes as C
+    from instagraal_b200 import _lib as L
+    o = np.zeros(2)
+    L.lib().ig_get_nuisance_stats(s._h, o.ctypes.data_as(C.c_void_p), int(reset))
+    return float(o[0]), int(o[1])
+
+
+def single_chain_passes(s, level, args, torch, flush, rank):
+    """C4: one chain on one GPU.  Returns the dict of measurements (device-timed steps, per-kernel profile, e2e through
+    step_sampler, the same with the nuisance step interleaved as full_em does from cycle 5 on)."""
     dt = np.float32(0.01)
-    for _ in range(n_cycles):
-        np.random.shuffle(frs)
-        for f in frs:
-            s.step_sampler(int(f), 5, dt)
+    frs = np.arange(level.n_frags)
+    rng = np.random.RandomState(7 + rank)
+
+    def frag_stream(n):
+        out = []
+        while len(out) < n:
+            rng.shuffle(frs)
+            out.extend(int(f) for f in frs)
+        return out[:n]
+
+    def step_loop(n, nuisance=False, flushing=True):
+        for i, f in enumerate(frag_stream(n)):
+            if flush is not None and flushing:
+                flush.fill_(i & 0xFF)
+                torch.cuda.current_stream().synchronize()   # the flush runs on torch's stream, the step on the library's
+            s.step_sampler(f, 5, dt)
+            if nuisance:
+                s.step_nuisance_parameters(dt, i, n)
+
+    res = {}
+    # ---- pass 1: device-timed (value of the single-chain configuration)
+    step_loop(args.warmup)
+    s.set_options(refresh_every=args.refresh_every, use_graph=bool(args.graph))
+    s.get_stats(reset=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    step_loop(args.steps)
+    torch.cuda.synchronize()
+    res["wall_s"] = time.perf_counter() - t0
+    st = s.get_stats(reset=True)
+    res["dev_ms"], res["proposals"], res["launches"], res["full_refreshes"] = st["ms_step"], st["proposals"], st["launches"], st["full_refreshes"]
+    # ---- pass 1b: per-kernel CUDA-event timing for the roofline (profiling on => direct launches, no graph)
+    s.set_profiling(True)
+    n_prof = min(args.steps, 500)
+    step_loop(n_prof)
+    res["prof"] = s.get_stats(reset=True)
+    res["ktimes"] = s.get_kernel_times(reset=True)
+    res["n_prof"] = n_prof
+    s.set_profiling(False)
+    # ---- pass 2: end to end through the facade (host RNG + ctypes + H2D/D2H), wall clock, no flush (production)
+    torch.cuda.synchronize()
+    np.random.seed(99 + rank)
+    t0 = time.perf_counter()
+    step_loop(args.steps, flushing=False)
+    torch.cuda.synchronize()
+    res["t_e2e"] = time.perf_counter() - t0
+    res["prop_e2e"] = s.get_stats(reset=True)["proposals"]
+    # ---- pass 3: the same with step_nuisance_parameters after every step (IG:242-252, cycles > 4 of a real run)
+    s.param_simu_test = s.param_simu
+    p_keep = np.array(list(s.param_simu[0]), dtype=np.float32)
+    nuis_stats(s)
+    n_nuis = min(args.steps, args.nuisance_steps)
+    np.random.seed(299 + rank)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    step_loop(n_nuis, nuisance=True, flushing=False)
+    torch.cuda.synchronize()
+    res["t_nuis"] = time.perf_counter() - t0
+    stn = s.get_stats(reset=True)
+    res["prop_nuis"], res["dev_ms_nuis_steps"] = stn["proposals"], stn["ms_step"]
+    res["nuis_dev_ms"], res["nuis_calls"] = nuis_stats(s)
+    res["n_nuis"] = n_nuis
+    s.set_param_simu(p_keep)   # the random walk of the nuisance parameters must not leak into the next passes
+    s.param_simu_test = s.param_simu
+    return res
 
 
 def run_ours(args):
-    import torch  # plumbing only: L2 flush buffer, NCCL all-gather of replica states
+    import torch  # plumbing only: L2 flush buffer, barriers / reductions of the timing numbers, broadcast of the NCCL id
     from instagraal_b200.cuda_lib_gl_single import sampler
+    from instagraal_b200.replicas import ReplicaSet, nccl_unique_id
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -138,192 +239,193 @@ def run_ours(args):
 
     level, t_gen = build_level(args.workload)
     p8 = params_for(level)
-    s = sampler(*level.sampler_args(), device=local, rigid_pruning=bool(args.rigid_pruning))
+    mode = args.mode
+    s = sampler(*level.sampler_args(), device=local, rigid_pruning={"exact": 0, "rigid": 1}[mode])
     s.set_param_simu(p8)
-    burn = args.burn_cycles if args.burn_cycles >= 0 else (2 if level.n_frags <= 5000 else 0)
+    big = level.sparse_matrix.nnz * 8 > 126e6
+    burn = args.burn_cycles if args.burn_cycles >= 0 else 2
     t0 = time.time()
-    if args.start == "true":  # fully assembled regime without burn-in: one contig per true chromosome
-        burn = 0
-        np.random.seed(1000 + rank)
-        s._set_state(level.true_state())
-    elif burn > 0:
-        burn_in(s, level, burn, 1000 + rank)
-    else:
-        np.random.seed(1000 + rank)
-        if args.bomb:
-            s.bomb_the_genome()
+
+    def burnt_state():
+        """bomb + `burn` cycles of MCMC (device RNG cycle API): the mid-assembly regime a run spends its time in"""
+        np.random.seed(1000)
+        s.bomb_the_genome()
+        frs = np.arange(level.n_frags)
+        for c in range(burn):
+            np.random.shuffle(frs)
+            s.run_cycle_device(frs, 5, seed=1000, cycle=c)
+        return s._get_state()
+
+    st_mid = burnt_state() if args.start in ("bomb", "both") else None
     t_burn = time.time() - t0
-    st_burn = s._get_state()
-    n_contigs0 = int((st_burn[0] == 0).sum())
+    st_true = level.true_state() if args.start in ("true", "both") else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if (args.flush_l2 and not big) else None
 
-    from instagraal_b200.replicas import ReplicaExchange
-    xchg = ReplicaExchange(s, dist, dev) if world > 1 else None
+    # ---------------- single chain (C2/C3/C4), on rank 0's GPU only when N > 1 is not needed: every rank measures its own
+    single = {}
+    if world == 1:
+        for name, st0 in (("mid", st_mid), ("assembled", st_true)):
+            if st0 is None:
+                continue
+            s._set_state(st0)
+            np.random.seed(1000 + rank)
+            single[name] = single_chain_passes(s, level, args, torch, flush, rank)
+            single[name]["n_contigs_at_start"] = int((st0[0] == 0).sum())
+    st_start = st_mid if st_mid is not None else st_true
+    start_name = "mid" if st_mid is not None else "assembled"
 
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if args.flush_l2 else None
-    dt = np.float32(0.01)
-    frs = np.arange(level.n_frags)
-    rng = np.random.RandomState(7 + rank)
-
-    def frag_stream(n):
-        out = []
-        while len(out) < n:
-            rng.shuffle(frs)
-            out.extend(int(f) for f in frs)
-        return out[:n]
-
-    # ---------------- pass 1: device-timed (value, roofline)
-    for f in frag_stream(args.warmup):
-        s.step_sampler(f, 5, dt)
-    s.set_options(refresh_every=args.refresh_every, use_graph=bool(args.graph))
-    s.get_stats(reset=True)
+    # ---------------- replica chains (C5): `--chains` in total, chains / N per GPU, all-gather every gather_every steps
+    n_total = args.chains
+    n_local = max(1, n_total // world)
+    rs = ReplicaSet(s, n_local, seeds=np.arange(rank * n_local, (rank + 1) * n_local, dtype=np.uint64) + 1)
+    for c in rs.chains:
+        c._set_state(st_start)
+        c.set_options(refresh_every=args.refresh_every, use_graph=True)
+    nid = None
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt = torch.tensor(list(nccl_unique_id()), dtype=torch.uint8, device=dev)
+        dist.broadcast(idt, 0)
+        nid = bytes(idt.cpu().tolist())
+    rs.init_comm(rank, world, nid)
+    seg = max(1, args.gather_every if args.gather_every > 0 else args.steps // 4)
+    warm = frag_orders(level, n_local, min(args.warmup, 200), 5 + rank)
+    rs.run_cycle(warm, 5, cycle=100)
+    rs.allgather()
+    for c in rs.chains:
+        c.get_stats(reset=True)
+    rs.gather_ms, rs.n_gathers = 0.0, 0
+    orders = frag_orders(level, n_local, args.steps, 50 + rank)
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
+    dev_ms_multi, prop_multi, launches = 0.0, 0.0, 0
     with ClockSampler(local) as clk:
         t_wall0 = time.perf_counter()
-        for i, f in enumerate(frag_stream(args.steps)):
-            if flush is not None:
-                flush.fill_(i & 0xFF)
-                torch.cuda.current_stream().synchronize()   # the flush runs on torch's stream, the step on the library's:
-                                                            # it must be over (and stays untimed) before the step starts
-            s.step_sampler(f, 5, dt)
-            if xchg is not None and (i + 1) % args.gather_every == 0:
-                xchg.allgather()
+        for a in range(0, args.steps, seg):
+            out = rs.run_cycle(orders[:, a:a + seg], 5, cycle=200 + a)
+            sts = [c.get_stats(reset=True) for c in rs.chains]
+            dev_ms_multi += max(x["ms_step"] for x in sts)      # the chains of one GPU start together: the slowest one
+            prop_multi += float(out["n_proposals"].sum())
+            launches += int(sum(x["launches"] for x in sts))
+            best, lik, nc = rs.allgather()
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
-        t_wall = time.perf_counter() - t_wall0
-    st = s.get_stats(reset=True)
-    dev_ms = st["ms_step"]
-    proposals = st["proposals"]
+        t_wall_multi = time.perf_counter() - t_wall0
+    dev_ms_multi += rs.gather_ms
+    launches += 3 * n_local * rs.n_gathers
 
-    # ---------------- pass 1b: per-kernel CUDA-event timing for the roofline (profiling on => no graph)
-    s.set_profiling(True)
-    n_prof = min(args.steps, 500)
-    for i, f in enumerate(frag_stream(n_prof)):
-        if flush is not None:
-            flush.fill_(i & 0xFF)
-            torch.cuda.current_stream().synchronize()
-        s.step_sampler(f, 5, dt)
-    stp = s.get_stats(reset=True)
-    ktimes = s.get_kernel_times(reset=True)
-    s.set_profiling(False)
-
-    # ---------------- pass 2: end to end through the facade (host RNG + ctypes + H2D/D2H), wall clock
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    np.random.seed(99 + rank)
-    t0 = time.perf_counter()
-    n_e2e = args.steps
-    for f in frag_stream(n_e2e):
-        s.step_sampler(f, 5, dt)  # candidates drawn by the facade with np.random (reference contract)
-    torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
-    st2 = s.get_stats(reset=True)
-
-    # ---------------- pass 3: the cycle API (one library call per run of steps, no per-step host sync)
-    np.random.seed(199 + rank)
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    cyc = s.run_cycle(frag_stream(args.steps), 5)
-    t_cyc = time.perf_counter() - t0
-    cyc_prop = float(cyc["n_proposals"].sum())
-    st3 = s.get_stats(reset=True)
-
-    # ---------------- pass 4: the same with the neighbour draws made on the device (production RNG mode)
-    s.run_cycle_device(frag_stream(8), 5, seed=7 + rank, cycle=0)   # uploads the neighbour weights, builds graphs
-    s.get_stats(reset=True)
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    cycd = s.run_cycle_device(frag_stream(args.steps), 5, seed=7 + rank, cycle=1)
-    t_cycd = time.perf_counter() - t0
-    cycd_prop = float(cycd["n_proposals"].sum())
-    st4 = s.get_stats(reset=True)
-
-    # ---------------- aggregate over ranks (max time, summed proposals)
-    vals = np.array([dev_ms, proposals, t_e2e, st2["proposals"], t_wall], dtype=np.float64)
+    vals = np.array([dev_ms_multi, prop_multi, t_wall_multi, rs.gather_ms, launches], dtype=np.float64)
     if dist is not None:
         tv = torch.tensor(vals, device=dev)
-        mx = tv.clone()
+        mx, sm = tv.clone(), tv.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = tv.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        dev_ms_max, t_e2e_max, t_wall_max = float(mx[0]), float(mx[2]), float(mx[4])
-        prop_sum, prop2_sum = float(sm[1]), float(sm[3])
+        dev_ms_max, t_wall_max, gather_ms_max = float(mx[0]), float(mx[2]), float(mx[3])
+        prop_sum, launches_sum = float(sm[1]), float(sm[4])
     else:
-        dev_ms_max, t_e2e_max, t_wall_max = dev_ms, t_e2e, t_wall
-        prop_sum, prop2_sum = proposals, st2["proposals"]
-
+        dev_ms_max, t_wall_max, gather_ms_max = dev_ms_multi, t_wall_multi, rs.gather_ms
+        prop_sum, launches_sum = prop_multi, launches
     if rank != 0:
+        rs.free()
         if dist is not None:
             dist.destroy_process_group()
         return
-    value = prop_sum / (dev_ms_max / 1e3)
-    e2e = prop2_sum / t_e2e_max
+
     peak, peak_src = measured_peak()
     nnz, ns = s.n_non_zero, int(s.init_n_sub_frags)
-    n_launch_score = stp["steps"]
-    n_full = max(stp["full_refreshes"], 0)
-    bytes_score = 8 * stp["contacts_read"] + 4 * (stp["rows"] + stp["steps"]) + 16 * stp["rows"] + 32 * stp["frags"]
-    bytes_full = (8 * nnz + 4 * (ns + 1) + 20 * ns) * n_full
-    kern = {"k_score": (stp["ms_score"], bytes_score, n_launch_score), "k_full_lnz": (stp["ms_full"], bytes_full, n_full)}
-    dom = max(kern, key=lambda k: kern[k][0])
-    ach = {k: (b / max(ms, 1e-9) / 1e6) for k, (ms, b, _n) in kern.items()}  # GB/s
+    value = prop_sum / (dev_ms_max / 1e3)
+    e2e_multi = prop_sum / t_wall_max
     out = {
         "metric": "delta-log-L proposals scored per second (MCMC step_sampler, pyramid level 4)",
         "value": value, "unit": "proposals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32 expected contacts / f64 log-likelihood accumulation / int32 scaffold",
         "data": "synthetic", "impl": "ours",
         "config": {"workload": args.workload, "n_frags": level.n_frags, "n_sub_frags": ns, "nnz": nnz,
-                   "chains": world, "n_neighbours": 5, "start": args.start, "burn_in_cycles": burn, "n_contigs_at_start": n_contigs0,
-                   "l2": ("flushed between steps with a 256 MiB write (untimed); timed = sum of per-step CUDA-event "
-                          "intervals" if args.flush_l2 else "not flushed (inputs %s L2)" % (">" if nnz * 8 > 126e6 else "<")),
-                   "full_likelihood": ("recomputed over every contact each step (reference schedule, CL:1409)"
-                                       if args.refresh_every == 1 else
-                                       "maintained incrementally, full recompute every %d steps (same values up to f64 "
-                                       "summation order; tests/test_gpu_parity.py)" % args.refresh_every),
-                   "cuda_graph": bool(args.graph), "rigid_pruning": bool(args.rigid_pruning), "full_refreshes_in_timed_region": st["full_refreshes"],
-                   "gather_every": args.gather_every if world > 1 else None},
+                   "chains": n_local * world, "chains_per_gpu": n_local, "n_neighbours": 5, "mode": mode,
+                   "start": start_name, "burn_in_cycles": burn, "n_contigs_at_start": int((st_start[0] == 0).sum()),
+                   "l2": ("inputs larger than L2 (%.0f MB of contacts), no flush" % (nnz * 8 / 1e6)) if big else
+                         "single-chain passes: flushed between steps with a 256 MiB write (untimed); replica pass: not flushed",
+                   "full_likelihood": "maintained incrementally, full recompute every %d steps" % args.refresh_every,
+                   "gather_every": seg, "timed": "whole job = %d chains x %d steps + %d all-gathers; time = max over GPUs of "
+                                                 "(slowest chain's CUDA-event interval per segment + all-gather events)" % (n_local * world, args.steps, rs.n_gathers)},
+        "allgather": {"count": rs.n_gathers, "ms_each_device": gather_ms_max / max(rs.n_gathers, 1), "ms_total": gather_ms_max,
+                      "bytes_per_rank": n_local * (64 + 64 * level.n_frags),
+                      "what": "ncclAllGather inside the library (ig_allgather_best): {likelihood, n_contigs, 64 B x NF live scaffold} per chain"
+                              if world > 1 else "single rank: device copy (no NCCL)"},
         "mcmc_cycle_s": dev_ms_max / 1e3 / args.steps * level.n_frags,
-        "proposals_per_step": prop_sum / world / args.steps,
+        "proposals_per_step": prop_sum / (n_local * world) / args.steps,
         "wall_s_timed_region": t_wall_max,
-        "e2e": {"value": e2e, "unit": "proposals/s", "h2d_bytes_per_step": 40, "d2h_bytes_per_step": 6360,  # sizeof(DevScalars): one copy
-                "ms_per_step": t_e2e_max / n_e2e * 1e3},
-        "e2e_cycle_api": {"value": cyc_prop / t_cyc, "unit": "proposals/s", "ms_per_step": t_cyc / args.steps * 1e3,
-                          "device_ms_per_step": st3["ms_step"] / args.steps,
-                          "note": "sampler.run_cycle: host draws every step's neighbours (reference RNG order), uploads the "
-                                  "plan once, the GPU replays one CUDA graph per step without host synchronisation"},
-        "e2e_cycle_device_rng": {"value": cycd_prop / t_cycd, "unit": "proposals/s", "ms_per_step": t_cycd / args.steps * 1e3,
-                                 "device_ms_per_step": st4["ms_step"] / args.steps,
-                                 "note": "sampler.run_cycle_device: the host uploads the visiting order only; candidates are "
-                                         "drawn on the GPU (Philox4x32-10), steps replay as CUDA graphs"},
-        "gpu_launches": int(st["launches"]),
-        "roofline": {"bound": "hbm", "kernel": dom, "kernel_launches": ("k_pick + k_eval_flat (flat scoring path of small levels)"
-                                                                         if dom == "k_score" and level.sparse_matrix.nnz <= 1500000 and level.n_sub_frags <= 16384
-                                                                         else dom), "achieved": ach[dom], "peak": peak, "unit": "GB/s",
-                     "frac": ach[dom] / peak, "traffic": measured_traffic(args.workload, dom), "peak_source": peak_src,
-                     "kernels": {k: {"launches": kern[k][2], "ms_per_launch": kern[k][0] / max(kern[k][2], 1),
-                                     "alg_bytes_per_launch": kern[k][1] / max(kern[k][2], 1),
-                                     "achieved_GBs": ach[k]} for k in kern},
-                     "terms_per_launch": stp["contacts_selected"] * (stp["proposals"] / max(stp["steps"], 1) / 5.0) / max(stp["steps"], 1),
-                     "note": "instruction/latency-bound, not HBM-bound: per 8-byte contact up to 24 float32 coordinate comparisons and, where a term changes, powf + f64 log10 (DESIGN.md 4a)"},
-        "kernel_us_per_step": {k: v / max(n_launch_score, 1) * 1e3 for k, v in ktimes.items()},
+        "e2e": {"value": e2e_multi, "unit": "proposals/s",
+                "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 56,
+                "ms_per_step": t_wall_max / args.steps * 1e3,
+                "note": "ReplicaSet.run_cycle -> ig_run_cycles_device_multi with HOST buffers: visiting orders in (4 B per step and chain), "
+                        "per-step records out (56 B per step and chain), all-gathers included, wall clock"},
+        "gpu_launches": int(launches_sum),
         "clocks": clk.summary(),
         "setup_s": {"generate": t_gen, "burn_in": t_burn},
     }
+    # ---------------- single-chain results (C4) + roofline per kernel
+    if single:
+        scs = {}
+        for name, r in single.items():
+            stp, n_prof = r["prof"], r["n_prof"]
+            n_full = max(stp["full_refreshes"], 0)
+            bytes_score = 8 * stp["contacts_read"] + 4 * (stp["rows"] + stp["steps"]) + 16 * stp["rows"] + 32 * stp["frags"]
+            bytes_full = 8 * nnz + 4 * (ns + 1) + 20 * ns
+            kt = r["ktimes"]
+            ms_score = stp["ms_score"] / max(n_prof, 1)
+            nuis_ms = r["nuis_dev_ms"] / max(r["nuis_calls"], 1)
+            scs[name] = {
+                "n_contigs_at_start": r["n_contigs_at_start"],
+                "value": r["proposals"] / (r["dev_ms"] / 1e3), "ms_per_step": r["dev_ms"] / args.steps,
+                "mcmc_cycle_s": r["dev_ms"] / 1e3 / args.steps * level.n_frags,
+                "e2e": {"value": r["prop_e2e"] / r["t_e2e"], "ms_per_step": r["t_e2e"] / args.steps * 1e3,
+                        "h2d_bytes_per_step": 40, "d2h_bytes_per_step": 6400,
+                        "note": "sampler.step_sampler: host RNG draw, ctypes, 40 B up, one result record down, blocking"},
+                "with_nuisance": {"e2e_value": r["prop_nuis"] / r["t_nuis"], "ms_per_step_e2e": r["t_nuis"] / r["n_nuis"] * 1e3,
+                                  "mcmc_cycle_s_e2e": r["t_nuis"] / r["n_nuis"] * level.n_frags,
+                                  "k_full_lnz_ms_per_call": nuis_ms, "steps": r["n_nuis"],
+                                  "note": "step_sampler + step_nuisance_parameters per step (IG:242-252): host fsolve + full likelihood under the test parameters"},
+                "without_nuisance_mcmc_cycle_s_e2e": r["t_e2e"] / args.steps * level.n_frags,
+                "kernels": {
+                    "scoring": {"launches_per_step": "k_stream + k_eval_flat<list> (+ k_score for circular contigs)" if (mode != "exact" and big)
+                                                     else ("k_pick + k_eval_flat" if not big else "k_score"),
+                                "ms_per_step": ms_score, "alg_bytes_per_step": bytes_score / max(n_prof, 1),
+                                "achieved_GBs": bytes_score / max(stp["ms_score"], 1e-9) / 1e6,
+                                "frac_hbm": bytes_score / max(stp["ms_score"], 1e-9) / 1e6 / peak,
+                                "traffic": measured_traffic(args.workload, "scoring", mode + "/" + name)},
+                    "k_full_lnz": {"ms_per_launch": nuis_ms, "alg_bytes_per_launch": bytes_full,
+                                   "achieved_GBs": bytes_full / max(nuis_ms, 1e-9) / 1e6,
+                                   "frac_hbm": bytes_full / max(nuis_ms, 1e-9) / 1e6 / peak,
+                                   "traffic": measured_traffic(args.workload, "k_full_lnz", mode + "/" + name)}},
+                "kernel_us_per_step": {k: v / max(n_prof, 1) * 1e3 for k, v in kt.items()},
+            }
+        out["single_chain"] = scs
+        hd = scs[start_name]
+        dom = "scoring" if hd["kernels"]["scoring"]["ms_per_step"] >= hd["kernels"]["k_full_lnz"]["ms_per_launch"] else "k_full_lnz"
+        kd = hd["kernels"][dom]
+        out["roofline"] = {"bound": "hbm", "kernel": dom, "state": start_name,
+                           "achieved": kd["achieved_GBs"], "peak": peak, "unit": "GB/s", "frac": kd["frac_hbm"],
+                           "traffic": kd["traffic"], "peak_source": peak_src,
+                           "kernels": {st_: scs[st_]["kernels"] for st_ in scs}}
+        if not big:
+            l2 = measure_l2_peak(torch, dev)
+            out["roofline"]["peak_l2_GBs"] = l2
+            out["roofline"]["frac_l2"] = kd["achieved_GBs"] / l2
+            out["roofline"]["note"] = "this level's contacts fit the 126 MB L2: frac_l2 is against the L2-resident copy bandwidth measured in this run"
+    rs.free()
     if not args.no_cpu_baseline and world == 1:
-        out["cpu_baseline"] = cpu_baseline(level, p8, st_burn, args.cpu_budget_s)
+        out["cpu_baseline"] = cpu_baseline(level, p8, st_start, args.cpu_budget_s)
     if not args.no_ref_gpu and world == 1:
         try:
-            s.free_gpu()
-            out["ref_gpu_baseline"] = ref_gpu_baseline(level, p8, st_burn, args.ref_gpu_budget_s, local)
-            out["ref_gpu_baseline"]["speedup_e2e_vs_ref_gpu"] = e2e / out["ref_gpu_baseline"]["value"]
+            out["ref_gpu_baseline"] = ref_gpu_baseline(level, p8, st_start, args.ref_gpu_budget_s, local)
+            sc_e2e = out["single_chain"][start_name]["e2e"]["value"] if single else None
+            if sc_e2e:
+                out["ref_gpu_baseline"]["speedup_single_chain_e2e_vs_ref_gpu"] = sc_e2e / out["ref_gpu_baseline"]["value"]
         except Exception as ex:  # the baseline must never break the bench line
             out["ref_gpu_baseline"] = {"unavailable": repr(ex)[:200]}
     print(json.dumps(out))
@@ -394,18 +496,22 @@ def ref_gpu_baseline(level, p8, state13, budget_s, device=0):
             "sample": "%d step_sampler calls from the same burnt-in scaffold, %.1f s" % (n_steps, dt)}
 
 
+_REF_LEVEL = None
+
+
 def _ref_worker(a):
-    name, seed, budget, max_steps, warm = a
-    level, _ = build_level(name)
+    seed, budget, max_steps, warm = a
+    level = _REF_LEVEL   # built once in the parent, inherited through fork (copy-on-write)
     p8 = params_for(level)
     return _oracle_chain(level, p8, None, seed, budget, max_steps, warm)
 
 
 def run_reference(args):
-    """CPU arm: the reference's algorithm (oracle port: NumPy transcription of its kernels + its
-    orchestration) on every host core, one independent chain per process.  A "step" of this arm is one
-    step_sampler call on every core; at most --steps of them are timed after min(--warmup, 2) untimed ones, and
-    the sample is cut at --cpu-budget-s seconds so the run stays bounded whatever K is."""
+    """CPU arm: the reference's algorithm (oracle port: NumPy transcription of its kernels + its orchestration) on every
+    host core, one independent chain per process.  A "step" of this arm is one step_sampler call on every core; at most
+    --steps of them are timed after min(--warmup, 2) untimed ones, and the sample is cut at --cpu-budget-s seconds so the
+    run stays bounded whatever K is (at the 1 Gb level one call takes tens of seconds: every core then times one call)."""
+    global _REF_LEVEL
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -413,10 +519,13 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     budget = max(5.0, min(args.cpu_budget_s, 60.0))
     level, _ = build_level(args.workload)
+    _REF_LEVEL = level
+    big = level.sparse_matrix.nnz > 20e6
+    n_proc = min(cores, 8) if big else cores   # ~6 GB of temporaries per worker at the 1 Gb level
     t0 = time.perf_counter()
-    with mp.get_context("fork").Pool(cores) as pool:
-        warm = max(0, min(args.warmup, 2))
-        res = pool.map(_ref_worker, [(args.workload, 100 + i, budget, args.steps, warm) for i in range(cores)])
+    with mp.get_context("fork").Pool(n_proc) as pool:
+        warm = 0 if big else max(0, min(args.warmup, 2))
+        res = pool.map(_ref_worker, [(100 + i, budget, args.steps, warm) for i in range(n_proc)])
     wall = time.perf_counter() - t0
     n_prop = sum(r[0] for r in res)
     n_steps = sum(r[1] for r in res)
@@ -426,17 +535,16 @@ def run_reference(args):
         "metric": "delta-log-L proposals scored per second (MCMC step_sampler, pyramid level 4)",
         "value": v, "unit": "proposals/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
         "steps": max(r[1] for r in res), "warmup": warm, "requested_steps": args.steps, "requested_warmup": args.warmup,
-        "ms_per_step": t_max / max(n_steps / cores, 1) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": t_max / max(n_steps / n_proc, 1) * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32 expected contacts / f64 accumulation / int32 scaffold", "data": "synthetic",
         "impl": "reference",
         "config": {"workload": args.workload, "n_frags": level.n_frags, "n_sub_frags": level.n_sub_frags,
-                   "chains": cores, "n_neighbours": 5,
+                   "nnz": int(level.sparse_matrix.nnz), "chains": n_proc, "n_neighbours": 5,
                    "note": "the reference is GPU-only (pycuda); this arm is its algorithm transcribed to NumPy (oracle/), "
-                           "one chain per host core from the contig-order start (the in-arm cpu_baseline of the GPU arm "
-                           "times the same port on the GPU arm's burnt-in scaffold: same rate per core)"},
-        "cpu_baseline": {"value": v, "unit": "proposals/s", "cores": cores, "kind": "port",
-                         "sample": "%d processes x %.0f s of step_sampler calls (%d steps, %d proposals), wall %.1f s"
-                                   % (cores, budget, n_steps, n_prop, wall)},
+                           "one chain per host process from the contig-order start"},
+        "cpu_baseline": {"value": v, "unit": "proposals/s", "cores": n_proc, "kind": "port",
+                         "sample": "%d processes x <= %.0f s of step_sampler calls (%d steps, %d proposals), wall %.1f s"
+                                   % (n_proc, budget, n_steps, n_prop, wall)},
         "e2e": {"value": v, "unit": "proposals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -446,20 +554,23 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8000)
-    ap.add_argument("--warmup", type=int, default=500)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="T")
+    ap.add_argument("--workload", default="G", help="G = BASELINE.json configs[3] (~1 Gb, the config the metric is quoted on); T, Y3, yeast_toy")
+    ap.add_argument("--chains", type=int, default=8, help="replica chains in total (configs[4]: 8), split evenly over the GPUs")
     ap.add_argument("--burn-cycles", type=int, default=-1)
-    ap.add_argument("--bomb", type=int, default=1)
-    ap.add_argument("--start", default="bomb", choices=["bomb", "true"])
+    ap.add_argument("--start", default="both", choices=["bomb", "true", "both"],
+                    help="single-chain passes from the mid-assembly state (bomb + burn-in), the fully assembled one, or both")
     ap.add_argument("--flush-l2", type=int, default=1)
-    ap.add_argument("--gather-every", type=int, default=500)
+    ap.add_argument("--gather-every", type=int, default=0, help="steps between all-gathers (0: steps / 4)")
     ap.add_argument("--refresh-every", type=int, default=4096)
     ap.add_argument("--graph", type=int, default=1)
-    ap.add_argument("--rigid-pruning", type=int, default=0,
-                    help="1: skip contacts whose ends move rigidly together (not the reference's float32 re-rounding; see DESIGN.md)")
-    ap.add_argument("--cpu-budget-s", type=float, default=15.0)
+    ap.add_argument("--mode", default=DEFAULT_MODE, choices=["exact", "rigid"],
+                    help="exact: reproduce the reference's float32 re-rounding of rigidly shifted coordinates bit for bit; "
+                         "rigid: skip contacts whose two ends move together (DESIGN.md D2)")
+    ap.add_argument("--nuisance-steps", type=int, default=500)
+    ap.add_argument("--cpu-budget-s", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
     ap.add_argument("--ref-gpu-budget-s", type=float, default=10.0)

@@ -299,7 +299,7 @@ static int create_impl(const ig_config* cfg, const ig_level_data* data, ig_handl
         }
         if (h->streaming) {
             h->rows_small = false;   // the two-pass row list also writes the bitmap and the class words
-            h->pick_cap = std::min<size_t>((size_t)h->nnz + 64, (size_t)4 << 20);
+            h->pick_cap = std::min<size_t>((size_t)h->nnz + 64, (size_t)2 << 20);   // 64-byte records: 128 MB per candidate slot at most
             if (const char* e = getenv("IG_PICK_CAP")) h->pick_cap = (size_t)std::max(64, atoi(e));
             if (dev_alloc(h, &h->bitmap, (size_t)IG_MAX_CANDS * h->bitmap_words) || dev_alloc(h, &h->cls16, (size_t)IG_MAX_CANDS * ns) ||
                 dev_alloc(h, &h->pick_list, (size_t)IG_MAX_CANDS * h->pick_cap)) return -2;

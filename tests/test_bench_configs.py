@@ -21,7 +21,7 @@ import numpy as np
 import pytest
 
 from instagraal_b200.synth import make_workload, workload_params
-from parity_common import FIELDS13
+from parity_common import FIELDS13, state_mismatch_modulo_length_ties
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -123,7 +123,7 @@ def lockstep_vs_reference_kernels(level, p8, state13, n_steps, seed, probes=()):
         if gid == gid_ref:
             same += 1
             got = mine.get_state()
-            bad = [FIELDS13[i] for i in range(13) if not np.array_equal(got[i], new_state[i])]
+            bad = state_mismatch_modulo_length_ties(got, new_state)   # (on a GPU the reference's labels of equal-length contigs are arbitrary)
             assert not bad, (t, f, cands, op, b, bad)
             assert float(r["dist"]) == float(dist), (t, r["dist"], dist)
             assert int(r["n_contigs"]) == int(nc), (t, r["n_contigs"], nc)
