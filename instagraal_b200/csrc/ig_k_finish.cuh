@@ -219,6 +219,7 @@ __global__ void k_select(DevScalars* sc) {
     sc->win_op = best % IG_N_OPS;
     sc->likelihood = sm[best];
     sc->n_heads = 0; sc->sum_l_cont = 0; sc->dist_half = 0;  // accumulators of k_post
+    sc->q4_hits = 0;                                          // counted by k_apply for THIS move
 }
 // step path: selection + the bookkeeping of k_post_scalars in one launch (k_apply reads the label base
 // from the descriptor, not from sc->max_label, so bumping it here cannot race)
@@ -246,7 +247,7 @@ __device__ void select_step(DevScalars* sc, const IgDescriptor* __restrict__ des
     if (lane < 12 && op >= 12) sc->valid[lane] = desc_g[kc].valid[lane];
     if (lane != 0) return;
     sc->win_cand = kc; sc->win_op = op; sc->likelihood = __ldcg(&sc->scores[best]);
-    sc->n_heads = 0; sc->sum_l_cont = 0; sc->dist_half = 0;
+    sc->n_heads = 0; sc->sum_l_cont = 0; sc->dist_half = 0; sc->q4_hits = 0;
     sc->max_label += 2;
     sc->prev_k = kc; sc->prev_u = hit ? (__ffs(hit) - 1) : 0;
     sc->prev_windowed = (sc->ci[kc].same && sc->ci[kc].is_circ == 0) ? 1 : 0;

@@ -160,6 +160,7 @@ struct ig_handle {
     DevScalars* h_sc;  // pinned mirror
     int* h_small;      // pinned scratch (cands, nuniq, nsub)
     bool params_set, coords_fresh, coords_ever; int init_max_label;
+    long long label_hi = 0;          // upper bound of the contig labels in use (2 new ones per applied move), see labels_guard
     bool incr_valid; int refresh_every; long long steps_since_full;
     double* part_out;
     int gs_div, sparse_div, grid_split;
@@ -187,6 +188,13 @@ static thread_local std::string g_err;
             return -2;                                                                             \
         }                                                                                          \
     } while (0)
+// Host-to-device copy from pageable memory that is COMPLETE when it returns: a plain cudaMemcpy may return once the data
+// is staged, and the kernels run on non-blocking streams that are not ordered against the legacy stream it uses.
+static inline cudaError_t h2d_sync(void* dst, const void* src, size_t bytes) {
+    cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(cudaStreamLegacy);
+}
 
 extern "C" const char* ig_last_error(ig_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
 extern "C" int ig_device_count(void) {
@@ -353,23 +361,23 @@ static int create_impl(const ig_config* cfg, const ig_level_data* data, ig_handl
                     s[i].crick = data->sub_crick[i]; s[i].j = data->sub_j[i];
                     if (s[i].parent < 0 || s[i].parent >= nf) { h->err = "ig_create: sub_parent out of range"; return -1; }
                 }
-                CK(cudaMemcpy(h->sub, s.data(), sizeof(SubRec) * ns, cudaMemcpyHostToDevice));
+                CK(h2d_sync(h->sub, s.data(), sizeof(SubRec) * ns));
             }
             if (data->row_ptr[0] != 0 || data->row_ptr[ns] != h->nnz) { h->err = "ig_create: row_ptr inconsistent with nnz"; return -1; }
-            CK(cudaMemcpy(h->row_ptr, data->row_ptr, sizeof(long long) * ((size_t)ns + 1), cudaMemcpyHostToDevice));
+            CK(h2d_sync(h->row_ptr, data->row_ptr, sizeof(long long) * ((size_t)ns + 1)));
             {
                 const size_t chunk = 1 << 24;
                 std::vector<int2> buf(std::min<size_t>(chunk, (size_t)h->nnz));
                 for (size_t off = 0; off < (size_t)h->nnz; off += chunk) {
                     const size_t n = std::min(chunk, (size_t)h->nnz - off);
                     for (size_t i = 0; i < n; i++) { buf[i].x = data->col[off + i]; buf[i].y = data->val[off + i]; }
-                    CK(cudaMemcpy(h->cv + off, buf.data(), n * sizeof(int2), cudaMemcpyHostToDevice));
+                    CK(h2d_sync(h->cv + off, buf.data(), n * sizeof(int2)));
                 }
             }
             CK(cudaMemset(h->cv + h->nnz, 0, 2 * sizeof(int2)));   // k_full_lnz reads contacts in aligned pairs
-            CK(cudaMemcpy(h->init_prev, data->init_prev, sizeof(int) * nf, cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(h->init_next, data->init_next, sizeof(int) * nf, cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(h->orientable, data->orientable, sizeof(int) * nf, cudaMemcpyHostToDevice));
+            CK(h2d_sync(h->init_prev, data->init_prev, sizeof(int) * nf));
+            CK(h2d_sync(h->init_next, data->init_next, sizeof(int) * nf));
+            CK(h2d_sync(h->orientable, data->orientable, sizeof(int) * nf));
         }
         // factorial table on the device (same libdevice calls as the reference's factorial())
         double* d16;
@@ -397,8 +405,8 @@ static int create_impl(const ig_config* cfg, const ig_level_data* data, ig_handl
         int maxlab = 0;
         if (parent) maxlab = parent->init_max_label;
         else for (int i = 0; i < nf; i++) maxlab = std::max(maxlab, data->frags13[(size_t)2 * nf + i]);
-        h->init_max_label = maxlab;
-        CK(cudaMemcpy(&h->sc->max_label, &maxlab, sizeof(int), cudaMemcpyHostToDevice));
+        h->init_max_label = maxlab; h->label_hi = maxlab;
+        CK(h2d_sync(&h->sc->max_label, &maxlab, sizeof(int)));
         return 0;
     };
     int rc = body();
@@ -519,7 +527,8 @@ extern "C" int ig_set_state(ig_handle* h, const int32_t* in13) {
     if (upload_state(h, in13, h->live)) return -2;
     int maxlab = 0;
     for (int i = 0; i < h->nf; i++) maxlab = std::max(maxlab, in13[(size_t)2 * h->nf + i]);
-    CK(cudaMemcpy(&h->sc->max_label, &maxlab, sizeof(int), cudaMemcpyHostToDevice));
+    CK(h2d_sync(&h->sc->max_label, &maxlab, sizeof(int)));
+    h->label_hi = maxlab;
     h->coords_fresh = false;
     h->incr_valid = false;
     return 0;
@@ -531,7 +540,7 @@ extern "C" int ig_get_valid_insert(ig_handle* h, int32_t out12[12]) {
 }
 extern "C" int ig_set_valid_insert(ig_handle* h, const int32_t in12[12]) {
     if (use(h)) return -1;
-    CK(cudaMemcpy(h->sc->valid, in12, 12 * sizeof(int), cudaMemcpyHostToDevice));
+    CK(h2d_sync(h->sc->valid, in12, 12 * sizeof(int)));
     return 0;
 }
 extern "C" int ig_bomb(ig_handle* h, const int32_t* perm) {
@@ -540,11 +549,23 @@ extern "C" int ig_bomb(ig_handle* h, const int32_t* perm) {
     k_explode<<<(h->nf + 255) / 256, 256, 0, h->stream>>>(h->live, h->nf, h->d_perm);
     if (launch_ok(h, "explode")) return -2;
     int maxlab = h->nf;  // perm values are 0..NF-1
+    h->label_hi = maxlab;
     CK(cudaMemcpyAsync(&h->sc->max_label, &maxlab, sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->coords_fresh = false;
     h->incr_valid = false;
     return 0;
+}
+
+// Contig labels are only ever compared for equality, so every applied move simply takes two fresh ones (max_label += 2).
+// Long before the int32 counter could wrap (~5e8 steps) the labels are re-based to 0..NC-1 through the canonical
+// relabelling of ig_get_state (what the reference does after every step, CL:2715-2806); the next step then refreshes fully.
+static int labels_guard(ig_handle* h) {
+    h->label_hi += 2;
+    if (h->label_hi < (1LL << 30)) return 0;
+    std::vector<int32_t> st((size_t)IG_N_FIELDS * h->nf);
+    if (int rc = ig_get_state(h, st.data())) return rc;
+    return ig_set_state(h, st.data());
 }
 
 // head of step_sampler: fill_dist_single + eval_likelihood (CL:1407-1409)
@@ -645,6 +666,7 @@ static int score_candidates(ig_handle* h, int a, const int32_t* cands, int n, in
 
 static int apply_and_post(ig_handle* h, int forced_cand, int forced_op) {
     const int nf = h->nf;
+    h->label_hi += 2;
     k_apply<<<(nf + 255) / 256, 256, 0, h->stream>>>(h->live, nf, h->sc, h->desc, forced_cand, forced_op);
     k_post_scalars<<<1, 1, 0, h->stream>>>(h->sc, h->desc, forced_cand, forced_op);
     k_post<<<(nf + 255) / 256, 256, 0, h->stream>>>(h->live, nf, h->init_prev, h->init_next, h->orientable, h->sc, nullptr, nullptr, nullptr);
@@ -787,6 +809,7 @@ extern "C" int ig_step(ig_handle* h, int32_t id_frag, const int32_t* cands, int3
     if (id_frag < 0 || id_frag >= h->nf) { h->err = "id_frag out of range"; return -1; }
     for (int i = 0; i < n_cands; i++) if (cands[i] < 0 || cands[i] >= h->nf) { h->err = "candidate out of range"; return -1; }
     for (int i = 0; i < n_cands; i++) if (cands[i] == id_frag) { h->err = "candidate equals the visited fragment (reference quirk Q4; see DESIGN.md D1)"; return -1; }
+    if (int rc = labels_guard(h)) return rc;
     int* hs = h->h_small;
     hs[0] = n_cands; hs[1] = id_frag;
     for (int i = 0; i < IG_MAX_CANDS; i++) hs[2 + i] = i < n_cands ? cands[i] : 0;
@@ -844,6 +867,7 @@ static int cycle_buffers(ig_handle* h, int n_steps) {
 // one step of the plan in h->cyc_in enqueued on the handle's stream (CUDA-graph replay); grid_n = number of candidate
 // slots the step's grid is built for
 static int enqueue_plan_step(ig_handle* h, int grid_n) {
+    if (int rc = labels_guard(h)) return rc;
     const int full = (!h->incr_valid || (h->refresh_every > 0 && h->steps_since_full >= h->refresh_every)) ? 1 : 0;
     cudaGraphExec_t ge = nullptr;
     if (h->use_graph) get_graph(h, full, &ge, 1, grid_n);
@@ -930,12 +954,12 @@ extern "C" int ig_set_neighbour_weights(ig_handle* h, const int64_t* ptr, const 
     L->nb_ptr = nullptr; L->nb_idx = nullptr; L->nb_cdf = nullptr; L->nb_nnz = nullptr;
     if (dev_alloc(h, &L->nb_ptr, (size_t)h->nf + 1) || dev_alloc(h, &L->nb_idx, n + 1) || dev_alloc(h, &L->nb_cdf, n + 1) ||
         dev_alloc(h, &L->nb_nnz, (size_t)h->nf)) return -2;
-    CK(cudaMemcpy(L->nb_ptr, ptr, sizeof(long long) * ((size_t)h->nf + 1), cudaMemcpyHostToDevice));
+    CK(h2d_sync(L->nb_ptr, ptr, sizeof(long long) * ((size_t)h->nf + 1)));
     if (n) {
-        CK(cudaMemcpy(L->nb_idx, idx, sizeof(int) * n, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(L->nb_cdf, cdf, sizeof(double) * n, cudaMemcpyHostToDevice));
+        CK(h2d_sync(L->nb_idx, idx, sizeof(int) * n));
+        CK(h2d_sync(L->nb_cdf, cdf, sizeof(double) * n));
     }
-    CK(cudaMemcpy(L->nb_nnz, n_nonzero, sizeof(int) * (size_t)h->nf, cudaMemcpyHostToDevice));
+    CK(h2d_sync(L->nb_nnz, n_nonzero, sizeof(int) * (size_t)h->nf));
     return 0;
 }
 

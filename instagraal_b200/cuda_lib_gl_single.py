@@ -169,6 +169,7 @@ class sampler:
         self.n_contigs = None
         self.mean_length_contigs = None
         self.n_proposals_scored = 0
+        self._last_dist = 1.0
         self.modification_str = [  # CL:1601-1620
             "eject frag", "flip frag", "pop out split insert @ left or 1", "pop out split insert @ left or -1",
             "pop out split insert @ right or 1", "pop out split insert @ right or -1", "pop out insert @ right or 1",
@@ -358,6 +359,16 @@ class sampler:
         return out
 
     # ------------------------------------------------------------------ the hot path
+    def _usable_candidates(self, id_frag, candidates):
+        """Sorted candidate list of one step: deviation D1 (B == A dropped, see step_sampler) and the library's limit of
+        IG_MAX_CANDS candidates per step (the reference has no limit; its CLI default is 5)."""
+        cs = sorted(int(c) for c in candidates if int(c) != int(id_frag))
+        if len(cs) > L.IG_MAX_CANDS:
+            raise ValueError("instagraal_b200 scores at most %d candidate neighbours per step (got %d: lower "
+                             "--neighborhood / n_neighbours, or rebuild the library with a larger IG_MAX_CANDS)"
+                             % (L.IG_MAX_CANDS, len(cs)))
+        return cs
+
     def step_sampler(self, id_frag, n_neighbours, dt, candidates=None):
         """CL:1401-1465.  ``candidates`` (optional) bypasses the host RNG draw (replay / parity)."""
         if candidates is None:
@@ -366,9 +377,14 @@ class sampler:
         # fragments (CL:3124), which can contain the fragment itself; for B == A the reference's
         # paste_contigs writes nothing (quirk Q4) and stale candidate structs get scored and possibly
         # applied.  The draw is made as in the reference (same RNG consumption) but B == A is dropped.
-        self.candidates = [c for c in candidates if int(c) != int(id_frag)]
-        self.candidates.sort()
+        self.candidates = self._usable_candidates(id_frag, candidates)
         n = len(self.candidates)
+        if n == 0:
+            # only reachable through D1 (the uniform fallback draw returned nothing but the visited fragment): nothing
+            # to score, the scaffold stays as it is and the previous step's outputs are returned with op_sampled = -1
+            self.all_scores = np.zeros(0)
+            self.n_uniq, self.n_sub_vals = [], []
+            return (self.likelihood_t, self._last_dist, -1, int(id_frag), self.mean_length_contigs, self.n_contigs)
         self._cand_buf[:n] = self.candidates
         res = self._res
         rc = self._ig_step(self._h, int(id_frag), self._cand_ptr, n, self._res_ref)
@@ -388,6 +404,7 @@ class sampler:
         self.o = o
         self.likelihood_t = o
         self.curr_likelihood_on_nz = res.lnz_full
+        self._last_dist = res.dist
         return (o, res.dist, op_sampled, id_f_sampled, self.mean_length_contigs, self.n_contigs)
 
     def run_cycle(self, list_frags, n_neighbours=5, candidates=None):
@@ -402,7 +419,10 @@ class sampler:
         nc = np.zeros(n, dtype=np.int32)
         for t in range(n):
             cs = candidates[t] if candidates is not None else self.return_neighbours(int(frags[t]), n_neighbours)
-            cs = sorted(int(c) for c in cs if int(c) != int(frags[t]))  # deviation D1, see step_sampler
+            cs = self._usable_candidates(frags[t], cs)  # deviation D1, see step_sampler
+            if not cs:
+                raise ValueError("run_cycle: step %d (fragment %d) has no candidate but the visited fragment itself; "
+                                 "use step_sampler (which skips such a step) or n_neighbours >= 2" % (t, int(frags[t])))
             nc[t] = len(cs)
             c8[t, :len(cs)] = cs
         out = np.zeros(n, dtype=L.CYCLE_DTYPE)

@@ -166,7 +166,15 @@ class DevStruct:
 
 # ------------------------------------------------------------------------------------------ the replay
 class RefReplaySampler:
-    def __init__(self, level, params8, backend="cpu", device=0):
+    def __init__(self, level, params8, backend="cpu", device=0, canonical_slice_order=False):
+        """canonical_slice_order: slice_sp_mat (KA:485-607) appends the selected contacts through an atomic counter, so
+        their order inside a row is whatever order the atomics executed in, and the stable host sort by row (CL:45-55)
+        keeps it.  Under the CPU emulation that order is ascending column; on a real GPU it VARIES FROM RUN TO RUN, and
+        eval_sub_likelihood's last-block quirk (KA:4362: uniq positions >= n_sub % 64 lose the final block's contacts)
+        makes the scores of those positions depend on it (two replays of one step from one state on the same B200
+        differ, profiles/r2_reference_nondeterminism.txt).  True sorts by (row, column) instead: the reference's kernels
+        stay untouched, its one arbitrary choice is pinned to the emulation's."""
+        self.canonical_slice_order = canonical_slice_order
         be = self.be = CpuBackend() if backend == "cpu" else GpuBackend(device)
         self.nf, self.ns = level.n_frags, level.n_sub_frags
         nf, ns = self.nf, self.ns
@@ -337,7 +345,7 @@ class RefReplaySampler:
                 ("i", ctg1), ("i", ctg2), ("i", a), ("i", b), ("i", self.max_bounds_insert), ("p", self.counter.ptr), ("i", self.nnz)])
         n = self.n_sub_vals = int(self.counter.get()[0])
         keys, va, vb = self.sub_rows.get(), self.sub_cols.get(), self.sub_dat.get()  # sort_by_keys_zip (CL:45-55)
-        idx = np.argsort(keys[:n], kind="stable")
+        idx = np.lexsort((va[:n], keys[:n])) if self.canonical_slice_order else np.argsort(keys[:n], kind="stable")
         keys[:n], va[:n], vb[:n] = keys[:n][idx], va[:n][idx], vb[:n][idx]
         self.sub_rows.set(keys); self.sub_cols.set(va); self.sub_dat.set(vb)
         self.counter.fill(0)

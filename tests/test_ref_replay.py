@@ -14,7 +14,7 @@ from parity_common import replay
 class ReplayImpl:
     def __init__(self, level, p8, backend):
         from oracle.ref_replay import RefReplaySampler
-        self.r = RefReplaySampler(level, p8, backend=backend)
+        self.r = RefReplaySampler(level, p8, backend=backend, canonical_slice_order=(backend == "gpu"))  # GPU: atomic order varies run to run
 
     def set_state(self, st):
         self.r.set_state(st)
