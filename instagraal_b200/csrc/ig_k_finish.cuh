@@ -323,7 +323,7 @@ k_lnz_outside(const long long* __restrict__ row_ptr, const int2* __restrict__ cv
 __global__ void __launch_bounds__(256)
 k_commit_coords(CoordRec* __restrict__ coord, int* __restrict__ clen, DevScalars* sc, const int* __restrict__ rows, int ns,
                 const RowMut* __restrict__ table, const int* __restrict__ table_len, const FragRec* __restrict__ live,
-                const SubRec* __restrict__ sub, SubX* __restrict__ subx) {
+                const SubRec* __restrict__ sub, SubX* __restrict__ subx, unsigned char* __restrict__ row_dirty) {
     TL(11);
     const int k = sc->prev_k, u = sc->prev_u, n = sc->prev_n_rows;
     const int* my_rows = rows + (size_t)k * ns;
@@ -334,6 +334,7 @@ k_commit_coords(CoordRec* __restrict__ coord, int* __restrict__ clen, DevScalars
         const RowMut m = tab[ri];
         CoordRec c; c.dist = m.dist; c.id_c = m.id_c; c.pos = m.pos; c.s_tot = m.s_tot;
         coord[r] = c; clen[r] = tlen[ri];
+        if (row_dirty) row_dirty[r] = 1;   // cached per-contact records of this row are stale (k_lnz_refresh)
         const SubRec sr = sub[r];
         const Frag f = live[sr.parent].f;   // the scaffold after the applied move
         SubX x; x.start_bp = f.start_bp; x.len_ori = f.len_bp * f.ori; x.watson = sr.watson; x.crick = sr.crick;

@@ -8,7 +8,8 @@
 __global__ void __launch_bounds__(IG_THREADS)
 k_coords(const FragRec* __restrict__ live, const SubRec* __restrict__ sub, CoordRec* __restrict__ coord,
          int* __restrict__ clen, int ns, const DevScalars* __restrict__ sc, float mbar, int use_test,
-         double* __restrict__ part_z, int* __restrict__ part_n, int write_coords, SubX* __restrict__ subx) {
+         double* __restrict__ part_z, int* __restrict__ part_n, int write_coords, SubX* __restrict__ subx,
+         unsigned char* __restrict__ row_dirty) {
     TL(13);
     __shared__ double sm[32];
     __shared__ int sn;
@@ -26,6 +27,7 @@ k_coords(const FragRec* __restrict__ live, const SubRec* __restrict__ sub, Coord
             coord[r] = c; clen[r] = len;
             SubX x; x.start_bp = f.start_bp; x.len_ori = f.len_bp * f.ori; x.watson = s.watson; x.crick = s.crick;
             subx[r] = x;
+            if (row_dirty) row_dirty[r] = 1;   // cached per-contact records of this row are stale (k_lnz_refresh)
         } else { c = coord[r]; len = clen[r]; }
         if (c.pos == 0) nloc += intra_pairs(len);
         z += zero_term(c.pos, len, c.s_tot, p, mbar);
@@ -161,6 +163,139 @@ k_obc_sum(const int2* __restrict__ cv, long long nnz, double* __restrict__ part)
     if (threadIdx.x == 0) part[blockIdx.x] = tot;
 }
 
+// ------------------------------------------------------------------------------------------------
+// K1': the same sum as k_full_lnz from CACHED per-contact records -- the nuisance step's likelihood
+//      (step_nuisance_parameters -> eval_likelihood_4_nuisance, CL:2961-3051 / 1296-1344) runs after EVERY step_sampler
+//      from cycle 5 on (IG:242-252): the parameters change with every call, the scaffold's coordinates only for the rows
+//      of the <= 2 contigs the last move touched.  What a contact's term needs from the scaffold is
+//          same contig?   s = |dist_i - dist_j| (float32, KA:4322)   dp = |pos_i - pos_j|
+//      so these are kept per contact in an 8-byte record {s (negative: other contig), dp | val << dp_bits} that is
+//      rebuilt for the rows whose coordinates were rewritten (row_dirty, set by k_coords / k_commit_coords: every row of
+//      an affected contig; a contact from an untouched row into a touched contig joined other contigs before and after).
+//        k_lnz_refresh  rows flagged dirty: the gather path of k_full_lnz, writing records; rows of circular contigs are
+//                       evaluated here on every call with the generic routine (their records say "skip");
+//        k_lnz_stream   a flat pass over the records: 8 bytes per contact, no row structure, no gathers but the
+//                       L1-resident expected-contact table; floor contacts are counted, the others queued per warp and
+//                       evaluated 32 at a time (powf_pos + log10_f32) exactly like k_full_lnz.
+//      Same terms, same double accumulation, different (fixed) summation order.
+// Record encoding (dp_bits low bits = index into the expected-contact table, the observed count above them):
+//   same contig      {s >= 0,  dp}        table[dp]     = expected contacts at separation dp (k_exz_table)
+//   other contig     {-1.0f,   ns + 1}    table[ns + 1] = v_inter
+//   skip             {-1.0f,   ns + 2}    table[ns + 2] = 0      (rows of circular contigs; the odd padding record)
+// so the flat pass needs no case distinction: a record is QUEUED when 0 < s < d_max and is a floor contact otherwise, and
+// every record adds table[idx] to the zero term.  Floor contacts are not even counted per record:
+//   sum_floor (ob log10 v - v) = log10 v * (V_all - V_queued) - v * (N_all - N_queued)
+// with V_all = the level's total observed count (constant) and N_all = the number of records streamed; the skip records
+// are in N_all (and, for circular rows, in V_all) and k_lnz_refresh, which evaluates those rows anyway, takes their
+// spurious floor terms out again.
+__global__ void __launch_bounds__(IG_THREADS)
+k_lnz_refresh(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, const CoordRec* __restrict__ coord,
+              const int* __restrict__ clen, int ns, const DevScalars* __restrict__ sc, float mbar, int use_test,
+              const float* __restrict__ exz_tab, int2* __restrict__ rec, unsigned char* __restrict__ row_dirty, int dp_bits,
+              double* __restrict__ part) {
+    TL(14);
+    __shared__ double sm[32];
+    const Params p = use_test ? sc->p_test : sc->p;
+    const double l10v = use_test ? sc->log10_vinter_test : sc->log10_vinter;
+    const int lane = threadIdx.x & 31;
+    const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    double acc = 0.0;
+    for (int base = wg * 32; base < ns; base += nw * 32) {
+        // 32 rows looked at together: which of them need work?
+        const int r_l = base + lane;
+        bool need = false;
+        if (r_l < ns) {
+            const bool circ = coord[r_l].s_tot != 0;
+            need = (row_ptr[r_l] != row_ptr[r_l + 1]) && (circ || row_dirty[r_l] != 0);
+            if (!need && row_dirty[r_l]) row_dirty[r_l] = 0;   // empty row
+        }
+        for (unsigned todo = __ballot_sync(0xffffffffu, need); todo; todo &= todo - 1) {
+            const int r = base + __ffs(todo) - 1;
+            const long long b = row_ptr[r], e = row_ptr[r + 1];
+            const CoordRec ci = coord[r];
+            const bool circ = ci.s_tot != 0;
+            const bool dirty = row_dirty[r] != 0;
+            const int len_i = clen[r];
+            for (long long k = b + lane; k < e; k += 32) {
+                const int2 c = __ldg(&cv[k]);
+                const CoordRec cj = coord[c.x];
+                int2 out;
+                out.x = __float_as_int(-1.0f);
+                if (circ) {   // KA:4428: the circular zero term uses the ROW's contig length; obc is hoisted (sc->obc_total)
+                    acc += contact_term(ci, cj, len_i, (double)c.y, 0.0, p, l10v, mbar, exz_tab)
+                           - (l10v * (double)c.y - (double)p.v_inter);   // what the flat pass adds for a skip record
+                    out.y = (ns + 2) | (c.y << dp_bits);
+                } else if (cj.id_c == ci.id_c) {
+                    out.x = __float_as_int(fabsf(ci.dist - cj.dist));
+                    out.y = abs(ci.pos - cj.pos) | (c.y << dp_bits);
+                } else out.y = (ns + 1) | (c.y << dp_bits);
+                if (dirty) rec[k] = out;
+            }
+            __syncwarp();
+            if (dirty && lane == 0) row_dirty[r] = 0;
+        }
+    }
+    const double tot = block_sum(acc, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(IG_THREADS, 4)
+k_lnz_stream(const int4* __restrict__ rec2, long long n_pairs, int n_pad, double val_total, const DevScalars* __restrict__ sc,
+             int use_test, const float* __restrict__ exz_tab, int dp_bits, double* __restrict__ part) {
+    TL(14);
+    __shared__ double sm[32];
+    __shared__ LnzQ queue[IG_WARPS_PER_BLOCK][IG_LNZ_QCAP];
+    const Params p = use_test ? sc->p_test : sc->p;
+    const double l10v = use_test ? sc->log10_vinter_test : sc->log10_vinter;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long wg = (long long)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const long long nw = (long long)((gridDim.x * blockDim.x) >> 5);
+    const unsigned dpmask = (1u << dp_bits) - 1u;
+    const unsigned lt = (1u << lane) - 1u;
+    LnzQ* myq = queue[w];
+    int qn = 0, n_queued = 0;         // warp-uniform
+    double acc = 0.0, acc_exz = 0.0;  // queued terms / expected contacts of the zero term
+    int v_queued = 0;                 // observed counts of the queued contacts
+    auto eval = [&](const LnzQ e) {
+        v_queued += e.val;
+        acc += lnz_eval(e, p, l10v);
+    };
+    auto append = [&](bool p0, int s0, unsigned y0, bool p1, int s1, unsigned y1) {
+        const unsigned m0 = __ballot_sync(0xffffffffu, p0), m1 = __ballot_sync(0xffffffffu, p1);
+        const int c0 = __popc(m0), c1 = __popc(m1);
+        if (p0) { LnzQ q; q.s = __int_as_float(s0); q.val = (int)(y0 >> dp_bits); myq[qn + __popc(m0 & lt)] = q; }
+        if (p1) { LnzQ q; q.s = __int_as_float(s1); q.val = (int)(y1 >> dp_bits); myq[qn + c0 + __popc(m1 & lt)] = q; }
+        qn += c0 + c1; n_queued += c0 + c1;
+        __syncwarp();
+        while (qn >= 32) {
+            qn -= 32;
+            eval(myq[qn + lane]);
+        }
+        __syncwarp();
+    };
+    for (long long base = wg * 64; base < n_pairs; base += nw * 64) {   // n_pairs is a multiple of 64: whole trips only
+        const int4 ra = __ldcs(rec2 + base + lane);        // streamed once per call: evict first
+        const int4 rb = __ldcs(rec2 + base + 32 + lane);
+        const float e0 = __ldg(&exz_tab[(unsigned)ra.y & dpmask]), e1 = __ldg(&exz_tab[(unsigned)ra.w & dpmask]);
+        const float e2 = __ldg(&exz_tab[(unsigned)rb.y & dpmask]), e3 = __ldg(&exz_tab[(unsigned)rb.w & dpmask]);
+        const float s0 = __int_as_float(ra.x), s1 = __int_as_float(ra.z), s2 = __int_as_float(rb.x), s3 = __int_as_float(rb.z);
+        append((s0 > 0.0f) && (s0 < p.d_max), ra.x, (unsigned)ra.y, (s1 > 0.0f) && (s1 < p.d_max), ra.z, (unsigned)ra.w);
+        append((s2 > 0.0f) && (s2 < p.d_max), rb.x, (unsigned)rb.y, (s3 > 0.0f) && (s3 < p.d_max), rb.z, (unsigned)rb.w);
+        acc_exz += ((double)e0 + (double)e1) + ((double)e2 + (double)e3);
+    }
+    if (lane < qn) eval(myq[lane]);
+    // the queued contacts are not floor contacts: take them out of the closed-form floor sum (block 0 adds its constants)
+    acc += acc_exz * (double)LOG10E_F - l10v * (double)v_queued;
+    if (lane == 0) acc += (double)p.v_inter * (double)n_queued;
+    double tot = block_sum(acc, sm);
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0)
+            tot += l10v * val_total - (double)p.v_inter * (2.0 * (double)n_pairs - (double)n_pad) - sc->obc_total;
+        part[blockIdx.x] = tot;
+    }
+}
+
 // generic deterministic final reduction of `n` doubles (and optionally ints) by one block
 __global__ void k_reduce(const double* __restrict__ part, int n, double* out, const int* __restrict__ ipart, int* iout) {
     __shared__ double sm[32];
@@ -179,6 +314,7 @@ __global__ void k_reduce(const double* __restrict__ part, int n, double* out, co
 // exz table: expected contacts at integer sub-fragment separation (linear contigs), KA:4330-4335
 __global__ void k_exz_table(float* __restrict__ tab, int n, const DevScalars* __restrict__ sc, float mbar, int use_test) {
     const Params p = use_test ? sc->p_test : sc->p;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { tab[n] = p.v_inter; tab[n + 1] = 0.0f; }   // slots of the likelihood records (k_lnz_stream)
     for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < n; d += gridDim.x * blockDim.x) {
         float s_z = __int2float_rn(d) * mbar;
         tab[d] = (s_z < p.d_max) ? rippe_contacts(s_z, p) : p.v_inter;

@@ -118,6 +118,8 @@ struct CycleOut {  // compact per-step record of ig_run_cycle (128 B)
 // the level's read-only arrays: shared by every chain cloned from one handle (ig_clone), freed with the last of them
 struct LevelBlock {
     int refs;
+    int max_val;   // largest observed count of the level (decides whether the packed likelihood records can hold it)
+    double val_total;   // sum of the observed counts of every stored contact
     int* sym_diag;
     long long* nb_ptr; int* nb_idx; double* nb_cdf; int* nb_nnz;
 };
@@ -154,6 +156,8 @@ struct ig_handle {
     IgClassTab* clstab; int rigid; SubX* subx; RowInfo* rinfo;
     int* cyc_frags;
     double *part_full; int n_part_full;
+    // cached per-contact records of the full likelihood (k_lnz_refresh / k_lnz_stream): 8 B x nnz per chain
+    int2* lnz_rec; unsigned char* row_dirty; int dp_bits; bool lnz_cache; int grid_lnz; long long lnz_pairs; int lnz_pad;
     double *part_zc; int* part_nc; int n_part_zc;
     int *d_nuniq, *d_nsub, *d_perm;
     unsigned long long* d_hist;
@@ -282,7 +286,7 @@ static int create_impl(const ig_config* cfg, const ig_level_data* data, ig_handl
             if (dev_alloc(h, &h->init_prev, nf) || dev_alloc(h, &h->init_next, nf) || dev_alloc(h, &h->orientable, nf)) return -2;
         }
         if (dev_alloc(h, &h->sc, 1) || dev_alloc(h, &h->desc, IG_MAX_CANDS)) return -2;
-        if (dev_alloc(h, &h->exz, (size_t)ns + 1) || dev_alloc(h, &h->exz_test, (size_t)ns + 1)) return -2;
+        if (dev_alloc(h, &h->exz, (size_t)ns + 3) || dev_alloc(h, &h->exz_test, (size_t)ns + 3)) return -2;   // + the two slots of k_lnz_stream
         h->n_chunks = (ns + IG_ROW_CHUNK - 1) / IG_ROW_CHUNK;
         if (dev_alloc(h, &h->chunk_cnt, (size_t)IG_MAX_CANDS * h->n_chunks)) return -2;
         h->rows_small = h->n_chunks <= IG_ROWS_SMALL_CHUNKS;
@@ -338,7 +342,8 @@ static int create_impl(const ig_config* cfg, const ig_level_data* data, ig_handl
         if (dev_alloc(h, &h->rowidx, (size_t)IG_MAX_CANDS * ns)) return -2;
         if (dev_alloc(h, &h->clstab, (size_t)IG_MAX_CANDS) || dev_alloc(h, &h->subx, (size_t)ns) || dev_alloc(h, &h->rinfo, (size_t)IG_MAX_CANDS * ns)) return -2;
         h->n_part_full = sms * 8;
-        if (dev_alloc(h, &h->part_full, h->n_part_full)) return -2;
+        if (dev_alloc(h, &h->part_full, 2 * (size_t)h->n_part_full)) return -2;
+        h->lnz_rec = nullptr; h->row_dirty = nullptr; h->lnz_cache = false; h->grid_lnz = sms * 4;
         if (dev_alloc(h, &h->part_out, h->n_part_full)) return -2;
         h->n_part_zc = sms * 2;
         if (dev_alloc(h, &h->part_zc, h->n_part_zc) || dev_alloc(h, &h->part_nc, h->n_part_zc)) return -2;
@@ -378,6 +383,27 @@ static int create_impl(const ig_config* cfg, const ig_level_data* data, ig_handl
             CK(h2d_sync(h->init_prev, data->init_prev, sizeof(int) * nf));
             CK(h2d_sync(h->init_next, data->init_next, sizeof(int) * nf));
             CK(h2d_sync(h->orientable, data->orientable, sizeof(int) * nf));
+        }
+        if (!parent) {
+            int mv = 0; long long tot = 0;
+            for (long long i = 0; i < h->nnz; i++) { mv = std::max(mv, data->val[i]); tot += data->val[i]; }
+            h->lvl->max_val = mv; h->lvl->val_total = (double)tot;
+        }
+        {   // packed likelihood records: table index (sub-fragment separation, or one of two special slots) in the low
+            // bits, the observed count above them; streamed in whole trips of 64 record pairs
+            h->dp_bits = 1;
+            while ((1 << h->dp_bits) < ns + 3) h->dp_bits++;
+            h->lnz_pairs = ((h->nnz + 1) / 2 + 63) / 64 * 64;
+            h->lnz_pad = (int)(2 * h->lnz_pairs - h->nnz);
+            h->lnz_cache = h->nnz > 0 && h->dp_bits <= 24 && (long long)h->lvl->max_val < (1LL << (32 - h->dp_bits));
+            if (const char* e = getenv("IG_LNZ_CACHE")) h->lnz_cache = h->lnz_cache && atoi(e) != 0;   // tests / A-B runs
+            if (h->lnz_cache) {
+                if (dev_alloc(h, &h->lnz_rec, (size_t)(2 * h->lnz_pairs)) || dev_alloc(h, &h->row_dirty, (size_t)ns)) return -2;
+                std::vector<int2> pad(h->lnz_pad);
+                for (auto& q : pad) { const float m1 = -1.0f; memcpy(&q.x, &m1, 4); q.y = ns + 2; }   // "skip" records
+                if (h->lnz_pad) CK(h2d_sync(h->lnz_rec + h->nnz, pad.data(), sizeof(int2) * pad.size()));
+                CK(cudaMemsetAsync(h->row_dirty, 1, (size_t)ns, h->stream));   // every row's records are built on first use
+            }
         }
         // factorial table on the device (same libdevice calls as the reference's factorial())
         double* d16;
@@ -441,7 +467,7 @@ extern "C" void ig_destroy(ig_handle* h) {
         delete h->lvl;
     }
     h->lvl = nullptr;
-    void* ptrs[] = {h->bitmap, h->cls16, h->pick_list, h->flat_cnt, h->flat_list, h->clstab, h->subx, h->rinfo, h->cyc_frags, h->live, h->part_out, h->part_c, h->table, h->table_len, h->rowidx, h->init_live, h->sub, h->coord, h->clen, h->row_ptr, h->cv,
+    void* ptrs[] = {h->lnz_rec, h->row_dirty, h->bitmap, h->cls16, h->pick_list, h->flat_cnt, h->flat_list, h->clstab, h->subx, h->rinfo, h->cyc_frags, h->live, h->part_out, h->part_c, h->table, h->table_len, h->rowidx, h->init_live, h->sub, h->coord, h->clen, h->row_ptr, h->cv,
                     h->init_prev, h->init_next, h->orientable, h->sc, h->desc, h->exz, h->exz_test, h->chunk_cnt,
                     h->rows, h->row_cnt, h->part_nz, h->part_z, h->part_i, h->part_full, h->part_zc, h->part_nc,
                     h->d_perm, h->d_hist};
@@ -575,7 +601,7 @@ static int refresh_current(ig_handle* h, cudaStream_t st, bool fork) {
         cudaEventRecord(h->ev_fork, h->stream);
         cudaStreamWaitEvent(st, h->ev_fork, 0);
     }
-    k_coords<<<h->n_part_zc, IG_THREADS, 0, st>>>(h->live, h->sub, h->coord, h->clen, h->ns, h->sc, mbar, 0, h->part_zc, h->part_nc, 1, h->subx);
+    k_coords<<<h->n_part_zc, IG_THREADS, 0, st>>>(h->live, h->sub, h->coord, h->clen, h->ns, h->sc, mbar, 0, h->part_zc, h->part_nc, 1, h->subx, h->row_dirty);
     k_reduce<<<1, 256, 0, st>>>(h->part_zc, h->n_part_zc, &h->sc->z_cur, h->part_nc, &h->sc->nintra_cur);
     if (fork) cudaEventRecord(h->ev_coords, st);
     if (h->profile) cudaEventRecord(h->ev[2], st);
@@ -724,7 +750,7 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands, int cycle = 0)
     }
     if (full) {
         k_coords<<<h->n_part_zc, IG_THREADS, 0, h->side>>>(h->live, h->sub, h->coord, h->clen, h->ns, h->sc, mbar, 0, h->part_zc,
-                                                          h->part_nc, 1, h->subx);
+                                                          h->part_nc, 1, h->subx, h->row_dirty);
         k_reduce<<<1, 256, 0, h->side>>>(h->part_zc, h->n_part_zc, &h->sc->z_cur, h->part_nc, &h->sc->nintra_cur);
         cudaEventRecord(h->ev_coords, h->side);
         if (h->profile && !h->capturing) cudaEventRecord(h->ev[2], h->side);
@@ -735,7 +761,7 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands, int cycle = 0)
         cudaEventRecord(h->ev_lnz, h->side);
     } else {
         k_commit_coords<<<std::min(h->n_part_zc, (h->ns + 255) / 256), 256, 0, h->side>>>(h->coord, h->clen, h->sc, h->rows, h->ns,
-                                                                                         h->table, h->table_len, h->live, h->sub, h->subx);
+                                                                                         h->table, h->table_len, h->live, h->sub, h->subx, h->row_dirty);
         cudaEventRecord(h->ev_coords, h->side);
         cudaEventRecord(h->ev_lnz, h->side);
     }
@@ -1095,13 +1121,24 @@ extern "C" int ig_full_likelihood(ig_handle* h, const float p8[8], int32_t use_s
     const int write = (use_stale_coords && h->coords_ever) ? 0 : 1;
     if (write) { h->coords_ever = true; h->coords_fresh = true; }
     k_coords<<<h->n_part_zc, IG_THREADS, 0, h->stream>>>(h->live, h->sub, h->coord, h->clen, h->ns, h->sc, mbar, 1,
-                                                        h->part_zc, h->part_nc, write, h->subx);
+                                                        h->part_zc, h->part_nc, write, h->subx, h->row_dirty);
     k_reduce<<<1, 256, 0, h->stream>>>(h->part_zc, h->n_part_zc, &h->sc->full_out[1], h->part_nc, &h->sc->full_nintra);
     cudaEventRecord(h->ev[2], h->stream);
-    k_full_lnz<<<h->n_part_full, IG_THREADS, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->ns, h->sc, mbar, 1,
-                                                            h->exz_test, h->part_full);
-    cudaEventRecord(h->ev[3], h->stream);
-    k_reduce<<<1, 256, 0, h->stream>>>(h->part_full, h->n_part_full, &h->sc->full_out[0], nullptr, nullptr);
+    if (h->lnz_cache && p.v_inter > 0.0f) {
+        // records of the rows whose coordinates were rewritten since the last call (+ circular contigs), then the flat pass
+        k_lnz_refresh<<<h->grid_lnz, IG_THREADS, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->ns, h->sc, mbar, 1, h->exz_test,
+                                                                 h->lnz_rec, h->row_dirty, h->dp_bits, h->part_full + h->grid_lnz);
+        k_lnz_stream<<<h->grid_lnz, IG_THREADS, 0, h->stream>>>(reinterpret_cast<const int4*>(h->lnz_rec), h->lnz_pairs, h->lnz_pad,
+                                                                h->lvl->val_total, h->sc, 1, h->exz_test, h->dp_bits, h->part_full);
+        cudaEventRecord(h->ev[3], h->stream);
+        k_reduce<<<1, 256, 0, h->stream>>>(h->part_full, 2 * h->grid_lnz, &h->sc->full_out[0], nullptr, nullptr);
+        h->n_launches += 1;
+    } else {
+        k_full_lnz<<<h->n_part_full, IG_THREADS, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->ns, h->sc, mbar, 1,
+                                                                h->exz_test, h->part_full);
+        cudaEventRecord(h->ev[3], h->stream);
+        k_reduce<<<1, 256, 0, h->stream>>>(h->part_full, h->n_part_full, &h->sc->full_out[0], nullptr, nullptr);
+    }
     if (launch_ok(h, "full_likelihood")) return -2;
     h->n_launches += 6;
     CK(cudaMemcpyAsync(h->h_sc, h->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, h->stream));

@@ -31,7 +31,7 @@ def main(rep, top=32):
         end = idx[n + 1] - 2 if n + 1 < len(idx) else len(src)
         fname = ""
         for back in range(start, max(start - 4, -1), -1):
-            if src[back].startswith('"File Name"'):
+            if src[back].startswith('"File Name"') or src[back].startswith('"File Path"'):
                 fname = src[back].split(",", 1)[1].strip('"').split("/")[-1]
                 break
         rows = list(csv.reader(src[start:end]))
@@ -56,11 +56,17 @@ def main(rep, top=32):
                     a[4][h[i]] = a[4].get(h[i], 0) + v
     ts, ti = sum(a[1] for a in agg.values()), sum(a[2] for a in agg.values())
     print(f"total warp instructions {ti}, samples {ts}")
+    per_file = {}
+    for (fn, ln), a in agg.items():
+        pf = per_file.setdefault(fn, [0, 0, 0])
+        pf[0] += a[2]; pf[1] += a[1]; pf[2] += a[3]
+    for fn, pf in sorted(per_file.items(), key=lambda kv: -kv[1][0]):
+        print(f"  file {fn:28s} inst={100 * pf[0] / max(ti, 1):5.1f}% samp={100 * pf[1] / max(ts, 1):5.1f}% thread-inst={pf[2]}")
     keys = set(k for k, _ in sorted(agg.items(), key=lambda kv: -kv[1][2])[:top]) | set(k for k, _ in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top])
     for ln in sorted(keys):
         a = agg[ln]
         ss = ",".join(f"{k.replace('stall_', '')}:{v}" for k, v in sorted(a[4].items(), key=lambda kv: -kv[1])[:2])
-        print(f"{ln[0][:18]:18s}{ln[1]:5d} inst={100 * a[2] / ti:5.1f}% samp={100 * a[1] / max(ts, 1):5.1f}% lanes={a[3] / max(a[2], 1):4.1f} [{ss}] | {a[0].strip()[:100]}")
+        print(f"{ln[0][:20]:20s}{ln[1]:5d} inst={100 * a[2] / ti:5.1f}% samp={100 * a[1] / max(ts, 1):5.1f}% lanes={a[3] / max(a[2], 1):4.1f} [{ss}] | {a[0].strip()[:100]}")
 
 
 if __name__ == "__main__":

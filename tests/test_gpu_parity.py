@@ -604,3 +604,77 @@ def test_streaming_path_random_scaffolds_with_circular_contigs(built, monkeypatc
         assert np.array_equal(res[0][0] != 0, res[1][0] != 0)
         assert np.max(np.abs(res[0][0] - res[1][0])) < 1e-6, (it, a, b, np.max(np.abs(res[0][0] - res[1][0])))
     ref.free_gpu(); st.free_gpu()
+
+
+def _nuis_params(p8, i):
+    q = np.array(p8, dtype=np.float32).copy()
+    q[3] += np.float32(0.002 * (i % 5))        # slope
+    q[5] *= np.float32(1.0 + 0.05 * (i % 3))   # d_max: moves contacts between the queued and the floor class
+    q[6] *= np.float32(1.0 + 0.01 * i)         # fact
+    return q
+
+
+@pytest.mark.parametrize("workload,steps", [("toy", 150), ("T", 300)])
+def test_cached_likelihood_records_equal_the_gather_kernel(built, workload, steps, monkeypatch):
+    """The nuisance likelihood from the cached per-contact records (k_lnz_refresh + k_lnz_stream, the default) against the
+    row-by-row gather kernel (k_full_lnz, IG_LNZ_CACHE=0) along one trajectory: after every step (only the rows of the
+    contigs the last move touched are rebuilt; the coordinates are the STALE ones of quirk Q5 in both), for several test
+    parameter sets per step (the second and third run on a clean cache), after a bomb and after a state upload."""
+    from instagraal_b200.synth import make_workload
+    level = make_workload(workload) if workload == "T" else make_level(WORKLOADS[workload])
+    a = GpuImpl(level)
+    monkeypatch.setenv("IG_LNZ_CACHE", "0")
+    b = GpuImpl(level)
+    monkeypatch.delenv("IG_LNZ_CACHE")
+    for impl in (a, b):
+        impl.set_params(P8_RIPPE)
+        np.random.seed(5)
+        impl.s.bomb_the_genome()
+    rng = np.random.RandomState(9)
+    worst = 0.0
+    t = 0
+    for f in rng.permutation(level.n_frags)[:steps]:
+        f = int(f)
+        cands = sorted(int(c) for c in rng.choice(level.n_frags, 4, replace=False) if c != f)
+        ra, rb = a.step(f, cands), b.step(f, cands)
+        assert (int(ra["op"]), int(ra["B"])) == (int(rb["op"]), int(rb["B"])) and float(ra["o"]) == float(rb["o"])
+        for i in range(3 if t % 7 == 0 else 1):
+            q = _nuis_params(P8_RIPPE, t + i)
+            va, vb = a.eval_nuisance(q), b.eval_nuisance(q)
+            worst = max(worst, abs(va - vb) / abs(vb))
+            assert abs(va - vb) <= 1e-11 * abs(vb), (t, i, va, vb)
+        if t == steps // 2:   # state upload in mid-run: every record is rebuilt from fresh coordinates
+            st = a.get_state()
+            for impl in (a, b):
+                impl.set_state(st)
+        t += 1
+    a.s.free_gpu(); b.s.free_gpu()
+
+
+def test_cached_likelihood_records_with_circular_contigs(built, monkeypatch):
+    """rows of circular contigs never enter the record stream: k_lnz_refresh evaluates them with the generic routine on
+    every call.  Random scaffolds with circular contigs, fresh and repeated evaluations, d == 2 and d != 2."""
+    from oracle.fuzz import random_state
+    level = make_level(WORKLOADS["micro"])
+    a = GpuImpl(level)
+    monkeypatch.setenv("IG_LNZ_CACHE", "0")
+    b = GpuImpl(level)
+    monkeypatch.delenv("IG_LNZ_CACHE")
+    rng = np.random.RandomState(3)
+    for it in range(10):
+        p8 = P8.copy()
+        if it % 2:
+            p8[4] = 2.37
+        st = random_state(level.n_frags, rng, p_circ=0.5)
+        for k in ("len_bp", "sub_len"):
+            st[k] = np.asarray(level.S_o_A_frags[k], dtype=np.int32).copy()
+        st = _rebuild_offsets(st)
+        st13 = np.stack([st[k] for k in FIELDS13]).astype(np.int32)
+        for impl in (a, b):
+            impl.set_params(p8)
+            impl.set_state(st13)
+        for i in range(3):
+            q = _nuis_params(p8, it + i)
+            va, vb = a.eval_nuisance(q), b.eval_nuisance(q)
+            assert abs(va - vb) <= 1e-11 * abs(vb), (it, i, va, vb)
+    a.s.free_gpu(); b.s.free_gpu()
