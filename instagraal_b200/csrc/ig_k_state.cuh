@@ -274,15 +274,22 @@ k_lnz_stream(const int4* __restrict__ rec2, long long n_pairs, int n_pad, double
         }
         __syncwarp();
     };
-    for (long long base = wg * 64; base < n_pairs; base += nw * 64) {   // n_pairs is a multiple of 64: whole trips only
-        const int4 ra = __ldcs(rec2 + base + lane);        // streamed once per call: evict first
-        const int4 rb = __ldcs(rec2 + base + 32 + lane);
+    // n_pairs is a multiple of 64: whole trips only; the next trip's records are in flight while this one is evaluated
+    const int4 skip2 = make_int4(__float_as_int(-1.0f), 0, __float_as_int(-1.0f), 0);
+    long long base = wg * 64;
+    int4 ra = skip2, rb = skip2;
+    if (base < n_pairs) { ra = __ldcs(rec2 + base + lane); rb = __ldcs(rec2 + base + 32 + lane); }   // streamed once per call: evict first
+    for (; base < n_pairs; base += nw * 64) {
+        const long long nxt = base + nw * 64;
+        int4 na = skip2, nb = skip2;
+        if (nxt < n_pairs) { na = __ldcs(rec2 + nxt + lane); nb = __ldcs(rec2 + nxt + 32 + lane); }
         const float e0 = __ldg(&exz_tab[(unsigned)ra.y & dpmask]), e1 = __ldg(&exz_tab[(unsigned)ra.w & dpmask]);
         const float e2 = __ldg(&exz_tab[(unsigned)rb.y & dpmask]), e3 = __ldg(&exz_tab[(unsigned)rb.w & dpmask]);
         const float s0 = __int_as_float(ra.x), s1 = __int_as_float(ra.z), s2 = __int_as_float(rb.x), s3 = __int_as_float(rb.z);
         append((s0 > 0.0f) && (s0 < p.d_max), ra.x, (unsigned)ra.y, (s1 > 0.0f) && (s1 < p.d_max), ra.z, (unsigned)ra.w);
         append((s2 > 0.0f) && (s2 < p.d_max), rb.x, (unsigned)rb.y, (s3 > 0.0f) && (s3 < p.d_max), rb.z, (unsigned)rb.w);
         acc_exz += ((double)e0 + (double)e1) + ((double)e2 + (double)e3);
+        ra = na; rb = nb;
     }
     if (lane < qn) eval(myq[lane]);
     // the queued contacts are not floor contacts: take them out of the closed-form floor sum (block 0 adds its constants)
