@@ -162,6 +162,8 @@ def single_chain_passes(s, level, args, torch, flush, rank):
             out.extend(int(f) for f in frs)
         return out[:n]
 
+    accepted = [0]
+
     def step_loop(n, nuisance=False, flushing=True):
         for i, f in enumerate(frag_stream(n)):
             if flush is not None and flushing:
@@ -169,7 +171,7 @@ def single_chain_passes(s, level, args, torch, flush, rank):
                 torch.cuda.current_stream().synchronize()   # the flush runs on torch's stream, the step on the library's
             s.step_sampler(f, 5, dt)
             if nuisance:
-                s.step_nuisance_parameters(dt, i, n)
+                accepted[0] += int(s.step_nuisance_parameters(dt, i, n)[6])
 
     res = {}
     # ---- pass 1: device-timed (value of the single-chain configuration)
@@ -214,6 +216,8 @@ def single_chain_passes(s, level, args, torch, flush, rank):
     res["prop_nuis"], res["dev_ms_nuis_steps"] = stn["proposals"], stn["ms_step"]
     res["nuis_dev_ms"], res["nuis_calls"] = nuis_stats(s)
     res["n_nuis"] = n_nuis
+    res["nuis_accepted"] = accepted[0]
+    res["nuis_overlapped"] = int(getattr(s, "n_nuis_overlapped", 0))
     s.set_param_simu(p_keep)   # the random walk of the nuisance parameters must not leak into the next passes
     s.param_simu_test = s.param_simu
     return res
@@ -389,6 +393,7 @@ def run_ours(args):
                 "with_nuisance": {"e2e_value": r["prop_nuis"] / r["t_nuis"], "ms_per_step_e2e": r["t_nuis"] / r["n_nuis"] * 1e3,
                                   "mcmc_cycle_s_e2e": r["t_nuis"] / r["n_nuis"] * level.n_frags,
                                   "k_full_lnz_ms_per_call": nuis_ms, "steps": r["n_nuis"],
+                                  "proposals_accepted": r["nuis_accepted"], "proposals_prepared_during_the_step": r["nuis_overlapped"],
                                   "note": "step_sampler + step_nuisance_parameters per step (IG:242-252): host fsolve + full likelihood under the test parameters"},
                 "without_nuisance_mcmc_cycle_s_e2e": r["t_e2e"] / args.steps * level.n_frags,
                 "kernels": {

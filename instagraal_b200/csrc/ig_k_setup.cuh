@@ -41,8 +41,10 @@ __global__ void k_cand_setup(const FragRec* __restrict__ live, DevScalars* sc, I
         c.up_b = max(0, pfb - B.sub_len); c.down_b = min(B.sub_l_cont - 1, pfb + B.sub_len);
         c.n_rows = 0; c.n_sub = 0; c.row_hi = -1;
         sc->ticket_cuts[k] = 0; sc->ticket_rows[k] = 0;
-        // streaming scoring path: not for circular contigs (every class pair may change there: k_score's generic route)
-        sc->use_stream[k] = (stream_mode && A.circ == 0 && B.circ == 0) ? 1 : 0;
+        // streaming scoring path: not for circular contigs (every class pair may change there: k_score's generic route),
+        // and only for candidates of at most stream_mode affected rows (their picks must fit the list)
+        const int rows_k = A.sub_l_cont + (A.id_c == B.id_c ? 0 : B.sub_l_cont);
+        sc->use_stream[k] = (stream_mode && A.circ == 0 && B.circ == 0 && rows_k <= stream_mode) ? 1 : 0;
         if (stream_mode) sc->flat_segtotal[k] = 0;   // pick-list fill
     }
     if (stream_mode && k >= n && k < IG_MAX_CANDS) { sc->use_stream[k] = 0; sc->flat_segtotal[k] = 0; }

@@ -201,17 +201,19 @@ k_lnz_refresh(const long long* __restrict__ row_ptr, const int2* __restrict__ cv
     const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nw = (gridDim.x * blockDim.x) >> 5;
     double acc = 0.0;
-    for (int base = wg * 32; base < ns; base += nw * 32) {
-        // 32 rows looked at together: which of them need work?
-        const int r_l = base + lane;
+    // warp w owns the rows r = w (mod nw): the rows of one contig are neighbours in r, so a move's dirty rows land on as many
+    // different warps as there are; each warp looks at 32 of its rows at a time (flags read in parallel)
+    for (int j0 = 0; wg + (long long)j0 * nw < ns; j0 += 32) {
+        const long long r_ll = wg + (long long)(j0 + lane) * nw;
+        const int r_l = r_ll < ns ? (int)r_ll : -1;
         bool need = false;
-        if (r_l < ns) {
+        if (r_l >= 0) {
             const bool circ = coord[r_l].s_tot != 0;
             need = (row_ptr[r_l] != row_ptr[r_l + 1]) && (circ || row_dirty[r_l] != 0);
             if (!need && row_dirty[r_l]) row_dirty[r_l] = 0;   // empty row
         }
         for (unsigned todo = __ballot_sync(0xffffffffu, need); todo; todo &= todo - 1) {
-            const int r = base + __ffs(todo) - 1;
+            const int r = wg + (j0 + __ffs(todo) - 1) * nw;
             const long long b = row_ptr[r], e = row_ptr[r + 1];
             const CoordRec ci = coord[r];
             const bool circ = ci.s_tot != 0;

@@ -120,6 +120,7 @@ struct LevelBlock {
     int refs;
     int max_val;   // largest observed count of the level (decides whether the packed likelihood records can hold it)
     double val_total;   // sum of the observed counts of every stored contact
+    long long max_row_len;   // longest CSR row (sizes the pick list of the streaming scoring path)
     int* sym_diag;
     long long* nb_ptr; int* nb_idx; double* nb_cdf; int* nb_nnz;
 };
@@ -138,6 +139,7 @@ struct ig_handle {
     bool prefetch;  // the level's arrays fit the L2 comfortably: prefetch them at the start of a step
     bool streaming; // streaming scoring path (k_stream + k_eval_flat<true>): large levels with rigid_pruning != 0
     unsigned* bitmap; int bitmap_words; unsigned short* cls16; FlatRec* pick_list; size_t pick_cap; int stream_smem;
+    int stream_rows_max;   // candidates with at most this many affected rows take the streaming path (exact mode: bounded by the pick list)
     FragRec *live, *init_live;
     SubRec* sub;
     CoordRec* coord;
@@ -166,10 +168,12 @@ struct ig_handle {
     bool params_set, coords_fresh, coords_ever; int init_max_label;
     long long label_hi = 0;          // upper bound of the contig labels in use (2 new ones per applied move), see labels_guard
     bool incr_valid; int refresh_every; long long steps_since_full;
+    bool vinter_pos;  // live v_inter > 0 (the per-contact records assume it)
+    bool lnz_stale;   // the parameters changed since lnz_full / z_cur were computed (the scaffold bookkeeping is intact)
     double* part_out;
     int gs_div, sparse_div, grid_split;
     long long last_n_full;
-    cudaGraphExec_t graph[4][IG_MAX_CANDS + 1];   // [full + 2 * cycle][candidates in the grid]
+    cudaGraphExec_t graph[6][IG_MAX_CANDS + 1];   // [step kind + 3 * cycle][candidates in the grid]
     int* cyc_in; CycleOut* cyc_out; int cyc_cap; bool graph_failed, capturing, use_graph; long long n_full;
     int pending_steps;   // steps enqueued by an asynchronous cycle call and not collected yet
     // measurement (CUDA events on the launching stream)
@@ -241,7 +245,7 @@ static int create_impl(const ig_config* cfg, const ig_level_data* data, ig_handl
     h->cfg = *cfg; h->nf = cfg->n_frags; h->ns = cfg->n_sub_frags; h->nnz = cfg->nnz;
     h->rigid = cfg->rigid_pruning ? 1 : 0;
     h->params_set = false; h->coords_fresh = false; h->coords_ever = false;
-    h->incr_valid = false; h->refresh_every = 4096; h->steps_since_full = 0;
+    h->incr_valid = false; h->lnz_stale = false; h->refresh_every = 4096; h->steps_since_full = 0;
     h->gs_div = 4;
     h->sparse_div = 4;
     h->grid_split = 0;
@@ -304,15 +308,26 @@ static int create_impl(const ig_config* cfg, const ig_level_data* data, ig_handl
         h->bitmap = nullptr; h->cls16 = nullptr; h->pick_list = nullptr;
         h->bitmap_words = (ns + 31) / 32;
         h->stream_smem = h->bitmap_words * (int)sizeof(unsigned);
-        h->streaming = !h->flat && h->rigid != 0 && h->stream_smem <= 200 * 1024;
+        // rigid pruning: every linear candidate (a few per cent of its contacts are picked).  Reference-faithful mode: almost
+        // every selected contact is a pick, so only candidates whose contacts are sure to fit the pick list take it (the
+        // mid-assembly regime: two contigs of a few hundred sub-fragments, where the row-per-warp kernel is all latency)
+        h->streaming = !h->flat && h->stream_smem <= 200 * 1024;
         if (const char* e = getenv("IG_STREAM")) h->streaming = h->streaming && atoi(e) != 0;   // experiments / tests
-        if (getenv("IG_FORCE_STREAM") && h->rigid != 0 && h->stream_smem <= 200 * 1024) {   // tests: small levels through the streaming path
+        if (getenv("IG_FORCE_STREAM") && h->stream_smem <= 200 * 1024) {   // tests: small levels through the streaming path
             h->streaming = true; h->flat = false;
         }
+        h->stream_rows_max = 0;
         if (h->streaming) {
             h->rows_small = false;   // the two-pass row list also writes the bitmap and the class words
             h->pick_cap = std::min<size_t>((size_t)h->nnz + 64, (size_t)2 << 20);   // 64-byte records: 128 MB per candidate slot at most
             if (const char* e = getenv("IG_PICK_CAP")) h->pick_cap = (size_t)std::max(64, atoi(e));
+            if (!parent) {
+                long long mr = 0;
+                for (int r = 0; r < ns; r++) mr = std::max(mr, (long long)(data->row_ptr[r + 1] - data->row_ptr[r]));
+                h->lvl->max_row_len = mr;
+            }
+            h->stream_rows_max = h->rigid ? INT32_MAX : (int)std::min<long long>(INT32_MAX, (long long)h->pick_cap / std::max<long long>(h->lvl->max_row_len, 1));
+            if (const char* e = getenv("IG_STREAM_ROWS")) h->stream_rows_max = atoi(e);   // experiments
             if (dev_alloc(h, &h->bitmap, (size_t)IG_MAX_CANDS * h->bitmap_words) || dev_alloc(h, &h->cls16, (size_t)IG_MAX_CANDS * ns) ||
                 dev_alloc(h, &h->pick_list, (size_t)IG_MAX_CANDS * h->pick_cap)) return -2;
             CK(cudaFuncSetAttribute(k_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, h->stream_smem));
@@ -476,7 +491,7 @@ extern "C" void ig_destroy(ig_handle* h) {
     if (h->h_small) cudaFreeHost(h->h_small);
     for (int i = 0; i < 6; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 16; i++) if (h->evk[i]) cudaEventDestroy(h->evk[i]);
-    for (int i = 0; i < 4; i++) for (int j = 0; j <= IG_MAX_CANDS; j++) if (h->graph[i][j]) cudaGraphExecDestroy(h->graph[i][j]);
+    for (int i = 0; i < 6; i++) for (int j = 0; j <= IG_MAX_CANDS; j++) if (h->graph[i][j]) cudaGraphExecDestroy(h->graph[i][j]);
     if (h->cyc_in) cudaFree(h->cyc_in);
     if (h->cyc_out) cudaFree(h->cyc_out);
     if (h->side) cudaStreamDestroy(h->side);
@@ -511,7 +526,8 @@ extern "C" int ig_set_params(ig_handle* h, const float p8[8]) {
     if (launch_ok(h, "set_params")) return -2;
     CK(cudaStreamSynchronize(h->stream));
     h->params_set = true;
-    h->incr_valid = false;  // lnz_full / z_cur depend on the parameters
+    h->vinter_pos = p.v_inter > 0.0f;
+    h->lnz_stale = true;  // lnz_full / z_cur depend on the parameters: the next step recomputes them (step_kind)
     return 0;
 }
 
@@ -676,7 +692,7 @@ static int score_candidates(ig_handle* h, int a, const int32_t* cands, int n, in
     for (int i = 0; i < IG_MAX_CANDS; i++) hs[2 + i] = i < n ? cands[i] : 0;
     CK(cudaMemcpyAsync(&h->sc->n_cands, hs, (2 + IG_MAX_CANDS) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     const FragRec* live = h->live;
-    k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, first_flip_eject, nullptr, h->streaming ? 1 : 0);
+    k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, first_flip_eject, nullptr, h->streaming ? h->stream_rows_max : 0);
     k_find_cuts<<<dim3((h->nf + 255) / 256, n), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc, h->clstab);
     k_classes<<<n, IG_N_OPS * 32, 0, h->stream>>>(h->sc, h->desc, h->clstab, h->rigid, h->cfg.mean_sub_len_kb);
     if (overlap) cudaStreamWaitEvent(h->stream, h->ev_coords, 0);
@@ -748,7 +764,25 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands, int cycle = 0)
         L.cnt = c;
         k_prefetch_l2<<<h->n_part_zc, 256, 0, h->pf>>>(L);
     }
-    if (full) {
+    if (full == 2) {
+        // parameters changed, scaffold bookkeeping intact (an accepted nuisance proposal): coordinates as in the incremental
+        // step (k_commit_coords flags the rows of the previous move), zero terms and the full non-zero likelihood recomputed
+        // under the new parameters -- the latter from the cached per-contact records (k_lnz_refresh + k_lnz_stream)
+        k_commit_coords<<<std::min(h->n_part_zc, (h->ns + 255) / 256), 256, 0, h->side>>>(h->coord, h->clen, h->sc, h->rows, h->ns,
+                                                                                         h->table, h->table_len, h->live, h->sub, h->subx, h->row_dirty);
+        k_coords<<<h->n_part_zc, IG_THREADS, 0, h->side>>>(h->live, h->sub, h->coord, h->clen, h->ns, h->sc, mbar, 0, h->part_zc,
+                                                          h->part_nc, 0, h->subx, nullptr);
+        k_reduce<<<1, 256, 0, h->side>>>(h->part_zc, h->n_part_zc, &h->sc->z_cur, h->part_nc, &h->sc->nintra_cur);
+        cudaEventRecord(h->ev_coords, h->side);
+        if (h->profile && !h->capturing) cudaEventRecord(h->ev[2], h->side);
+        k_lnz_refresh<<<h->grid_lnz, IG_THREADS, 0, h->side>>>(h->row_ptr, h->cv, h->coord, h->clen, h->ns, h->sc, mbar, 0, h->exz,
+                                                               h->lnz_rec, h->row_dirty, h->dp_bits, h->part_full + h->grid_lnz);
+        k_lnz_stream<<<h->grid_lnz, IG_THREADS, 0, h->side>>>(reinterpret_cast<const int4*>(h->lnz_rec), h->lnz_pairs, h->lnz_pad,
+                                                              h->lvl->val_total, h->sc, 0, h->exz, h->dp_bits, h->part_full);
+        if (h->profile && !h->capturing) cudaEventRecord(h->ev[3], h->side);
+        k_reduce<<<1, 256, 0, h->side>>>(h->part_full, 2 * h->grid_lnz, &h->sc->lnz_full, nullptr, nullptr);
+        cudaEventRecord(h->ev_lnz, h->side);
+    } else if (full) {
         k_coords<<<h->n_part_zc, IG_THREADS, 0, h->side>>>(h->live, h->sub, h->coord, h->clen, h->ns, h->sc, mbar, 0, h->part_zc,
                                                           h->part_nc, 1, h->subx, h->row_dirty);
         k_reduce<<<1, 256, 0, h->side>>>(h->part_zc, h->n_part_zc, &h->sc->z_cur, h->part_nc, &h->sc->nintra_cur);
@@ -767,7 +801,7 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands, int cycle = 0)
     }
     const FragRec* live = h->live;
     IG_MARK(0);
-    k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, 1, cycle ? h->cyc_in : nullptr, h->streaming ? 1 : 0);
+    k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, 1, cycle ? h->cyc_in : nullptr, h->streaming ? h->stream_rows_max : 0);
     IG_MARK(1);
     k_find_cuts<<<dim3((h->nf + 255) / 256, n), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc, h->clstab);
     cudaEventRecord(h->ev_cuts, h->stream);
@@ -807,9 +841,20 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands, int cycle = 0)
 }
 #define IG_LAUNCHES_FULL 15
 #define IG_LAUNCHES_INCR 12
+#define IG_LAUNCHES_LITE 17
+// 0: incremental step; 1: coordinates and likelihood sums from scratch (scaffold replaced from outside, periodic refresh);
+// 2: likelihood sums only (parameters changed; needs the per-contact records and v_inter > 0, which the records assume)
+static int step_kind(const ig_handle* h) {
+    if (!h->incr_valid || (h->refresh_every > 0 && h->steps_since_full >= h->refresh_every)) return 1;
+    if (h->lnz_stale) return (h->lnz_cache && h->vinter_pos) ? 2 : 1;
+    return 0;
+}
+static int step_launches(const ig_handle* h, int kind) {
+    return (kind == 2 ? IG_LAUNCHES_LITE : kind ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR) - (h->rigid ? 1 : 0) + (h->prefetch ? 1 : 0) - (h->rows_small ? 1 : 0) + (h->flat ? 1 : 0) + (h->streaming ? 2 : 0);
+}
 
 static int get_graph(ig_handle* h, int full, cudaGraphExec_t* out, int cycle, int n) {
-    cudaGraphExec_t& ge = h->graph[full + 2 * cycle][n];
+    cudaGraphExec_t& ge = h->graph[full + 3 * cycle][n];
     if (!ge && !h->graph_failed) {
         cudaGraph_t g = nullptr;
         h->capturing = true;
@@ -839,7 +884,7 @@ extern "C" int ig_step(ig_handle* h, int32_t id_frag, const int32_t* cands, int3
     int* hs = h->h_small;
     hs[0] = n_cands; hs[1] = id_frag;
     for (int i = 0; i < IG_MAX_CANDS; i++) hs[2 + i] = i < n_cands ? cands[i] : 0;
-    const int full = (!h->incr_valid || (h->refresh_every > 0 && h->steps_since_full >= h->refresh_every)) ? 1 : 0;
+    const int full = step_kind(h);
     cudaGraphExec_t ge = nullptr;
     if (h->use_graph && !h->profile) get_graph(h, full, &ge, 0, n_cands);
     cudaEventRecord(h->ev[0], h->stream);
@@ -850,10 +895,10 @@ extern "C" int ig_step(ig_handle* h, int32_t id_frag, const int32_t* cands, int3
     }
     cudaEventRecord(h->ev[1], h->stream);
     CK(cudaStreamSynchronize(h->stream));
-    h->n_launches += (full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR) - (h->rigid ? 1 : 0) + (h->prefetch ? 1 : 0) - (h->rows_small ? 1 : 0) + (h->flat ? 1 : 0) + (h->streaming ? 2 : 0);
+    h->n_launches += step_launches(h, full);
     h->steps_since_full = full ? 1 : h->steps_since_full + 1;
-    h->n_full += full;
-    h->incr_valid = true;
+    h->n_full += full ? 1 : 0;
+    h->incr_valid = true; h->lnz_stale = false;
     h->coords_fresh = false; h->coords_ever = true;
     int rc = fetch_result(h, n_cands, cands, out, true, false);
     if (rc) return rc;
@@ -880,7 +925,7 @@ static int cycle_buffers(ig_handle* h, int n_steps) {
         if (h->cyc_out) cudaFree(h->cyc_out);
         if (h->cyc_frags) cudaFree(h->cyc_frags);
         h->cyc_in = nullptr; h->cyc_out = nullptr; h->cyc_frags = nullptr; h->cyc_cap = 0;
-        for (int i = 2; i < 4; i++) for (int j = 0; j <= IG_MAX_CANDS; j++) if (h->graph[i][j]) { cudaGraphExecDestroy(h->graph[i][j]); h->graph[i][j] = nullptr; }  // pointers are baked in
+        for (int i = 3; i < 6; i++) for (int j = 0; j <= IG_MAX_CANDS; j++) if (h->graph[i][j]) { cudaGraphExecDestroy(h->graph[i][j]); h->graph[i][j] = nullptr; }  // pointers are baked in
         if (dev_alloc(h, &h->cyc_in, (size_t)n_steps * (2 + IG_MAX_CANDS)) || dev_alloc(h, &h->cyc_out, (size_t)n_steps) ||
             dev_alloc(h, &h->cyc_frags, (size_t)n_steps)) return -2;
         h->cyc_cap = n_steps;
@@ -894,15 +939,15 @@ static int cycle_buffers(ig_handle* h, int n_steps) {
 // slots the step's grid is built for
 static int enqueue_plan_step(ig_handle* h, int grid_n) {
     if (int rc = labels_guard(h)) return rc;
-    const int full = (!h->incr_valid || (h->refresh_every > 0 && h->steps_since_full >= h->refresh_every)) ? 1 : 0;
+    const int full = step_kind(h);
     cudaGraphExec_t ge = nullptr;
     if (h->use_graph) get_graph(h, full, &ge, 1, grid_n);
     if (ge) { CK(cudaGraphLaunch(ge, h->stream)); }
     else if (enqueue_step(h, full, grid_n, 1)) return -2;
     h->steps_since_full = full ? 1 : h->steps_since_full + 1;
-    h->n_full += full;
-    h->incr_valid = true;
-    h->n_launches += (full ? IG_LAUNCHES_FULL : IG_LAUNCHES_INCR) - (h->rigid ? 1 : 0) + (h->prefetch ? 1 : 0) - (h->rows_small ? 1 : 0) + (h->flat ? 1 : 0) + (h->streaming ? 2 : 0);
+    h->n_full += full ? 1 : 0;
+    h->incr_valid = true; h->lnz_stale = false;
+    h->n_launches += step_launches(h, full);
     return 0;
 }
 static int begin_plan(ig_handle* h) {

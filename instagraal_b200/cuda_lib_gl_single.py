@@ -170,6 +170,13 @@ class sampler:
         self.mean_length_contigs = None
         self.n_proposals_scored = 0
         self._last_dist = 1.0
+        # step_nuisance_parameters' proposal (host RNG draws + scipy fsolve, ~0.35 ms) is prepared while the GPU scores the
+        # step before it; results and RNG stream are unchanged (see _speculate_nuisance).  False = strictly in place.
+        self.overlap_nuisance_proposal = True
+        self._nuis_follows = False
+        self._spec = None
+        self._spec_pool = None
+        self.n_nuis_overlapped = 0
         self.modification_str = [  # CL:1601-1620
             "eject frag", "flip frag", "pop out split insert @ left or 1", "pop out split insert @ left or -1",
             "pop out split insert @ right or 1", "pop out split insert @ right or -1", "pop out insert @ right or 1",
@@ -203,6 +210,7 @@ class sampler:
         s.all_scores = np.zeros(0)
         s.n_proposals_scored = 0
         s.likelihood_t = None
+        s._nuis_follows, s._spec, s._spec_pool = False, None, None
         s._res = L.ig_step_result()
         s._res_scores = np.frombuffer(s._res, dtype=np.float64, count=L.IG_MAX_CANDS * L.IG_N_OPS, offset=L.ig_step_result.scores.offset)
         s._res_nuniq = np.frombuffer(s._res, dtype=np.int32, count=L.IG_MAX_CANDS, offset=L.ig_step_result.n_uniq.offset)
@@ -308,6 +316,9 @@ class sampler:
         self.gpu_vect_frags.copy_from_gpu()
 
     def free_gpu(self):
+        if getattr(self, "_spec_pool", None) is not None:
+            self._spec_pool.shutdown(wait=True)
+            self._spec_pool = None
         if self._h is not None:
             L.lib().ig_destroy(self._h)
             self._h = None
@@ -387,7 +398,15 @@ class sampler:
             return (self.likelihood_t, self._last_dist, -1, int(id_frag), self.mean_length_contigs, self.n_contigs)
         self._cand_buf[:n] = self.candidates
         res = self._res
+        fut = None
+        if self._nuis_follows and self.param_simu is not None:   # the previous call was a nuisance step: expect the next one
+            if self._spec_pool is None:
+                from concurrent.futures import ThreadPoolExecutor
+                self._spec_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="ig-nuisance")
+            fut = self._spec_pool.submit(self._speculate_nuisance, np.random.get_state())
+        self._nuis_follows = False
         rc = self._ig_step(self._h, int(id_frag), self._cand_ptr, n, self._res_ref)
+        self._spec = fut.result() if fut is not None else None
         if rc != 0:
             L.check(self._h, rc, "ig_step")
         self.all_scores = self._res_scores[:self.n_tmp_struct * n].copy()
@@ -590,8 +609,10 @@ class sampler:
     def temperature(self, t, n_step):
         return 1.0
 
-    def step_nuisance_parameters(self, dt, t, n_step):
-        """CL:2961-3051 (same host RNG calls, same scipy fsolve)."""
+    def _nuisance_proposal(self):
+        """First half of step_nuisance_parameters (CL:2961-3032): the random-walk proposal of one of the four nuisance
+        parameters and the d_max that goes with it (scipy fsolve).  Depends on the live parameters and the host RNG
+        only -- not on the scaffold -- which is what lets step_sampler compute it while the GPU scores the step."""
         curr_param = np.copy(self.param_simu)
         kuhn, lm, c1, slope, d, d_max, fact, d_nuc = curr_param[0]
         self.sigma_fact = 10 ** (np.log10(fact) - 2)
@@ -627,7 +648,41 @@ class sampler:
             new_d_max = opti.estimate_max_dist_intra_nuis(test_param, new_d_nuc, d_max)
             c1 = np.float32((0.53 * np.power(lm / kuhn, slope)) * np.power(kuhn, -3))
             out_test_param = [(kuhn, lm, c1, slope, d, new_d_max, fact, new_d_nuc)]
-        out_test_param = np.array(out_test_param, dtype=PARAM_SIMU_RIPPE)
+        return np.array(out_test_param, dtype=PARAM_SIMU_RIPPE)
+
+    # -- the proposal of the NEXT step_nuisance_parameters call, computed on a worker thread while ig_step blocks (the
+    #    ctypes call releases the GIL).  The reference's RNG order is: neighbours of step t, proposal draws of the nuisance
+    #    step t, its acceptance draw, neighbours of step t + 1 ...  The worker runs the proposal draws from the generator
+    #    state left by the neighbour draw, records the state after them and PUTS THE FIRST STATE BACK; the nuisance step
+    #    takes the prepared proposal (and jumps to the recorded state) only if the generator and the parameters are still
+    #    exactly where the worker found them -- otherwise (the caller drew numbers in between, or never calls the nuisance
+    #    step) nothing has happened and the proposal is computed in place as before.
+    def _speculate_nuisance(self, st0):
+        try:
+            key = self.param_simu.tobytes()
+            prop = self._nuisance_proposal()
+            st1 = np.random.get_state()
+            return (st0, st1, key, prop)
+        except Exception:
+            return None
+        finally:
+            np.random.set_state(st0)
+
+    @staticmethod
+    def _same_rng_state(a, b):
+        return a[2] == b[2] and a[3] == b[3] and a[4] == b[4] and a[0] == b[0] and np.array_equal(a[1], b[1])
+
+    def step_nuisance_parameters(self, dt, t, n_step):
+        """CL:2961-3051 (same host RNG calls, same scipy fsolve)."""
+        spec, self._spec = self._spec, None
+        self._nuis_follows = self.overlap_nuisance_proposal
+        if (spec is not None and spec[2] == self.param_simu.tobytes()
+                and self._same_rng_state(spec[0], np.random.get_state())):
+            np.random.set_state(spec[1])
+            out_test_param = spec[3]
+            self.n_nuis_overlapped += 1
+        else:
+            out_test_param = self._nuisance_proposal()
         self.param_simu_test = out_test_param
         self.likelihood_nuis = self.eval_likelihood_4_nuisance()
         F_t = self.temperature(t, n_step)

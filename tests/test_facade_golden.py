@@ -25,14 +25,18 @@ CASES = {  # oracle/make_golden.py CASES: (n_cycles, nuis_after)
 }
 
 
+@pytest.mark.parametrize("overlap", [True, False])
 @pytest.mark.parametrize("name", GOLDEN_CASES)
-def test_facade_replays_reference_driver_loop(built, name):
+def test_facade_replays_reference_driver_loop(built, name, overlap):
+    """overlap = the facade prepares the nuisance proposal (RNG draws + fsolve) on a worker thread while the GPU scores
+    the step before it (the default) / strictly in place: same stream, same values either way."""
     from test_gpu_parity import make_sampler
     g = load_golden(name)
     level = make_level(WORKLOADS[str(g["workload"])])
     n_cycles, nuis_after = CASES[name]
     np.random.seed(int(g["seed"]))
     s = make_sampler(level)
+    s.overlap_nuisance_proposal = overlap
     max_kb, bin_kb, _ = g["hist_args"]
     s.estimate_parameters_rippe(max_kb, bin_kb, False)
     assert np.allclose(np.array(list(s.param_simu[0]), dtype=np.float32), g["params8"], rtol=1e-5)
@@ -84,6 +88,7 @@ def test_facade_replays_reference_driver_loop(built, name):
             prev_state = g["step_states"][t]
             t += 1
     assert t == n_steps and n_nuis == len(g["step_nuis_step"])
+    assert s.n_nuis_overlapped == (max(n_nuis - 1, 0) if overlap else 0)   # every nuisance step but the first found its proposal ready
     # the RNG stream position after the whole run: one more draw must equal the reference's next draw, which the
     # golden file does not hold -- instead the visiting order / candidates / nuisance draws above pin every consumed value
     s.free_gpu()

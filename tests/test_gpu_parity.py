@@ -527,19 +527,21 @@ def test_medium_level_with_long_contigs_takes_the_large_level_paths_naturally(bu
     assert ties <= 6
 
 
+@pytest.mark.parametrize("rigid", [True, False])
 @pytest.mark.parametrize("workload,steps", [("T", 1200), ("toy", 400)])
-def test_streaming_path_equals_row_per_warp_rigid_path(built, workload, steps, monkeypatch):
+def test_streaming_path_equals_row_per_warp_rigid_path(built, workload, steps, rigid, monkeypatch):
     """The streaming scoring path of large levels (k_stream + k_eval_flat<true>, rigid_pruning=1) forced on small levels:
     same selected-contact counts, scores equal to the row-per-warp kernel's in rigid mode up to the 2^-32 fixed-point
     rounding of its order-independent sums, same trajectory (unless two scores are that close), and two runs of the
-    streaming path are bit-identical although its pick list is appended in arbitrary order."""
+    streaming path are bit-identical although its pick list is appended in arbitrary order.  rigid = False: the same in the
+    reference-faithful mode, where large levels send their small candidates (mid-assembly contigs) down this path."""
     level = make_level(WORKLOADS[workload])
     p8 = P8_RIPPE if workload == "T" else P8
     monkeypatch.setenv("IG_FLAT", "0")
-    ref = make_sampler(level, rigid_pruning=True)        # k_score, rigid class-pair table
+    ref = make_sampler(level, rigid_pruning=rigid)        # k_score (rigid: with the rigid class-pair table)
     monkeypatch.setenv("IG_FORCE_STREAM", "1")
-    st1 = make_sampler(level, rigid_pruning=True)
-    st2 = make_sampler(level, rigid_pruning=True)
+    st1 = make_sampler(level, rigid_pruning=rigid)
+    st2 = make_sampler(level, rigid_pruning=rigid)
     ss = [ref, st1, st2]
     for s in ss:
         s.set_param_simu(p8)
@@ -574,15 +576,16 @@ def test_streaming_path_equals_row_per_warp_rigid_path(built, workload, steps, m
         s.free_gpu()
 
 
-def test_streaming_path_random_scaffolds_with_circular_contigs(built, monkeypatch):
+@pytest.mark.parametrize("rigid", [True, False])
+def test_streaming_path_random_scaffolds_with_circular_contigs(built, rigid, monkeypatch):
     """eval on random scaffolds incl. circular contigs (left to k_score inside a streaming-mode step) and reversed
     fragments: streaming == row-per-warp in rigid mode."""
     from oracle.fuzz import random_state
     level = make_level(WORKLOADS["micro"])
     monkeypatch.setenv("IG_FLAT", "0")
-    ref = make_sampler(level, rigid_pruning=True)
+    ref = make_sampler(level, rigid_pruning=rigid)
     monkeypatch.setenv("IG_FORCE_STREAM", "1")
-    st = make_sampler(level, rigid_pruning=True)
+    st = make_sampler(level, rigid_pruning=rigid)
     for s in (ref, st):
         s.set_param_simu(P8)
     rng = np.random.RandomState(3)
@@ -619,7 +622,8 @@ def test_cached_likelihood_records_equal_the_gather_kernel(built, workload, step
     """The nuisance likelihood from the cached per-contact records (k_lnz_refresh + k_lnz_stream, the default) against the
     row-by-row gather kernel (k_full_lnz, IG_LNZ_CACHE=0) along one trajectory: after every step (only the rows of the
     contigs the last move touched are rebuilt; the coordinates are the STALE ones of quirk Q5 in both), for several test
-    parameter sets per step (the second and third run on a clean cache), after a bomb and after a state upload."""
+    parameter sets per step (the second and third run on a clean cache), after a bomb and after a state upload.  Every
+    tenth step follows a parameter change: the default then recomputes lnz_full from the records too (step kind 2)."""
     from instagraal_b200.synth import make_workload
     level = make_workload(workload) if workload == "T" else make_level(WORKLOADS[workload])
     a = GpuImpl(level)
@@ -636,8 +640,13 @@ def test_cached_likelihood_records_equal_the_gather_kernel(built, workload, step
     for f in rng.permutation(level.n_frags)[:steps]:
         f = int(f)
         cands = sorted(int(c) for c in rng.choice(level.n_frags, 4, replace=False) if c != f)
+        if t % 10 == 5:   # an accepted nuisance proposal: the next step recomputes the likelihood sums under the new parameters
+            q = _nuis_params(P8_RIPPE, t)   # (a: from the records, coordinates through the incremental commit; b: from scratch)
+            a.set_params(q); b.set_params(q)
         ra, rb = a.step(f, cands), b.step(f, cands)
-        assert (int(ra["op"]), int(ra["B"])) == (int(rb["op"]), int(rb["B"])) and float(ra["o"]) == float(rb["o"])
+        assert (int(ra["op"]), int(ra["B"])) == (int(rb["op"]), int(rb["B"])), (t, ra["op"], rb["op"])
+        assert abs(float(ra["o"]) - float(rb["o"])) <= 1e-11 * abs(float(rb["o"])), (t, ra["o"], rb["o"])
+        assert np.allclose(ra["scores"], rb["scores"], rtol=1e-11, atol=0)
         for i in range(3 if t % 7 == 0 else 1):
             q = _nuis_params(P8_RIPPE, t + i)
             va, vb = a.eval_nuisance(q), b.eval_nuisance(q)
