@@ -82,6 +82,20 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class stdout_to_stderr:
+    """NCCL / torch.distributed print banners to file descriptor 1; the contract is ONE JSON line on stdout"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -237,7 +251,8 @@ def run_ours(args):
         dist = dist_
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
 
@@ -290,9 +305,12 @@ def run_ours(args):
         idt = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:
             idt = torch.tensor(list(nccl_unique_id()), dtype=torch.uint8, device=dev)
-        dist.broadcast(idt, 0)
+        with stdout_to_stderr():
+            dist.broadcast(idt, 0)
         nid = bytes(idt.cpu().tolist())
-    rs.init_comm(rank, world, nid)
+    with stdout_to_stderr():
+        rs.init_comm(rank, world, nid)
+        rs.allgather()
     seg = max(1, args.gather_every if args.gather_every > 0 else args.steps // 4)
     warm = frag_orders(level, n_local, min(args.warmup, 200), 5 + rank)
     rs.run_cycle(warm, 5, cycle=100)
@@ -398,7 +416,8 @@ def run_ours(args):
                 "without_nuisance_mcmc_cycle_s_e2e": r["t_e2e"] / args.steps * level.n_frags,
                 "kernels": {
                     "scoring": {"launches_per_step": "k_stream + k_eval_flat<list> (+ k_score for circular contigs)" if (mode != "exact" and big)
-                                                     else ("k_pick + k_eval_flat" if not big else "k_score"),
+                                                     else ("k_pick + k_eval_flat" if not big else
+                                                           "k_stream + k_eval_flat<list> (candidates whose picks fit the list) + k_score (the others)"),
                                 "ms_per_step": ms_score, "alg_bytes_per_step": bytes_score / max(n_prof, 1),
                                 "achieved_GBs": bytes_score / max(stp["ms_score"], 1e-9) / 1e6,
                                 "frac_hbm": bytes_score / max(stp["ms_score"], 1e-9) / 1e6 / peak,
@@ -434,6 +453,14 @@ def run_ours(args):
                 out["ref_gpu_baseline"]["speedup_single_chain_e2e_vs_ref_gpu"] = sc_e2e / out["ref_gpu_baseline"]["value"]
         except Exception as ex:  # the baseline must never break the bench line
             out["ref_gpu_baseline"] = {"unavailable": repr(ex)[:200]}
+        try:
+            with stdout_to_stderr():   # the reference class logs to stdout
+                ri = ref_gpu_baseline_unmodified(level, p8, st_start, args.ref_gpu_budget_s, local)
+            out["ref_gpu_baseline_unmodified_class"] = ri
+            if single and "value" in ri:
+                ri["speedup_single_chain_e2e_vs_ref_gpu"] = out["single_chain"][start_name]["e2e"]["value"] / ri["value"]
+        except Exception as ex:
+            out["ref_gpu_baseline_unmodified_class"] = {"unavailable": repr(ex)[:300]}
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
@@ -499,6 +526,37 @@ def ref_gpu_baseline(level, p8, state13, budget_s, device=0):
     return {"value": n_prop / dt, "unit": "proposals/s", "ms_per_step": dt / n_steps * 1e3, "steps": n_steps,
             "kernel_launches_per_step": (r.be.n_launch - l0) / n_steps,
             "kind": "reference kernels (cubin built from /root/reference) + restated reference host sequence (route ii)",
+            "sample": "%d step_sampler calls from the same burnt-in scaffold, %.1f s" % (n_steps, dt)}
+
+
+def ref_gpu_baseline_unmodified(level, p8, state13, budget_s, device=0):
+    """B-ref (GPU), route (i): the UNMODIFIED reference sampler class (verbatim copy under baseline/_ref) on this GPU through
+    oracle/ref_harness_gpu, a stand-in for pycuda over cuda-python; its own return_neighbours, its own step_sampler."""
+    from oracle import ref_unmodified as ru
+    if not ru.available():
+        return {"unavailable": "baseline/_ref/instagraal or oracle/_ref/ref_kernels.cubin not built"}
+    t0 = time.perf_counter()
+    r = ru.UnmodifiedSampler(level, p8, device=device)
+    t_ctor = time.perf_counter() - t0
+    if state13 is not None:
+        r.set_state(state13)
+    np.random.seed(3)
+    frs = np.arange(level.n_frags)
+    np.random.shuffle(frs)
+    r.step_sampler(int(frs[0]))   # warm-up
+    l0 = r.n_launch
+    t0 = time.perf_counter()
+    n_prop = n_steps = 0
+    for f in frs[1:]:
+        r.step_sampler(int(f))
+        n_prop += int(np.count_nonzero(r.all_scores))
+        n_steps += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": n_prop / dt, "unit": "proposals/s", "ms_per_step": dt / n_steps * 1e3, "steps": n_steps,
+            "kernel_launches_per_step": (r.n_launch - l0) / n_steps, "constructor_s": t_ctor,
+            "kind": "unmodified reference sampler class (baseline/_ref copy) + pycuda stand-in over cuda-python + reference cubin (route i)",
             "sample": "%d step_sampler calls from the same burnt-in scaffold, %.1f s" % (n_steps, dt)}
 
 

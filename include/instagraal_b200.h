@@ -162,6 +162,9 @@ int ig_get_kernel_times(ig_handle* h, double out11[11], int32_t reset);
  * outside); in between they are maintained incrementally (identical up to f64 summation order).
  * use_graph: replay each step as one CUDA graph. */
 int ig_set_options(ig_handle* h, int32_t refresh_every, int32_t use_graph);
+/* chains that share one GPU (ig_clone): this chain's scoring grids take 1/share of the SMs so the chains' kernels overlap
+ * (no counterpart in the reference, which runs one chain per process and GPU); 1 = the whole machine (default) */
+int ig_set_gpu_share(ig_handle* h, int32_t share);
 /* device milliseconds spent inside the full-likelihood kernel by ig_full_likelihood calls (the nuisance step's
  * eval_likelihood_4_nuisance, CL:1296-1344) and the number of such calls: out2 = { ms, calls } */
 int ig_get_nuisance_stats(ig_handle* h, double out2[2], int32_t reset);

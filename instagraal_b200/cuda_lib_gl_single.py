@@ -271,6 +271,10 @@ class sampler:
         summation order)."""
         L.check(self._h, L.lib().ig_set_options(self._h, int(refresh_every), int(bool(use_graph))), "ig_set_options")
 
+    def set_gpu_share(self, share):
+        """this chain's scoring grids use 1/share of the GPU (several chains per GPU, see ReplicaSet)"""
+        L.check(self._h, L.lib().ig_set_gpu_share(self._h, int(share)), "ig_set_gpu_share")
+
     def get_stats(self, reset=False):
         out = np.zeros(10, dtype=np.float64)
         L.check(self._h, L.lib().ig_get_stats(self._h, _ptr(out), int(bool(reset))), "ig_get_stats")

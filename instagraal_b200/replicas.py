@@ -50,6 +50,10 @@ class ReplicaSet:
         self.nf = int(first_sampler.n_new_frags)
         self.gather_ms = 0.0
         self.n_gathers = 0
+        # several chains on this GPU: each takes a share of the SMs so that their (latency-bound) kernels overlap
+        self.gpu_share = min(n_chains, 4)
+        for c in self.chains:
+            c.set_gpu_share(self.gpu_share)
 
     def init_comm(self, rank=0, n_ranks=1, nccl_id=None):
         lead = self.chains[0]

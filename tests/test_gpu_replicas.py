@@ -33,6 +33,7 @@ def test_chains_sharing_a_level_equal_separate_handles(built):
     want, want_state = [], []
     for i in range(n):
         s = make_sampler(level)
+        s.set_gpu_share(4)   # what ReplicaSet gives each of 4 chains (the share groups the partial sums, compare like with like)
         s.set_param_simu(P8)
         np.random.seed(100 + i)
         s.bomb_the_genome()
