@@ -201,6 +201,14 @@ int ig_allgather_best(ig_handle* lead, ig_handle** local_chains, int32_t n_local
                       float* ms);
 int ig_get_gathered_state(ig_handle* lead, int32_t index, int32_t* out13xNF);
 int ig_nccl_finalize(ig_handle* lead);
+/* ---- pyramid build (pyramid_sparse.py:331-397 fill_sparse_pyramid_level, :686-722 the contact part of
+ * subsample_data_set): bin n contacts (fa, fb 0-based, count nc) of one level.  old2new (may be NULL = identity) maps an
+ * old 0-based fragment id to its new 0-based id; each pair is ordered (smaller id first), equal pairs are summed.
+ * first_appearance_order = 0: output sorted by (a, b) -- the text file of the next level;
+ * first_appearance_order = 1: rows ascending, inside a row in order of first appearance in the input -- the HDF5 layout.
+ * out_* must hold n entries; *n_out = number of distinct pairs.  Handle-free; `device` = CUDA ordinal. */
+int ig_bin_contacts(int32_t device, int64_t n, const int32_t* fa, const int32_t* fb, const int32_t* nc, const int32_t* old2new,
+                    int32_t n_old, int32_t first_appearance_order, int32_t* out_a, int32_t* out_b, int64_t* out_n, int64_t* n_out);
 /* device address of the live scaffold records (64 B per fragment) -- diagnostics */
 int ig_device_state_ptr(ig_handle* h, void** dev_ptr, int64_t* n_bytes);
 

@@ -24,7 +24,7 @@ EXPORTS = (
     "ig_set_profiling", "ig_get_stats", "ig_set_options", "ig_set_gpu_share", "ig_get_full_refresh_count", "ig_get_kernel_times", "ig_run_cycle", "ig_contact_thumbnail", "ig_set_neighbour_weights",
            "ig_run_cycle_device", "ig_get_cycle_plan", "ig_timeline_reset", "ig_timeline_get", "ig_timeline_blocks", "ig_timeline_phases",
     "ig_selftest_math", "ig_get_nuisance_stats", "ig_clone", "ig_run_cycles_device_multi", "ig_run_cycle_device_async", "ig_cycle_wait",
-    "ig_nccl_unique_id", "ig_nccl_init", "ig_allgather_best", "ig_get_gathered_state", "ig_nccl_finalize",
+    "ig_bin_contacts", "ig_nccl_unique_id", "ig_nccl_init", "ig_allgather_best", "ig_get_gathered_state", "ig_nccl_finalize",
 )
 
 
@@ -91,6 +91,7 @@ def lib():
         L.ig_get_stats.argtypes = [vp, vp, i32]
         L.ig_set_options.argtypes = [vp, i32, i32]
         L.ig_set_gpu_share.argtypes = [vp, i32]
+        L.ig_bin_contacts.argtypes = [i32, i64, vp, vp, vp, vp, i32, i32, vp, vp, vp, C.POINTER(i64)]
         L.ig_get_kernel_times.argtypes = [vp, vp, i32]
         L.ig_run_cycle.argtypes = [vp, i32, vp, vp, vp, vp]
         L.ig_contact_thumbnail.argtypes = [vp, vp, i32, vp]

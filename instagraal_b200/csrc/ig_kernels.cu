@@ -1400,3 +1400,5 @@ extern "C" int ig_timeline_get(ig_handle* h, int32_t n_steps, uint64_t* out) {
 }
 
 #include "ig_replicas.cuh"   // replica chains across GPUs: NCCL all-gather inside the library
+
+#include "ig_pyramid.cuh"   // pyramid build: binning of a level's contact list (handle-free entry point)

@@ -84,3 +84,20 @@ def test_export_is_faster_on_a_large_scaffold(tmp_path):
     assert filecmp.cmp(tmp_path / "ref.fa", tmp_path / "new.fa", shallow=False)
     assert filecmp.cmp(tmp_path / "ref.txt", tmp_path / "new.txt", shallow=False)
     print("generate_new_fasta: restated reference %.2f s, instagraal_b200.export %.2f s" % (t_ref, t_new))
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_against_files_written_by_the_reference_method(tmp_path, seed):
+    """pinned: tests/golden/export/* were written by the reference's OWN level.generate_new_fasta (pyramid_sparse.py:1963-2033,
+    called unbound on a stand-in level by oracle/make_export_golden.py); the product and the restatement reproduce them byte
+    for byte from the same seeded inputs."""
+    import os
+    from oracle.make_export_golden import make_case, stand_in_level
+    names, starts, ends, seqs, vf = make_case(seed)
+    lvl = stand_in_level(names, starts, ends, seqs)
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "export")
+    for impl, tag in ((export, "new"), (export_ref, "ref")):
+        fa, tx = str(tmp_path / (tag + ".fa")), str(tmp_path / (tag + ".txt"))
+        impl.generate_new_fasta(lvl, types.SimpleNamespace(**vf), fa, tx)
+        assert filecmp.cmp(fa, os.path.join(g, "genome_%d.fasta" % seed), shallow=False), tag
+        assert filecmp.cmp(tx, os.path.join(g, "info_frags_%d.txt" % seed), shallow=False), tag

@@ -1,0 +1,124 @@
+"""Pyramid build: instagraal_b200.pyramid_build against golden files written by the UNMODIFIED reference
+functions (oracle/make_pyramid_golden.py ran pyramid_sparse.init_frag_list / subsample_data_set / fill_sparse_pyramid_level on
+tests/golden/pyramid/input): every text file of every level byte for byte, the (3, nnz) HDF5 arrays element for element --
+including the reference's quirk Q13 (the first data line of a contact file is dropped by subsample_data_set)."""
+import filecmp
+import os
+
+import numpy as np
+import pytest
+
+from instagraal_b200 import pyramid_build as pb
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pyramid")
+N_LEVELS = 4
+
+
+def _paths(root, level):
+    d = os.path.join(root, "level_%d" % level)
+    pre = "%d_" % level
+    return {k: os.path.join(d, pre + k) for k in ("contig_info.txt", "fragments_list.txt", "abs_frag_contacts.txt", "sub_2_super_index_frag.txt")}
+
+
+def _same(a, b):
+    assert filecmp.cmp(a, b, shallow=False), (a, b)
+
+
+def test_fragment_and_contig_bookkeeping_matches_reference(built, tmp_path):
+    """host part (no GPU): level-0 fragment list, then contig list / fragment list / old->new index of levels 1..3"""
+    exp0 = _paths(os.path.join(G, "expected"), 0)
+    os.makedirs(tmp_path / "level_0")
+    got0 = _paths(str(tmp_path), 0)
+    n = pb.init_frag_list(os.path.join(G, "input", "fragments_list.txt"), got0["fragments_list.txt"])
+    assert n == 374
+    _same(got0["fragments_list.txt"], exp0["fragments_list.txt"])
+    want_nfrags = np.load(os.path.join(G, "expected", "hdf5_arrays.npz"))
+    for level in range(1, N_LEVELS):
+        prev, exp = _paths(os.path.join(G, "expected"), level - 1), _paths(os.path.join(G, "expected"), level)
+        os.makedirs(tmp_path / ("level_%d" % level))
+        got = _paths(str(tmp_path), level)
+        s2s = os.path.join(str(tmp_path), "s2s_%d.txt" % level)
+        nf = pb.subsample_data_set(prev["contig_info.txt"], prev["fragments_list.txt"], 3, "SIMU", got["abs_frag_contacts.txt"], 1,
+                                   got["contig_info.txt"], got["fragments_list.txt"], s2s)
+        assert nf == int(want_nfrags["nfrags_%d" % level])
+        _same(got["contig_info.txt"], exp["contig_info.txt"])
+        _same(got["fragments_list.txt"], exp["fragments_list.txt"])
+        _same(s2s, prev["sub_2_super_index_frag.txt"])
+    # factor 1: plain copies + identity index (PS:482-495)
+    os.makedirs(tmp_path / "f1")
+    f1 = {k: str(tmp_path / "f1" / k) for k in ("c", "f", "a", "s")}
+    p1 = _paths(os.path.join(G, "expected"), 1)
+    assert pb.subsample_data_set(p1["contig_info.txt"], p1["fragments_list.txt"], 1, p1["abs_frag_contacts.txt"], f1["a"], 1, f1["c"], f1["f"], f1["s"]) == 132
+    _same(f1["a"], p1["abs_frag_contacts.txt"])
+    assert open(f1["s"]).read().splitlines()[:3] == ["current_id\tsuper_id", "1\t1", "2\t2"]
+
+
+class _Dataset:
+    def __init__(self, shape):
+        self.a = np.zeros(shape, dtype=np.int32)
+
+    def __setitem__(self, k, v):
+        self.a[k] = v
+
+
+class _Group:
+    def __init__(self):
+        self.d = {}
+
+    def create_dataset(self, name, shape, dtype):
+        self.d[name] = _Dataset(shape)
+        return self.d[name]
+
+
+class FakeH5:
+    def __init__(self):
+        self.g, self.attrs = {}, {}
+
+    def create_group(self, name):
+        self.g[name] = _Group()
+        return self.g[name]
+
+
+@pytest.mark.gpu
+def test_build_matches_reference_levels_and_hdf5_arrays(built, tmp_path):
+    """the whole level loop through the C ABI (ig_bin_contacts): contact files of every level and the HDF5 group contents"""
+    base = os.path.join(G, "input")
+    nfr = pb.build(base, N_LEVELS, 3, 1, output_folder=str(tmp_path))
+    root = os.path.join(str(tmp_path), "pyramids", "pyramid_%d_no_thresh" % N_LEVELS)
+    want = np.load(os.path.join(G, "expected", "hdf5_arrays.npz"))
+    assert nfr == [int(want["nfrags_%d" % lv]) for lv in range(N_LEVELS)]
+    for level in range(N_LEVELS):
+        got, exp = _paths(root, level), _paths(os.path.join(G, "expected"), level)
+        for k in ("contig_info.txt", "fragments_list.txt", "abs_frag_contacts.txt"):
+            _same(got[k], exp[k])
+        if level < N_LEVELS - 1:
+            _same(got["sub_2_super_index_frag.txt"], exp["sub_2_super_index_frag.txt"])
+        h5 = FakeH5()
+        arr = pb.fill_sparse_pyramid_level(h5, level, got["abs_frag_contacts.txt"], nfr[level])
+        assert np.array_equal(arr, want["data_%d" % level]), level
+        assert np.array_equal(h5.g[str(level)].d["data"].a, want["data_%d" % level])
+        assert int(h5.g[str(level)].d["nfrags"].a[0, 0]) == nfr[level]
+
+
+@pytest.mark.gpu
+def test_bin_contacts_edge_cases(built):
+    a, b, n = pb.bin_contacts(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32))
+    assert len(a) == 0
+    # one pair given in both orders and twice: summed once, ordered
+    a, b, n = pb.bin_contacts([5, 2, 5, 0], [2, 5, 5, 0], [3, 4, 1, 9])
+    assert a.tolist() == [0, 2, 5] and b.tolist() == [0, 5, 5] and n.tolist() == [9, 7, 1]
+    # first-appearance order inside a row; sums above int32
+    a, b, n = pb.bin_contacts([1, 1, 1, 0, 1], [9, 3, 9, 4, 3], [2**31 - 1, 1, 2**31 - 1, 5, 1], first_appearance_order=True)
+    assert a.tolist() == [0, 1, 1] and b.tolist() == [4, 9, 3] and n.tolist() == [5, 2 * (2**31 - 1), 2]
+    with pytest.raises(RuntimeError, match="out of range"):
+        pb.bin_contacts([0, 7], [1, 1], [1, 1], old2new=[0, 0, 1])
+    # a larger random case against NumPy
+    rng = np.random.RandomState(1)
+    fa, fb, nc = rng.randint(0, 5000, 400000), rng.randint(0, 5000, 400000), rng.randint(1, 9, 400000)
+    m = rng.randint(0, 1700, 5000)
+    a, b, n = pb.bin_contacts(fa, fb, nc, old2new=m)
+    lo, hi = np.minimum(m[fa], m[fb]), np.maximum(m[fa], m[fb])
+    key = lo.astype(np.int64) * 1700 + hi
+    uk, inv = np.unique(key, return_inverse=True)
+    assert np.array_equal(a.astype(np.int64) * 1700 + b, uk)
+    assert np.array_equal(n, np.bincount(inv, weights=nc).astype(np.int64))
