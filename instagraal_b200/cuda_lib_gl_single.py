@@ -171,11 +171,12 @@ class sampler:
         self.n_proposals_scored = 0
         self._last_dist = 1.0
         # step_nuisance_parameters' proposal (host RNG draws + scipy fsolve, ~0.35 ms) is prepared while the GPU scores the
-        # step before it; results and RNG stream are unchanged (see _speculate_nuisance).  False = strictly in place.
+        # step before it, on a private copy of the generator; results and RNG stream are unchanged (see _speculate_nuisance).
         self.overlap_nuisance_proposal = True
         self._nuis_follows = False
         self._spec = None
         self._spec_pool = None
+        self._twin = None
         self.n_nuis_overlapped = 0
         self.modification_str = [  # CL:1601-1620
             "eject frag", "flip frag", "pop out split insert @ left or 1", "pop out split insert @ left or -1",
@@ -210,7 +211,7 @@ class sampler:
         s.all_scores = np.zeros(0)
         s.n_proposals_scored = 0
         s.likelihood_t = None
-        s._nuis_follows, s._spec, s._spec_pool = False, None, None
+        s._nuis_follows, s._spec, s._spec_pool, s._twin = False, None, None, None
         s._res = L.ig_step_result()
         s._res_scores = np.frombuffer(s._res, dtype=np.float64, count=L.IG_MAX_CANDS * L.IG_N_OPS, offset=L.ig_step_result.scores.offset)
         s._res_nuniq = np.frombuffer(s._res, dtype=np.int32, count=L.IG_MAX_CANDS, offset=L.ig_step_result.n_uniq.offset)
@@ -407,7 +408,7 @@ class sampler:
             if self._spec_pool is None:
                 from concurrent.futures import ThreadPoolExecutor
                 self._spec_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="ig-nuisance")
-            fut = self._spec_pool.submit(self._speculate_nuisance, np.random.get_state())
+            fut = self._spec_pool.submit(self._speculate_nuisance)
         self._nuis_follows = False
         rc = self._ig_step(self._h, int(id_frag), self._cand_ptr, n, self._res_ref)
         self._spec = fut.result() if fut is not None else None
@@ -613,80 +614,85 @@ class sampler:
     def temperature(self, t, n_step):
         return 1.0
 
-    def _nuisance_proposal(self):
-        """First half of step_nuisance_parameters (CL:2961-3032): the random-walk proposal of one of the four nuisance
-        parameters and the d_max that goes with it (scipy fsolve).  Depends on the live parameters and the host RNG
-        only -- not on the scaffold -- which is what lets step_sampler compute it while the GPU scores the step."""
-        curr_param = np.copy(self.param_simu)
-        kuhn, lm, c1, slope, d, d_max, fact, d_nuc = curr_param[0]
+    def _nuisance_draws(self, rng):
+        """The random part of a nuisance proposal (CL:2961-3032): which of the four parameters moves (``choice(4)``) and by how
+        much (one ``normal`` draw).  ``rng`` = the ``np.random`` module (the reference's global stream) or a RandomState."""
+        kuhn, lm, c1, slope, d, d_max, fact, d_nuc = self.param_simu[0]
         self.sigma_fact = 10 ** (np.log10(fact) - 2)
         self.sigma_slope = 0.005
         self.sigma_d_max = 100
         self.sigma_d_nuc = 10 ** (np.log10(d_nuc) - 2)
         self.sigma_d = 10
-        id_modif = np.random.choice(4)
+        id_modif = rng.choice(4)
         if id_modif == 0:
-            new_fact = fact + np.random.normal(loc=0.0, scale=self.sigma_fact)
+            draw = rng.normal(loc=0.0, scale=self.sigma_fact)
+        elif id_modif == 1:
+            draw = rng.normal(loc=0.0, scale=self.sigma_slope)
+        elif id_modif == 2:
+            draw = rng.normal(loc=0.0, scale=self.sigma_d_max)
+        else:
+            draw = None if self.sigma_d_nuc <= 0 else rng.normal(loc=0.0, scale=self.sigma_d_nuc)
+        return int(id_modif), draw
+
+    def _nuisance_finish(self, id_modif, draw):
+        """The deterministic part: the test parameter set for these draws, incl. the d_max that goes with it (scipy fsolve)."""
+        curr_param = np.copy(self.param_simu)
+        kuhn, lm, c1, slope, d, d_max, fact, d_nuc = curr_param[0]
+        if id_modif == 0:
+            new_fact = fact + draw
             test_param = [kuhn, lm, slope, d, new_fact]
             new_d_max = opti.estimate_max_dist_intra_nuis(test_param, d_nuc, d_max)
             c1 = np.float32((0.53 * np.power(lm / kuhn, slope)) * np.power(kuhn, -3))
             out_test_param = [(kuhn, lm, c1, slope, d, new_d_max, new_fact, d_nuc)]
         elif id_modif == 1:
-            new_slope = slope + np.random.normal(loc=0.0, scale=self.sigma_slope)
+            new_slope = slope + draw
             test_param = [kuhn, lm, new_slope, d, fact]
             new_d_max = opti.estimate_max_dist_intra_nuis(test_param, d_nuc, d_max)
             c1 = np.float32((0.53 * np.power(lm / kuhn, new_slope)) * np.power(kuhn, -3))
             out_test_param = [(kuhn, lm, c1, new_slope, d, new_d_max, fact, d_nuc)]
         elif id_modif == 2:
-            new_d_max = d_max + np.random.normal(loc=0.0, scale=self.sigma_d_max)
+            new_d_max = d_max + draw
             test_param = [kuhn, lm, slope, d, fact]
             new_d_nuc = opti.peval(new_d_max, test_param)  # sic: 5-vector, param[3] = d (quirk Q7)
             c1 = np.float32((0.53 * np.power(lm / kuhn, slope)) * np.power(kuhn, -3))
             out_test_param = [(kuhn, lm, c1, slope, d, new_d_max, fact, new_d_nuc)]
         else:
-            if self.sigma_d_nuc <= 0:
-                new_d_nuc = d_nuc
-            else:
-                new_d_nuc = d_nuc + np.random.normal(loc=0.0, scale=self.sigma_d_nuc)
+            new_d_nuc = d_nuc if draw is None else d_nuc + draw
             test_param = [kuhn, lm, slope, d, fact]
             new_d_max = opti.estimate_max_dist_intra_nuis(test_param, new_d_nuc, d_max)
             c1 = np.float32((0.53 * np.power(lm / kuhn, slope)) * np.power(kuhn, -3))
             out_test_param = [(kuhn, lm, c1, slope, d, new_d_max, fact, new_d_nuc)]
         return np.array(out_test_param, dtype=PARAM_SIMU_RIPPE)
 
-    # -- the proposal of the NEXT step_nuisance_parameters call, computed on a worker thread while ig_step blocks (the
-    #    ctypes call releases the GIL).  The reference's RNG order is: neighbours of step t, proposal draws of the nuisance
-    #    step t, its acceptance draw, neighbours of step t + 1 ...  The worker runs the proposal draws from the generator
-    #    state left by the neighbour draw, records the state after them and PUTS THE FIRST STATE BACK; the nuisance step
-    #    takes the prepared proposal (and jumps to the recorded state) only if the generator and the parameters are still
-    #    exactly where the worker found them -- otherwise (the caller drew numbers in between, or never calls the nuisance
-    #    step) nothing has happened and the proposal is computed in place as before.
-    def _speculate_nuisance(self, st0):
+    # -- the proposal of the NEXT step_nuisance_parameters call, PREDICTED on a worker thread while ig_step blocks (the ctypes
+    #    call releases the GIL).  The reference's RNG order is: neighbours of step t, proposal draws of the nuisance step t,
+    #    its acceptance draw, neighbours of step t + 1 ...  The worker copies the global generator's state (as the neighbour
+    #    draw left it) into a private twin, makes the two proposal draws THERE and runs the expensive deterministic part
+    #    (fsolve) for them.  The global stream is never touched: the nuisance step makes its own draws on it as always and
+    #    takes the prepared parameter set only if its draws and the live parameters are the predicted ones, bit for bit --
+    #    anything else (the caller drew numbers in between, parameters changed) just means the prediction is not used.
+    def _speculate_nuisance(self):
         try:
+            if self._twin is None:
+                self._twin = np.random.RandomState()
+            self._twin.set_state(np.random.get_state())
             key = self.param_simu.tobytes()
-            prop = self._nuisance_proposal()
-            st1 = np.random.get_state()
-            return (st0, st1, key, prop)
+            id_modif, draw = self._nuisance_draws(self._twin)
+            return (key, id_modif, draw, self._nuisance_finish(id_modif, draw))
         except Exception:
             return None
-        finally:
-            np.random.set_state(st0)
-
-    @staticmethod
-    def _same_rng_state(a, b):
-        return a[2] == b[2] and a[3] == b[3] and a[4] == b[4] and a[0] == b[0] and np.array_equal(a[1], b[1])
 
     def step_nuisance_parameters(self, dt, t, n_step):
         """CL:2961-3051 (same host RNG calls, same scipy fsolve)."""
         spec, self._spec = self._spec, None
         self._nuis_follows = self.overlap_nuisance_proposal
-        if (spec is not None and spec[2] == self.param_simu.tobytes()
-                and self._same_rng_state(spec[0], np.random.get_state())):
-            np.random.set_state(spec[1])
+        id_modif, draw = self._nuisance_draws(np.random)
+        if (spec is not None and spec[0] == self.param_simu.tobytes() and spec[1] == id_modif
+                and ((draw is None and spec[2] is None) or (draw is not None and spec[2] is not None and float(draw) == float(spec[2])))):
             out_test_param = spec[3]
             self.n_nuis_overlapped += 1
         else:
-            out_test_param = self._nuisance_proposal()
+            out_test_param = self._nuisance_finish(id_modif, draw)
         self.param_simu_test = out_test_param
         self.likelihood_nuis = self.eval_likelihood_4_nuisance()
         F_t = self.temperature(t, n_step)
