@@ -33,6 +33,8 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
     // 25 + 25 + 25 + 2 slots, one warp per slot, lanes stride the partial blocks, fixed shuffle tree
     // 32 warps, one slot each per round; every lane first issues all of its loads (independent, in
     // flight together), then adds them in index order; fixed shuffle tree => deterministic
+    // (k_precompute's block b owns the row tiles b, b + grid, ...: blocks beyond the candidate's tile count wrote zeros)
+    const int n_z_eff = min(n_part_z, max(1, (ci_k.n_rows + 31) >> 5));
     int nz_first = 0, nz_count = n_part;
     const bool fixed = sc->use_stream[k] != 0;   // streaming path: int64 fixed-point partials from k_eval_flat<true>
     if (flat || fixed) { int t_, c_; flat_block_range(sc, sc->n_cands, n_part, k, 0, &nz_first, &nz_count, &t_, &c_); }   // k_eval_flat's blocks for k
@@ -46,7 +48,7 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
             if (lane == 0) s_nz[slot] = (double)v * (1.0 / IG_FIX_SCALE);   // exact integer total, whatever the order
         } else if (slot < 50) {
             const double* src = slot < 25 ? &part_nz[PART_IDX(k, 25, slot, n_part, nz_first)] : &part_z[PART_IDX(k, 25, slot - 25, n_part_z, 0)];
-            const int n = slot < 25 ? nz_count : n_part_z;
+            const int n = slot < 25 ? nz_count : n_z_eff;
             double v = 0.0;
             for (int i0 = 0; i0 < n; i0 += 32 * 16) {
                 double x[16];
@@ -60,7 +62,7 @@ k_finalize(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, c
         } else {
             // (the selection counters may come from another kernel than the likelihood partials: own block count)
             const int* src = slot < 75 ? &part_i[PART_IDX(k, 25, slot - 50, n_part_z, 0)] : &part_c[PART_IDX(k, 2, slot - 75, n_part_c, 0)];
-            const int n = slot < 75 ? n_part_z : n_part_c;
+            const int n = slot < 75 ? n_z_eff : n_part_c;
             int v = 0;
             for (int i0 = 0; i0 < n; i0 += 32 * 16) {
                 int x[16];

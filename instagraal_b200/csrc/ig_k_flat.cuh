@@ -295,14 +295,18 @@ k_stream(const int2* __restrict__ cv, const CoordRec* __restrict__ coord, const 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int wg = blockIdx.x * IG_WARPS_PER_BLOCK + w, nw = gridDim.x * IG_WARPS_PER_BLOCK;
     if (threadIdx.x == 0) { s_sel = 0; s_read = 0; }
-    if ((int)blockIdx.x * IG_WARPS_PER_BLOCK < n_rows) {
+    // a candidate with few rows (mid-assembly contigs) cuts each row into `parts` interleaved sets of 64-contact trips, one
+    // warp each, so that its critical path is one trip and not a whole row
+    const int parts = n_rows * 8 <= nw ? 8 : (n_rows * 4 <= nw ? 4 : (n_rows * 2 <= nw ? 2 : 1));
+    const int n_items = n_rows * parts;
+    if ((int)blockIdx.x * IG_WARPS_PER_BLOCK < n_items) {
         const unsigned* gb = bitmap + (size_t)k * bitmap_words;
         for (int i = threadIdx.x; i < bitmap_words; i += blockDim.x) s_bits[i] = gb[i];
         const unsigned allmask = (1u << desc_g[k].n_uniq) - 1u;
         for (int i = threadIdx.x; i < IG_MAX_CLS * IG_MAX_CLS; i += blockDim.x) s_mask[i] = clstab[k].mask[i] & allmask;
     }
     __syncthreads();
-    if ((int)blockIdx.x * IG_WARPS_PER_BLOCK < n_rows) {
+    if ((int)blockIdx.x * IG_WARPS_PER_BLOCK < n_items) {
         const Params p = sc->p;
         const double l10v = sc->log10_vinter;
         const double inter_const = (double)p.v_inter * LOG10E_F;
@@ -313,14 +317,15 @@ k_stream(const int2* __restrict__ cv, const CoordRec* __restrict__ coord, const 
         const unsigned short* my_cls = cls16 + (size_t)k * ns;
         FlatRec* my_list = list + (size_t)k * list_cap;
         int sel_w = 0, read_w = 0;
-        for (int ri = wg; ri < n_rows; ri += nw) {
+        for (int it = wg; it < n_items; it += nw) {
+            const int ri = it / parts, part = it - ri * parts;
             const RowInfo info = rinfo[(size_t)k * ns + ri];
             const CoordRec ci = info.ci;
             const unsigned* mrow = s_mask + info.cls * IG_MAX_CLS;
             const unsigned fr = window_flags(ci.pos, ci_k);
             const long long b = info.b, e = info.b + info.n;
             int row_sel = 0;
-            for (long long k0 = (b & ~1LL); k0 < e; k0 += 64) {
+            for (long long k0 = (b & ~1LL) + 64 * part; k0 < e; k0 += 64 * parts) {
                 const long long kk = k0 + 2 * lane;
                 int4 c2 = make_int4(0, 0, 0, 0);
                 if (kk < e) c2 = __ldcs(reinterpret_cast<const int4*>(cv + kk));
@@ -358,9 +363,12 @@ k_stream(const int2* __restrict__ cv, const CoordRec* __restrict__ coord, const 
                 }
             }
             row_sel = __reduce_add_sync(0xffffffffu, row_sel);
-            if (lane == 0) row_cnt[(size_t)k * ns + ri] = row_sel;
+            if (lane == 0) {   // (zeroed by k_rows_write)
+                if (parts == 1) row_cnt[(size_t)k * ns + ri] = row_sel;
+                else if (row_sel) atomicAdd(&row_cnt[(size_t)k * ns + ri], row_sel);
+            }
             sel_w += row_sel;
-            read_w += info.n;
+            if (part == 0) read_w += info.n;
         }
         if (lane == 0 && (sel_w | read_w)) { atomicAdd(&s_sel, sel_w); atomicAdd(&s_read, read_w); }
     }

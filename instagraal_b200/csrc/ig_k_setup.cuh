@@ -61,33 +61,37 @@ __global__ void k_cand_setup(const FragRec* __restrict__ live, DevScalars* sc, I
 __global__ void __launch_bounds__(256)
 k_find_cuts(const FragRec* __restrict__ live, int nf, DevScalars* sc, IgDescriptor* desc, IgClassTab* __restrict__ clstab) {
     TL(1);
-    const int k = blockIdx.y;
-    if (k >= sc->n_cands) return;
+    // ONE pass over the scaffold for all candidates of the step (they share the visited fragment A, hence A's contig): a
+    // fragment record is read once and tested against every candidate's cut positions
+    const int n = sc->n_cands;
     __shared__ int is_last;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    IgDescriptor& d = desc[k];
     if (i < nf) {
         const Frag f = live[i].f;
-        if (f.id_c == d.A.id_c) {
+        if (f.id_c == desc[0].A.id_c) {
+            for (int k = 0; k < n; k++) {
+                IgDescriptor& d = desc[k];
 #pragma unroll
-            for (int c = 0; c < IG_N_CUT; c++) {
-                if (f.pos == d.cut_pos_down[c]) d.f_down[c] = i;
-                if (f.pos == d.cut_pos_up[c]) d.f_up[c] = i;
+                for (int c = 0; c < IG_N_CUT; c++) {
+                    if (f.pos == d.cut_pos_down[c]) d.f_down[c] = i;
+                    if (f.pos == d.cut_pos_up[c]) d.f_up[c] = i;
+                }
             }
         }
     }
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(&sc->ticket_cuts[k], 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0) is_last = (atomicAdd(&sc->ticket_cuts[0], 1u) == gridDim.x - 1);
     __syncthreads();
     if (!is_last) return;
-    if (threadIdx.x < 32) {
-        __threadfence();
-        ig_build_descriptor_part(desc[k], [&](int j) { return live[j].f; }, threadIdx.x);
-    }
+    // the last block: warp k evaluates every pivot of candidate k's descriptor
+    __threadfence();
+    const int k = threadIdx.x >> 5;
+    if (k < n) ig_build_descriptor_part(desc[k], [&](int j) { return live[j].f; }, threadIdx.x & 31);
     __syncthreads();
     // breakpoints of the rigid-motion classes (ig_moves.cuh): k_rows_write classifies the rows with them
-    if (threadIdx.x == 0) {
+    if (k < n && (threadIdx.x & 31) == 0) {
+        const IgDescriptor& d = desc[k];
         IgClassTab& ct = clstab[k];
         int bpf[IG_MAX_BP + 2], bps[IG_MAX_BP], bpbs[2];
         ig_class_breakpoints(d, bpf, bps, bpf + IG_MAX_BP, bpbs);
@@ -187,50 +191,61 @@ __device__ __forceinline__ bool window_selected(unsigned fi, unsigned fj) {
     const unsigned both = fi & fj;
     return ((both & 3u) == 0u) || ((both & 12u) == 0u);
 }
+// (large levels) ONE pass over the coordinates for all candidates of the step: a chunk of 1024 rows is read once and tested
+// against every candidate's <= 2 affected contigs
 __global__ void __launch_bounds__(IG_ROW_CHUNK)
 k_rows_count(const CoordRec* __restrict__ coord, int ns, DevScalars* sc, int* __restrict__ chunk_cnt, int n_chunks) {
     TL(3);
-    const int k = blockIdx.y;
-    if (k >= sc->n_cands) return;
+    const int n = sc->n_cands;
     __shared__ int is_last, carry;
     __shared__ int wsum[32];
+    __shared__ int s_ida[IG_MAX_CANDS], s_idb[IG_MAX_CANDS];
+    if (threadIdx.x < n) { s_ida[threadIdx.x] = sc->ci[threadIdx.x].id_a; s_idb[threadIdx.x] = sc->ci[threadIdx.x].id_b; }
+    __syncthreads();
     const int r = blockIdx.x * IG_ROW_CHUNK + threadIdx.x;
-    const bool f = r < ns && row_affected(coord[r], sc->ci[k]);
-    const int cnt = __syncthreads_count(f);
+    const int idc = r < ns ? coord[r].id_c : -1;
+    for (int k = 0; k < n; k++) {
+        const bool f = r < ns && (idc == s_ida[k] || idc == s_idb[k]);
+        const int cnt = __syncthreads_count(f);
+        if (threadIdx.x == 0) chunk_cnt[k * n_chunks + blockIdx.x] = cnt;
+    }
     if (threadIdx.x == 0) {
-        chunk_cnt[k * n_chunks + blockIdx.x] = cnt;
         __threadfence();
-        is_last = (atomicAdd(&sc->ticket_rows[k], 1u) == gridDim.x - 1);
-        carry = 0;
+        is_last = (atomicAdd(&sc->ticket_rows[0], 1u) == gridDim.x - 1);
     }
     __syncthreads();
     if (!is_last) return;
-    // the last block to finish this candidate turns the chunk counts into exclusive offsets
+    // the last block to finish turns every candidate's chunk counts into exclusive offsets
     __threadfence();
-    volatile int* c = chunk_cnt + k * n_chunks;
-    for (int base = 0; base < n_chunks; base += blockDim.x) {
-        const int i = base + threadIdx.x;
-        const int v = i < n_chunks ? c[i] : 0;
-        int x = v;
-        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-        if (lane == 31) wsum[w] = x;
+    for (int k = 0; k < n; k++) {
+        if (threadIdx.x == 0) carry = 0;
         __syncthreads();
-        if (w == 0) {
-            int s2 = lane < (blockDim.x >> 5) ? wsum[lane] : 0;
+        volatile int* c = chunk_cnt + k * n_chunks;
+        for (int base = 0; base < n_chunks; base += blockDim.x) {
+            const int i = base + threadIdx.x;
+            const int v = i < n_chunks ? c[i] : 0;
+            int x = v;
+            const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s2, o); if (lane >= o) s2 += y; }
-            wsum[lane] = s2;
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            if (lane == 31) wsum[w] = x;
+            __syncthreads();
+            if (w == 0) {
+                int s2 = lane < (blockDim.x >> 5) ? wsum[lane] : 0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s2, o); if (lane >= o) s2 += y; }
+                wsum[lane] = s2;
+            }
+            __syncthreads();
+            const int excl = carry + (w ? wsum[w - 1] : 0) + x - v;
+            if (i < n_chunks) c[i] = excl;
+            __syncthreads();
+            if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+            __syncthreads();
         }
-        __syncthreads();
-        const int excl = carry + (w ? wsum[w - 1] : 0) + x - v;
-        if (i < n_chunks) c[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+        if (threadIdx.x == 0) sc->ci[k].n_rows = carry;
         __syncthreads();
     }
-    if (threadIdx.x == 0) sc->ci[k].n_rows = carry;
 }
 __global__ void __launch_bounds__(IG_ROW_CHUNK)
 k_rows_write(const CoordRec* __restrict__ coord, int ns, const DevScalars* __restrict__ sc, const int* __restrict__ chunk_off,
@@ -238,37 +253,52 @@ k_rows_write(const CoordRec* __restrict__ coord, int ns, const DevScalars* __res
              const IgClassTab* __restrict__ clstab, const long long* __restrict__ row_ptr, RowInfo* __restrict__ rinfo,
              unsigned* __restrict__ bitmap, int bitmap_words, unsigned short* __restrict__ cls16) {
     TL(4);
-    const int k = blockIdx.y;
-    if (k >= sc->n_cands) return;
-    __shared__ int wsum[32];
-    __shared__ int s_bp[IG_MAX_BP + 4];
-    if (threadIdx.x < IG_MAX_BP + 4) s_bp[threadIdx.x] = reinterpret_cast<const int*>(clstab + k)[threadIdx.x];  // bp_sub, bp_sub_b, distinct_b, id_b
-    const int r = blockIdx.x * IG_ROW_CHUNK + threadIdx.x;
-    CoordRec cr;
-    if (r < ns) cr = coord[r];
-    const bool f = r < ns && row_affected(cr, sc->ci[k]);
-    const unsigned b = __ballot_sync(0xffffffffu, f);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) wsum[w] = __popc(b);
-    // streaming scoring path: membership bitmap of the affected contigs (one bit per sub-fragment, staged in shared
-    // memory by k_stream)
-    if (bitmap && lane == 0 && r < ns) bitmap[(size_t)k * bitmap_words + (r >> 5)] = b;
+    const int n = sc->n_cands;
+    __shared__ int wsum[IG_MAX_CANDS][32];
+    __shared__ int s_bp[IG_MAX_CANDS][IG_MAX_BP + 4];
+    __shared__ int s_ida[IG_MAX_CANDS], s_idb[IG_MAX_CANDS];
+    for (int t = threadIdx.x; t < n * (IG_MAX_BP + 4); t += blockDim.x) {
+        const int k = t / (IG_MAX_BP + 4), j = t - k * (IG_MAX_BP + 4);
+        s_bp[k][j] = reinterpret_cast<const int*>(clstab + k)[j];  // bp_sub, bp_sub_b, distinct_b, id_b
+    }
+    if (threadIdx.x < n) { s_ida[threadIdx.x] = sc->ci[threadIdx.x].id_a; s_idb[threadIdx.x] = sc->ci[threadIdx.x].id_b; }
     __syncthreads();
-    if (w == 0) {
-        int s = wsum[lane];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
-        wsum[lane] = s;
+    const int r = blockIdx.x * IG_ROW_CHUNK + threadIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    CoordRec cr;
+    cr.id_c = -1; cr.pos = 0; cr.dist = 0.f; cr.s_tot = 0.f;
+    if (r < ns) cr = coord[r];
+    unsigned fmask = 0;   // candidates this row belongs to
+    for (int k = 0; k < n; k++) {
+        const bool f = r < ns && (cr.id_c == s_ida[k] || cr.id_c == s_idb[k]);
+        const unsigned b = __ballot_sync(0xffffffffu, f);
+        if (f) fmask |= 1u << k;
+        if (lane == 0) {
+            wsum[k][w] = __popc(b);
+            // streaming scoring path: membership bitmap of the affected contigs (one bit per sub-fragment, staged in shared
+            // memory by k_stream)
+            if (bitmap && r < ns) bitmap[(size_t)k * bitmap_words + (r >> 5)] = b;
+        }
     }
     __syncthreads();
-    if (f) {
-        const int off = chunk_off[k * n_chunks + blockIdx.x] + (w ? wsum[w - 1] : 0) + __popc(b & ((1u << lane) - 1));
+    if (w < n) {   // warp k: inclusive scan of candidate k's per-warp counts
+        int s = wsum[w][lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+        wsum[w][lane] = s;
+    }
+    __syncthreads();
+    for (int k = 0; k < n; k++) {
+        const bool f = (fmask >> k) & 1u;
+        const unsigned b = __ballot_sync(0xffffffffu, f);
+        if (!f) continue;
+        const int off = chunk_off[k * n_chunks + blockIdx.x] + (w ? wsum[k][w - 1] : 0) + __popc(b & ((1u << lane) - 1));
         rows[(size_t)k * rows_stride + off] = r;
-        const int cls = ig_class_of(s_bp, s_bp + IG_MAX_BP, s_bp[IG_MAX_BP + 2], s_bp[IG_MAX_BP + 3], cr.id_c, cr.pos);
+        const int cls = ig_class_of(s_bp[k], s_bp[k] + IG_MAX_BP, s_bp[k][IG_MAX_BP + 2], s_bp[k][IG_MAX_BP + 3], cr.id_c, cr.pos);
         rowidx[(size_t)k * rows_stride + r] = off | (cls << IG_CLS_SHIFT);
         if (cls16) cls16[(size_t)k * rows_stride + r] = (unsigned short)(cls | (window_flags(cr.pos, sc->ci[k]) << 8));
-        const long long b = row_ptr[r];
-        RowInfo ri; ri.r = r; ri.cls = cls; ri.n = (int)(row_ptr[r + 1] - b); ri.pad = 0; ri.b = b; ri.seg = 0; ri.ci = cr;
+        const long long rb = row_ptr[r];
+        RowInfo ri; ri.r = r; ri.cls = cls; ri.n = (int)(row_ptr[r + 1] - rb); ri.pad = 0; ri.b = rb; ri.seg = 0; ri.ci = cr;
         rinfo[(size_t)k * rows_stride + off] = ri;
         row_cnt[(size_t)k * rows_stride + off] = 0;  // k_score (block mode) accumulates into it
     }

@@ -132,7 +132,7 @@ struct ig_handle {
     int nf, ns;
     long long nnz;
     cudaStream_t stream, side, pf;
-    cudaEvent_t ev_coords, ev_lnz, ev_fork, ev_sel, ev_out, ev_cuts, ev_cls;
+    cudaEvent_t ev_coords, ev_lnz, ev_fork, ev_sel, ev_out, ev_cuts, ev_cls, ev_pre, ev_ksc;
     bool rows_small;  // affected-row list in one launch (small levels)
     bool flat;        // flat scoring path (k_pick + k_eval_flat) for small levels
     int grid_flat, flat_items; int* flat_cnt; FlatRec* flat_list; size_t flat_stride, chunk_stride;
@@ -268,6 +268,8 @@ static int create_impl(const ig_config* cfg, const ig_level_data* data, ig_handl
         CK(cudaStreamCreateWithFlags(&h->pf, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&h->ev_cuts, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_cls, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_pre, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_ksc, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_coords, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_lnz, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -499,6 +501,8 @@ extern "C" void ig_destroy(ig_handle* h) {
     if (h->pf) cudaStreamDestroy(h->pf);
     if (h->ev_cuts) cudaEventDestroy(h->ev_cuts);
     if (h->ev_cls) cudaEventDestroy(h->ev_cls);
+    if (h->ev_pre) cudaEventDestroy(h->ev_pre);
+    if (h->ev_ksc) cudaEventDestroy(h->ev_ksc);
     if (h->ev_coords) cudaEventDestroy(h->ev_coords);
     if (h->ev_lnz) cudaEventDestroy(h->ev_lnz);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -649,9 +653,9 @@ static void enqueue_scoring(ig_handle* h, int n, bool in_step) {
         k_rows_small<<<n, IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->n_chunks, h->rows, h->rowidx, h->row_cnt, h->ns,
                                                         h->clstab, h->row_ptr, h->rinfo);
     } else {
-        k_rows_count<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks);
+        k_rows_count<<<h->n_chunks, IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks);
         if (in_step) IG_MARK(3);
-        k_rows_write<<<dim3(h->n_chunks, n), IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks, h->rows,
+        k_rows_write<<<h->n_chunks, IG_ROW_CHUNK, 0, h->stream>>>(h->coord, h->ns, h->sc, h->chunk_cnt, h->n_chunks, h->rows,
                                                                            h->rowidx, h->row_cnt, h->ns, h->clstab, h->row_ptr, h->rinfo,
                                                                            h->bitmap, h->bitmap_words, h->cls16);
     }
@@ -668,6 +672,15 @@ static void enqueue_scoring(ig_handle* h, int n, bool in_step) {
         k_eval_flat<false><<<h->grid_score, IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->sc, h->desc, h->ns, h->flat_cnt, h->chunk_stride, h->flat_list,
                                                                             h->flat_stride, h->table, h->table_len, mbar, h->exz, h->part_nz, h->clstab, h->flat_items);
     } else {
+        // (streaming mode: k_score only works for the candidates k_stream leaves to it -- circular contigs, and in the
+        //  reference-faithful mode the candidates whose picks would not fit the list.  Inside a step it runs BESIDE the
+        //  streaming pair on the third stream -- different candidates, different partials -- and joins before k_finalize.)
+        cudaStream_t ks = h->stream;
+        if (h->streaming && in_step) {
+            ks = h->pf;   // (k_classes ran on it: already ordered)
+            cudaEventRecord(h->ev_pre, h->stream);
+            cudaStreamWaitEvent(ks, h->ev_pre, 0);
+        }
         if (h->streaming) {
             k_stream<<<dim3(gsx, n), IG_THREADS, h->stream_smem, h->stream>>>(h->cv, h->coord, h->clen, h->sc, h->desc, h->rowidx, h->ns, h->row_cnt,
                                                                              h->bitmap, h->bitmap_words, h->cls16, h->part_c, h->pick_list, h->pick_cap,
@@ -675,10 +688,13 @@ static void enqueue_scoring(ig_handle* h, int n, bool in_step) {
             k_eval_flat<true><<<h->grid_score, IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->sc, h->desc, h->ns, nullptr, 0, h->pick_list, h->pick_cap,
                                                                                h->table, h->table_len, mbar, h->exz, h->part_nz, h->clstab, h->flat_items);
         }
-        // (streaming mode: k_score only works for the candidates k_stream leaves to it -- circular contigs)
-        k_score<<<dim3(gsx, n), IG_THREADS, IG_SCORE_SMEM, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
-                                                                     h->ns, h->row_cnt, h->table, h->table_len, mbar, h->exz, h->part_nz,
-                                                                     h->part_c, h->gs_div, h->clstab, h->subx, h->rinfo, h->sparse_div);
+        k_score<<<dim3(gsx, n), IG_THREADS, IG_SCORE_SMEM, ks>>>(h->row_ptr, h->cv, h->coord, h->clen, h->sc, h->desc, h->rows, h->rowidx,
+                                                                h->ns, h->row_cnt, h->table, h->table_len, mbar, h->exz, h->part_nz,
+                                                                h->part_c, h->gs_div, h->clstab, h->subx, h->rinfo, h->sparse_div);
+        if (ks != h->stream) {
+            cudaEventRecord(h->ev_ksc, ks);
+            cudaStreamWaitEvent(h->stream, h->ev_ksc, 0);
+        }
     }
     if (h->profile && !h->capturing) cudaEventRecord(h->ev[5], h->stream);
 }
@@ -694,7 +710,7 @@ static int score_candidates(ig_handle* h, int a, const int32_t* cands, int n, in
     CK(cudaMemcpyAsync(&h->sc->n_cands, hs, (2 + IG_MAX_CANDS) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     const FragRec* live = h->live;
     k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, first_flip_eject, nullptr, h->streaming ? h->stream_rows_max : 0);
-    k_find_cuts<<<dim3((h->nf + 255) / 256, n), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc, h->clstab);
+    k_find_cuts<<<(h->nf + 255) / 256, 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc, h->clstab);
     k_classes<<<n, IG_N_OPS * 32, 0, h->stream>>>(h->sc, h->desc, h->clstab, h->rigid, h->cfg.mean_sub_len_kb);
     if (overlap) cudaStreamWaitEvent(h->stream, h->ev_coords, 0);
     enqueue_scoring(h, n, false);
@@ -804,7 +820,7 @@ static int enqueue_step(ig_handle* h, int full, int n_grid_cands, int cycle = 0)
     IG_MARK(0);
     k_cand_setup<<<1, 32, 0, h->stream>>>(live, h->sc, h->desc, h->cfg.max_bounds_insert, 1, cycle ? h->cyc_in : nullptr, h->streaming ? h->stream_rows_max : 0);
     IG_MARK(1);
-    k_find_cuts<<<dim3((h->nf + 255) / 256, n), 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc, h->clstab);
+    k_find_cuts<<<(h->nf + 255) / 256, 256, 0, h->stream>>>(live, h->nf, h->sc, h->desc, h->clstab);
     cudaEventRecord(h->ev_cuts, h->stream);
     cudaStreamWaitEvent(h->pf, h->ev_cuts, 0);
     k_classes<<<n, IG_N_OPS * 32, 0, h->pf>>>(h->sc, h->desc, h->clstab, h->rigid, h->cfg.mean_sub_len_kb);   // beside the row list; k_score needs it
