@@ -317,18 +317,26 @@ k_stream(const int2* __restrict__ cv, const CoordRec* __restrict__ coord, const 
         const unsigned short* my_cls = cls16 + (size_t)k * ns;
         FlatRec* my_list = list + (size_t)k * list_cap;
         int sel_w = 0, read_w = 0;
+        // software pipeline: the NEXT item's row record and the NEXT trip's contacts are in flight while this trip is classified
+        RowInfo info_nxt;
+        if (wg < n_items) info_nxt = rinfo[(size_t)k * ns + wg / parts];
         for (int it = wg; it < n_items; it += nw) {
             const int ri = it / parts, part = it - ri * parts;
-            const RowInfo info = rinfo[(size_t)k * ns + ri];
+            const RowInfo info = info_nxt;
+            if (it + nw < n_items) info_nxt = rinfo[(size_t)k * ns + (it + nw) / parts];
             const CoordRec ci = info.ci;
             const unsigned* mrow = s_mask + info.cls * IG_MAX_CLS;
             const unsigned fr = window_flags(ci.pos, ci_k);
             const long long b = info.b, e = info.b + info.n;
             int row_sel = 0;
-            for (long long k0 = (b & ~1LL) + 64 * part; k0 < e; k0 += 64 * parts) {
+            const long long k_first = (b & ~1LL) + 64 * part, k_step = 64 * parts;
+            int4 c2_nxt = make_int4(0, 0, 0, 0);
+            if (k_first + 2 * lane < e) c2_nxt = __ldcs(reinterpret_cast<const int4*>(cv + k_first + 2 * lane));
+            for (long long k0 = k_first; k0 < e; k0 += k_step) {
                 const long long kk = k0 + 2 * lane;
-                int4 c2 = make_int4(0, 0, 0, 0);
-                if (kk < e) c2 = __ldcs(reinterpret_cast<const int4*>(cv + kk));
+                const int4 c2 = c2_nxt;
+                c2_nxt = make_int4(0, 0, 0, 0);
+                if (kk + k_step < e) c2_nxt = __ldcs(reinterpret_cast<const int4*>(cv + kk + k_step));
                 unsigned m0 = 0, m1 = 0;
                 if (kk >= b && kk < e && c2.y > 0 && ((s_bits[c2.x >> 5] >> (c2.x & 31)) & 1u)) {
                     const unsigned cb = my_cls[c2.x];
