@@ -329,6 +329,12 @@ __global__ void k_exz_table(float* __restrict__ tab, int n, const DevScalars* __
         tab[d] = (s_z < p.d_max) ? rippe_contacts(s_z, p) : p.v_inter;
     }
 }
+__global__ void k_set_params_dev(DevScalars* sc, const float* __restrict__ p8, int test) {   // parameters from device memory (graph replay)
+    Params p;
+    p.kuhn = p8[0]; p.lm = p8[1]; p.c1 = p8[2]; p.slope = p8[3]; p.d = p8[4]; p.d_max = p8[5]; p.fact = p8[6]; p.v_inter = p8[7];
+    if (test) { sc->p_test = p; sc->log10_vinter_test = log10((double)p.v_inter); }
+    else { sc->p = p; sc->log10_vinter = log10((double)p.v_inter); }
+}
 __global__ void k_set_params(DevScalars* sc, Params p, int test) {
     if (test) { sc->p_test = p; sc->log10_vinter_test = log10((double)p.v_inter); }
     else { sc->p = p; sc->log10_vinter = log10((double)p.v_inter); }

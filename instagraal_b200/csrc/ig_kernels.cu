@@ -159,6 +159,7 @@ struct ig_handle {
     int* cyc_frags;
     double *part_full; int n_part_full;
     // cached per-contact records of the full likelihood (k_lnz_refresh / k_lnz_stream): 8 B x nnz per chain
+    cudaGraphExec_t graph_nuis = nullptr; bool nuis_graph_failed = false; float *h_p8 = nullptr, *d_p8 = nullptr;   // nuisance evaluation as one graph
     int2* lnz_rec; unsigned char* row_dirty; int dp_bits; bool lnz_cache; int grid_lnz; long long lnz_pairs; int lnz_pad;
     double *part_zc; int* part_nc; int n_part_zc;
     int *d_nuniq, *d_nsub, *d_perm;
@@ -370,6 +371,8 @@ static int create_impl(const ig_config* cfg, const ig_level_data* data, ig_handl
         if (dev_alloc(h, &h->d_hist, 1 << 16)) return -2;
         CK(cudaMallocHost((void**)&h->h_sc, sizeof(DevScalars)));
         CK(cudaMallocHost((void**)&h->h_small, 64 * sizeof(int)));
+        CK(cudaMallocHost((void**)&h->h_p8, sizeof(Params)));
+        if (dev_alloc(h, &h->d_p8, 8)) return -2;
         CK(cudaMemsetAsync(h->sc, 0, sizeof(DevScalars), h->stream));
         // uploads
         if (parent) {
@@ -492,6 +495,9 @@ extern "C" void ig_destroy(ig_handle* h) {
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_sc) cudaFreeHost(h->h_sc);
     if (h->h_small) cudaFreeHost(h->h_small);
+    if (h->h_p8) cudaFreeHost(h->h_p8);
+    if (h->d_p8) cudaFree(h->d_p8);
+    if (h->graph_nuis) cudaGraphExecDestroy(h->graph_nuis);
     for (int i = 0; i < 6; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 16; i++) if (h->evk[i]) cudaEventDestroy(h->evk[i]);
     for (int i = 0; i < 6; i++) for (int j = 0; j <= IG_MAX_CANDS; j++) if (h->graph[i][j]) cudaGraphExecDestroy(h->graph[i][j]);
@@ -1190,19 +1196,18 @@ extern "C" int ig_apply(ig_handle* h, int32_t id_frag, int32_t id_cand, int32_t 
     return 0;
 }
 
-extern "C" int ig_full_likelihood(ig_handle* h, const float p8[8], int32_t use_stale_coords, double out3[3]) {
-    if (use(h)) return -1;
+// everything one nuisance-likelihood evaluation enqueues (test parameters in the pinned h->h_p8): used directly and under
+// graph capture.  write_coords = 0: on the coordinates of the last fill (quirk Q5)
+static void enqueue_full_likelihood(ig_handle* h, int write_coords, bool records) {
     const float mbar = h->cfg.mean_sub_len_kb;
-    Params p; memcpy(&p, p8, sizeof p);
-    k_set_params<<<1, 1, 0, h->stream>>>(h->sc, p, 1);
+    cudaMemcpyAsync(h->d_p8, h->h_p8, sizeof(Params), cudaMemcpyHostToDevice, h->stream);
+    k_set_params_dev<<<1, 1, 0, h->stream>>>(h->sc, h->d_p8, 1);
     k_exz_table<<<std::min(1024, (h->ns + 256) / 256), 256, 0, h->stream>>>(h->exz_test, h->ns + 1, h->sc, mbar, 1);
-    const int write = (use_stale_coords && h->coords_ever) ? 0 : 1;
-    if (write) { h->coords_ever = true; h->coords_fresh = true; }
     k_coords<<<h->n_part_zc, IG_THREADS, 0, h->stream>>>(h->live, h->sub, h->coord, h->clen, h->ns, h->sc, mbar, 1,
-                                                        h->part_zc, h->part_nc, write, h->subx, h->row_dirty);
+                                                        h->part_zc, h->part_nc, write_coords, h->subx, h->row_dirty);
     k_reduce<<<1, 256, 0, h->stream>>>(h->part_zc, h->n_part_zc, &h->sc->full_out[1], h->part_nc, &h->sc->full_nintra);
     cudaEventRecord(h->ev[2], h->stream);
-    if (h->lnz_cache && p.v_inter > 0.0f) {
+    if (records) {
         // records of the rows whose coordinates were rewritten since the last call (+ circular contigs), then the flat pass
         k_lnz_refresh<<<h->grid_lnz, IG_THREADS, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->ns, h->sc, mbar, 1, h->exz_test,
                                                                  h->lnz_rec, h->row_dirty, h->dp_bits, h->part_full + h->grid_lnz);
@@ -1210,20 +1215,47 @@ extern "C" int ig_full_likelihood(ig_handle* h, const float p8[8], int32_t use_s
                                                                 h->lvl->val_total, h->sc, 1, h->exz_test, h->dp_bits, h->part_full);
         cudaEventRecord(h->ev[3], h->stream);
         k_reduce<<<1, 256, 0, h->stream>>>(h->part_full, 2 * h->grid_lnz, &h->sc->full_out[0], nullptr, nullptr);
-        h->n_launches += 1;
     } else {
         k_full_lnz<<<h->n_part_full, IG_THREADS, 0, h->stream>>>(h->row_ptr, h->cv, h->coord, h->clen, h->ns, h->sc, mbar, 1,
                                                                 h->exz_test, h->part_full);
         cudaEventRecord(h->ev[3], h->stream);
         k_reduce<<<1, 256, 0, h->stream>>>(h->part_full, h->n_part_full, &h->sc->full_out[0], nullptr, nullptr);
     }
+    // full_out[3] + full_nintra: 32 contiguous bytes of the scalar record
+    cudaMemcpyAsync(&h->h_sc->full_out[0], &h->sc->full_out[0], 3 * sizeof(double) + 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+}
+
+extern "C" int ig_full_likelihood(ig_handle* h, const float p8[8], int32_t use_stale_coords, double out3[3]) {
+    if (use(h)) return -1;
+    Params p; memcpy(&p, p8, sizeof p);
+    memcpy(h->h_p8, p8, sizeof(Params));
+    const int write = (use_stale_coords && h->coords_ever) ? 0 : 1;
+    if (write) { h->coords_ever = true; h->coords_fresh = true; }
+    const bool records = h->lnz_cache && p.v_inter > 0.0f;
+    // the nuisance step's evaluation (stale coordinates, records) replays as ONE CUDA graph: 8 launches + 2 copies otherwise
+    bool graphed = false;
+    if (!write && records && h->use_graph && !h->nuis_graph_failed) {
+        if (!h->graph_nuis) {
+            cudaGraph_t g = nullptr;
+            cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+            if (e == cudaSuccess) {
+                enqueue_full_likelihood(h, 0, true);
+                e = cudaStreamEndCapture(h->stream, &g);
+            }
+            if (e == cudaSuccess && g) e = cudaGraphInstantiate(&h->graph_nuis, g, 0);
+            if (g) cudaGraphDestroy(g);
+            if (e != cudaSuccess || !h->graph_nuis) { h->graph_nuis = nullptr; h->nuis_graph_failed = true; cudaGetLastError(); }
+        }
+        if (h->graph_nuis) { CK(cudaGraphLaunch(h->graph_nuis, h->stream)); graphed = true; }
+    }
+    if (!graphed) enqueue_full_likelihood(h, write, records);
     if (launch_ok(h, "full_likelihood")) return -2;
-    h->n_launches += 6;
-    CK(cudaMemcpyAsync(h->h_sc, h->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, h->stream));
+    h->n_launches += records ? 7 : 6;
     CK(cudaStreamSynchronize(h->stream));
-    {   // device time of the nuisance likelihood (always measured: two events per call)
+    {   // device time of the likelihood kernels (always measured: two events per call)
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) { h->ms_nuis += ms; h->n_nuis++; }
+        else { cudaGetLastError(); if (graphed) h->nuis_graph_failed = true; }   // (events recorded by graph nodes must stay measurable)
     }
     out3[0] = h->h_sc->full_out[0];
     out3[1] = h->h_sc->full_out[1];

@@ -177,6 +177,7 @@ class sampler:
         self._spec = None
         self._spec_pool = None
         self._twin = None
+        self._twin_synced = False
         self.n_nuis_overlapped = 0
         self.modification_str = [  # CL:1601-1620
             "eject frag", "flip frag", "pop out split insert @ left or 1", "pop out split insert @ left or -1",
@@ -211,7 +212,7 @@ class sampler:
         s.all_scores = np.zeros(0)
         s.n_proposals_scored = 0
         s.likelihood_t = None
-        s._nuis_follows, s._spec, s._spec_pool, s._twin = False, None, None, None
+        s._nuis_follows, s._spec, s._spec_pool, s._twin, s._twin_synced = False, None, None, None, False
         s._res = L.ig_step_result()
         s._res_scores = np.frombuffer(s._res, dtype=np.float64, count=L.IG_MAX_CANDS * L.IG_N_OPS, offset=L.ig_step_result.scores.offset)
         s._res_nuniq = np.frombuffer(s._res, dtype=np.int32, count=L.IG_MAX_CANDS, offset=L.ig_step_result.n_uniq.offset)
@@ -675,11 +676,22 @@ class sampler:
         try:
             if self._twin is None:
                 self._twin = np.random.RandomState()
-            self._twin.set_state(np.random.get_state())
+                self._twin_addr = self._twin._bit_generator.ctypes.state_address
+                self._glob_addr = np.random.mtrand._rand._bit_generator.ctypes.state_address
+                self._twin_synced = False
+            if self._twin_synced:
+                # the Mersenne-Twister words + position (624 x 4 + 4 bytes) straight from the global generator; the cached
+                # second Gaussian of the legacy stream is already the same in both: since the last full copy every normal()
+                # the global made was made by the twin first, from the same state (checked when the prediction is adopted)
+                C.memmove(self._twin_addr, self._glob_addr, 624 * 4 + 4)
+            else:
+                self._twin.set_state(np.random.get_state())   # full copy, ~0.1 ms (first use, or after a missed prediction)
+                self._twin_synced = True
             key = self.param_simu.tobytes()
             id_modif, draw = self._nuisance_draws(self._twin)
             return (key, id_modif, draw, self._nuisance_finish(id_modif, draw))
         except Exception:
+            self._twin_synced = False
             return None
 
     def step_nuisance_parameters(self, dt, t, n_step):
@@ -692,6 +704,7 @@ class sampler:
             out_test_param = spec[3]
             self.n_nuis_overlapped += 1
         else:
+            self._twin_synced = False   # the twin's Gaussian cache may have parted from the global one: full copy next time
             out_test_param = self._nuisance_finish(id_modif, draw)
         self.param_simu_test = out_test_param
         self.likelihood_nuis = self.eval_likelihood_4_nuisance()
