@@ -296,8 +296,13 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
     const unsigned* g_mask = clstab[k].mask;    // small per-candidate tables: read through L1
     const unsigned* g_farok = clstab[k].farok;
     const IgMotion* g_mot = clstab[k].mot;
+    const unsigned* g_rep = clstab[k].repmask;
+    const unsigned* g_mem = clstab[k].members;
     const float far_s = clstab[k].far_s;
     const int far_dp = clstab[k].far_dp;
+    // whole-row items (all 24 slots in one item): slots whose two classes undergo the same motions are evaluated once, through
+    // their representative, and the result is credited to every member of the group (bit-identical terms)
+    const bool dedup = gs == IG_N_OPS;
     if (lane < 25) red[w][lane] = 0.0;
     if (lane < 2) redi[w][lane] = 0;
     for (int u = 0; u < IG_N_OPS; u++) acc_s[u * IG_THREADS + threadIdx.x] = 0.0;  // kept zero between items (see the item epilogue)
@@ -378,34 +383,39 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
                 }
             }
             if (ahead && q + q_step < e) cj_nxt = coord[c_nxt.x];
-            const unsigned um = __reduce_or_sync(0xffffffffu, m);
+            // mr = the slots to EVALUATE (group representatives when dedup; u0 == 0 then), m = the slots to credit
+            const int t_pair = cls_r * IG_MAX_CLS + (x.rjc >> IG_CLS_SHIFT);
+            const unsigned mr = (dedup && m) ? (m & __ldg(&g_rep[t_pair])) : m;
+            const unsigned um = __reduce_or_sync(0xffffffffu, mr);
             if (!um) continue;
             unsigned chg = 0;
             // number of (contact, mutation) pairs of this chunk
-            const int n_pairs = __reduce_add_sync(0xffffffffu, __popc(m));
+            const int n_pairs = __reduce_add_sync(0xffffffffu, __popc(mr));
             if (n_pairs * (sparse_div & 0xffff) > __popc(um) * 32) {
                 // DENSE: most lanes take part in most mutations -> loop over the mutations, lane = contact
 #pragma unroll 1
                 for (unsigned uw = um; uw; uw &= uw - 1) {
                     const int u = __ffs(uw) - 1;
                     float s_m = 0.f; int dp_m = 0; bool push = false;
-                    if ((m >> u) & 1u) {
+                    unsigned mem = 1u << (u - u0);
+                    if ((mr >> u) & 1u) {
                         double add;
                         if (eval_pair(x, u, myrow[u - u0], g_mot, ci.s_tot, p, l10v, inter_const, mbar, exz_tab, tab, tlen, ns, s_m, dp_m, push, add)) {
-                            chg |= 1u << (u - u0);
-                            my_acc[(u - u0) * IG_THREADS] += add;
+                            if (dedup) mem = __ldg(&g_mem[t_pair * IG_N_OPS + u]) & m;
+                            chg |= mem;
+                            for (unsigned mm = mem; mm; mm &= mm - 1) my_acc[(__ffs(mm) - 1) * IG_THREADS] += add;
                         }
                     }
-                    queue_push(push, s_m, dp_m, 1u << (u - u0), x.val, myq, qn, my_acc, p, l10v, exz_tab);
+                    queue_push(push, s_m, dp_m, mem, x.val, myq, qn, my_acc, p, l10v, exz_tab);
                 }
             } else {
                 // SPARSE (long contigs: only the contacts that cross a breakpoint change): the pairs are dealt
                 // densely to the lanes; the executing lane fetches the contact from its owner by shuffles
-                int pre = __popc(m);   // inclusive prefix over the lanes
+                int pre = __popc(mr);   // inclusive prefix over the lanes
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += y; }
                 __syncwarp();
-                mychg[lane] = 0; myoff[lane] = pre - __popc(m);
+                mychg[lane] = 0; myoff[lane] = pre - __popc(mr);
                 __syncwarp();
 #pragma unroll 1
                 for (int base = 0; base < n_pairs; base += 32) {
@@ -416,7 +426,8 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
 #pragma unroll
                         for (int stp = 16; stp > 0; stp >>= 1) if (src + stp < 32 && myoff[src + stp] <= pi) src += stp;
                     }
-                    const unsigned msrc = __shfl_sync(0xffffffffu, m, src);
+                    const unsigned msrc = __shfl_sync(0xffffffffu, mr, src);
+                    const unsigned mfull = __shfl_sync(0xffffffffu, m, src);
                     Ctc y;
                     y.pos = __shfl_sync(0xffffffffu, x.pos, src); y.start_bp = __shfl_sync(0xffffffffu, x.start_bp, src);
                     y.len_ori = __shfl_sync(0xffffffffu, x.len_ori, src); y.watson = __shfl_sync(0xffffffffu, x.watson, src);
@@ -426,15 +437,18 @@ k_score(const long long* __restrict__ row_ptr, const int2* __restrict__ cv, cons
                     y.flags = __shfl_sync(0xffffffffu, x.flags, src);
                     float s_m = 0.f; int dp_m = 0; bool push = false;
                     int u = u0;
+                    unsigned mem = 0;
                     if (valid) {
                         u = __fns(msrc, 0, pi - myoff[src] + 1);
+                        mem = 1u << (u - u0);
                         double add;
                         if (eval_pair(y, u, myrow[u - u0], g_mot, ci.s_tot, p, l10v, inter_const, mbar, exz_tab, tab, tlen, ns, s_m, dp_m, push, add)) {
-                            atomicOr(&mychg[src], 1u << (u - u0));
-                            my_acc[(u - u0) * IG_THREADS] += add;
+                            if (dedup) mem = __ldg(&g_mem[(cls_r * IG_MAX_CLS + (y.rjc >> IG_CLS_SHIFT)) * IG_N_OPS + u]) & mfull;
+                            atomicOr(&mychg[src], mem);
+                            for (unsigned mm = mem; mm; mm &= mm - 1) my_acc[(__ffs(mm) - 1) * IG_THREADS] += add;
                         }
                     }
-                    queue_push(push, s_m, dp_m, 1u << (u - u0), y.val, myq, qn, my_acc, p, l10v, exz_tab);
+                    queue_push(push, s_m, dp_m, mem, y.val, myq, qn, my_acc, p, l10v, exz_tab);
                 }
                 __syncwarp();
                 chg = mychg[lane];

@@ -158,6 +158,26 @@ k_classes(const DevScalars* __restrict__ sc, const IgDescriptor* __restrict__ de
             for (int u = 0; u < n_uniq; u++)
                 if (ig_class_pair_far_ok(s_sig[c1][u], s_sig[c2][u])) fo |= 1u << u;
         ct.farok[t] = fo;
+        // groups of slots with identical motions of both classes (ig_class_pair_same_motion): lowest slot = representative
+        unsigned rep = 0, mem[IG_N_OPS];
+#pragma unroll
+        for (int u = 0; u < IG_N_OPS; u++) mem[u] = 0;
+        if (s_have[c1] && s_have[c2] && !circ_a && !circ_b) {
+            for (int u = 0; u < n_uniq; u++) {
+                if (!((m >> u) & 1u)) continue;
+                int r = -1;
+                for (unsigned rr = rep; rr && r < 0; rr &= rr - 1) {
+                    const int v = __ffs(rr) - 1;
+                    if (ig_class_pair_same_motion(s_sig[c1][v], s_sig[c2][v], s_sig[c1][u], s_sig[c2][u])) r = v;
+                }
+                if (r < 0) { rep |= 1u << u; mem[u] = 1u << u; } else mem[r] |= 1u << u;
+            }
+        } else {
+            rep = m;
+            for (int u = 0; u < IG_N_OPS; u++) mem[u] = 1u << u;
+        }
+        ct.repmask[t] = rep;
+        for (int u = 0; u < IG_N_OPS; u++) ct.members[t * IG_N_OPS + u] = mem[u];
     }
     // margin: twice the largest shift of any class under any non-reflecting mutation
     if (threadIdx.x < 32) {

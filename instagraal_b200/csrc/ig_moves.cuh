@@ -558,7 +558,20 @@ struct IgClassTab {
     // before AND after every mutation that does not reflect either end: bit u of farok[c1][c2] marks those.
     unsigned farok[IG_MAX_CLS * IG_MAX_CLS];
     float far_s; int far_dp;
+    // Uniq slots whose two classes undergo the SAME motions give a contact between them bit-identical terms (same float32
+    // operations on the same inputs): repmask = one representative per group of such slots (subset of mask),
+    // members[pair][representative] = the slots of its group.  Whole-row work items of the scoring kernel evaluate the
+    // representatives only and credit the result to every member.
+    unsigned repmask[IG_MAX_CLS * IG_MAX_CLS];
+    unsigned members[IG_MAX_CLS * IG_MAX_CLS * IG_N_OPS];
 };
+// do uniq slots with signatures (a1, a2) and (b1, b2) of the two classes of a pair give every contact the same term?
+IG_HD int ig_class_pair_same_motion(const IgSig& a1, const IgSig& a2, const IgSig& b1, const IgSig& b2) {
+    if (a1.circ | a2.circ | b1.circ | b2.circ) return 0;   // (circular contigs: the term also depends on the contig length)
+    if (a1.dbp != b1.dbp || a1.dsp != b1.dsp || a1.flip != b1.flip) return 0;
+    if (a2.dbp != b2.dbp || a2.dsp != b2.dsp || a2.flip != b2.flip) return 0;
+    return (a1.id_c == a2.id_c) == (b1.id_c == b2.id_c);
+}
 
 // breakpoints in fragment-position units (bpf) and sub-fragment-position units (bps)
 IG_HD void ig_class_breakpoints(const IgDescriptor& d, int* bpf, int* bps, int* bpbf, int* bpbs) {
