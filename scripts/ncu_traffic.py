@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel captured in an `ncu --set full` report, written to
 profiles/r2_traffic.json under the key bench.py looks up ("<workload>/<mode>/<state>/<kernel>"):
-   python scripts/ncu_traffic.py G/exact/assembled/scoring gpurun_out/r2_score_G_true.ncu-rep [key report ...]"""
+   python scripts/ncu_traffic.py [--sum] G/exact/assembled/scoring gpurun_out/r2_score_G_true.ncu-rep [key report ...]"""
 import csv, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -18,10 +18,16 @@ def traffic(rep):
             i = hdr.index(m)
             tot += float(r[i]) * UNIT[units[i]]
     name = rows[2][hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
-    return tot / max(launches, 1), name, launches
+    return (tot if SUM else tot / max(launches, 1)), name, launches
+
+
+SUM = False
 
 
 def main(argv):
+    global SUM
+    if argv and argv[0] == "--sum":   # the report holds the kernels of ONE evaluation (e.g. k_lnz_refresh + k_lnz_stream): add them up
+        SUM, argv = True, argv[1:]
     path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     d = json.load(open(path)) if os.path.exists(path) else {}
     for key, rep in zip(argv[0::2], argv[1::2]):
