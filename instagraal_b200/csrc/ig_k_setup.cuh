@@ -158,7 +158,10 @@ k_classes(const DevScalars* __restrict__ sc, const IgDescriptor* __restrict__ de
             for (int u = 0; u < n_uniq; u++)
                 if (ig_class_pair_far_ok(s_sig[c1][u], s_sig[c2][u])) fo |= 1u << u;
         ct.farok[t] = fo;
-        // groups of slots with identical motions of both classes (ig_class_pair_same_motion): lowest slot = representative
+        // groups of slots with identical motions of both classes (ig_class_pair_same_motion): lowest slot = representative.
+        // Only the row-per-warp kernel reads them: skipped for candidates that take the streaming path (this kernel sits
+        // beside the row list on the step's critical path at mid-assembly; the grouping is a few thousand instructions).
+        if (sc->use_stream[k]) continue;
         unsigned rep = 0, mem[IG_N_OPS];
 #pragma unroll
         for (int u = 0; u < IG_N_OPS; u++) mem[u] = 0;
