@@ -431,11 +431,15 @@ def run_ours(args):
             }
         out["single_chain"] = scs
         hd = scs[start_name]
-        dom = "scoring" if hd["kernels"]["scoring"]["ms_per_step"] >= hd["kernels"]["k_full_lnz"]["ms_per_launch"] else "k_full_lnz"
+        # the top-level object is the SCORING kernels: the only ones of the two that run inside the headline's timed region
+        # (step_sampler without the nuisance step) and the ones north_star's roofline target names; the full likelihood of the
+        # nuisance step (k_lnz_stream), which takes longer per call at mid-assembly, is listed beside them under "kernels"
+        dom = "scoring"
         kd = hd["kernels"][dom]
         out["roofline"] = {"bound": "hbm", "kernel": dom, "state": start_name,
                            "achieved": kd["achieved_GBs"], "peak": peak, "unit": "GB/s", "frac": kd["frac_hbm"],
                            "traffic": kd["traffic"], "peak_source": peak_src,
+                           "share_of_step": kd["ms_per_step"] / hd["ms_per_step"],
                            "kernels": {st_: scs[st_]["kernels"] for st_ in scs}}
         if not big:
             l2 = measure_l2_peak(torch, dev)
