@@ -25,7 +25,10 @@ import numpy as np
 
 from . import _lib as L
 from . import host_rng
-from . import rippe_fit as opti
+try:   # inside the reference's tree: its own host-side p(s) fitting module (scipy leastsq / fsolve), untouched
+    from instagraal import optim_rippe_curve_update as opti
+except ImportError:   # stand-alone: the restatement of the same functions
+    from . import rippe_fit as opti
 
 FIELDS13 = L.FIELDS13
 ALL17 = ("pos", "sub_pos", "id_c", "start_bp", "len_bp", "sub_len", "circ", "id", "prev", "next",

@@ -14,8 +14,7 @@ The contact arrays come from ``pyramid.hdf5`` when h5py is importable (group ``"
 ``pyramid_build.fill_sparse_pyramid_level`` (GPU binning, same row order as the reference's HDF5 writer); a caller may also
 pass any mapping with that layout as ``data=``.
 
-Reference behaviours kept on purpose (golden vectors from the unmodified reference classes, oracle/make_pyramid_load_golden.py,
-tests/test_pyramid_load.py):
+Reference behaviours kept on purpose (golden vectors dumped from the unmodified reference classes, tests/test_pyramid_load.py):
   * the scaffold arrays are listed contig by contig (order of first appearance of the contig name), not by fragment id;
   * ``sub_l_cont`` is the number of fragments of the same contig one level below (the level itself at level 0);
   * ``mean_value_trans = total_trans / np.float32(n_pairs_trans)`` -- the divisor is rounded to float32 first (PS:1888-1889);
