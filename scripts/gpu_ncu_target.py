@@ -8,7 +8,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 ap = argparse.ArgumentParser()
-ap.add_argument("--workload", default="G"); ap.add_argument("--state", default="true", choices=["init", "true", "mid"])
+ap.add_argument("--workload", default="G"); ap.add_argument("--state", default="true", choices=["init", "true", "mid", "file"])
+ap.add_argument("--state-file", default="/tmp/ig_state13.npy", help="--state file: scaffold saved by an earlier --save-state run (burn-in outside ncu)")
+ap.add_argument("--save-state", action="store_true", help="reach the state, save the 13 x NF scaffold to --state-file and exit")
 ap.add_argument("--steps", type=int, default=6); ap.add_argument("--nuis", type=int, default=4)
 ap.add_argument("--rigid", type=int, default=0); ap.add_argument("--burn", type=int, default=2)
 a = ap.parse_args()
@@ -23,6 +25,13 @@ elif a.state == "mid":
     np.random.seed(1000); s.bomb_the_genome(); frs = np.arange(level.n_frags)
     for c in range(a.burn):
         np.random.shuffle(frs); s.run_cycle_device(frs, 5, seed=1000, cycle=c)
+elif a.state == "file":
+    s._set_state(np.load(a.state_file))
+if a.save_state:
+    np.save(a.state_file, np.asarray(s._get_state()))
+    print("saved", a.state_file, "n_contigs", int(s.n_contigs) if s.n_contigs is not None else None)
+    s.free_gpu()
+    sys.exit(0)
 s.set_options(refresh_every=4096, use_graph=False)
 np.random.seed(5)
 frs = np.random.permutation(level.n_frags)

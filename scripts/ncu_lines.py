@@ -5,8 +5,9 @@ import subprocess
 import sys
 
 
-def main(rep, top=32):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+def main(rep, top=32, extra=()):
+    """extra: ncu filter options for reports that hold several launches, e.g. --launch-skip 1 --launch-count 1"""
+    raw = subprocess.run(["ncu", "-i", rep, *extra, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr = rows[0]
     want = ["gpu__time_duration.sum", "launch__grid_size", "smsp__inst_executed.sum", "sm__inst_executed.avg.per_cycle_elapsed",
@@ -21,7 +22,7 @@ def main(rep, top=32):
         for i, h in enumerate(hdr):
             if "issue_stalled" in h and "per_issue_active" in h and float(r[i] or 0) > 0.3:
                 print("  stall", h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), r[i])
-    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True,
+    src = subprocess.run(["ncu", "-i", rep, *extra, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True,
                          text=True).stdout.splitlines()
     # one section per source file of the kernel (the kernels live in several included .cuh files)
     idx = [i for i, l in enumerate(src) if l.startswith('"Line No","Source","Address"')]
@@ -70,4 +71,4 @@ def main(rep, top=32):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], extra=tuple(sys.argv[2:]))
