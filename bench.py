@@ -440,6 +440,8 @@ def run_ours(args):
                            "achieved": kd["achieved_GBs"], "peak": peak, "unit": "GB/s", "frac": kd["frac_hbm"],
                            "traffic": kd["traffic"], "peak_source": peak_src,
                            "share_of_step": kd["ms_per_step"] / hd["ms_per_step"],
+                           "traffic_source": "profiles/r2_traffic.json: dram__bytes_read + write per step from the committed ncu --set full "
+                                             "captures of this workload and state (cold caches: ncu flushes the L2 before every kernel)",
                            "kernels": {st_: scs[st_]["kernels"] for st_ in scs}}
         if not big:
             l2 = measure_l2_peak(torch, dev)
