@@ -613,7 +613,7 @@ def run_reference(args):
                    "chains": n_proc, "n_neighbours": 5,
                    "note": "the reference is GPU-only (pycuda); this arm is its algorithm transcribed to NumPy (oracle/), "
                            "one chain per host process from the contig-order start (the synthetic assembly's initial contigs: the "
-                           "regime of the GPU arm's mid-assembly state; reaching that state itself takes 2 MCMC cycles = weeks on the host)"},
+                           "regime of the GPU arm's mid-assembly state, which itself lies 2 MCMC cycles of this arm away: weeks on the host at the 1 Gb level)"},
         "cpu_baseline": {"value": v, "unit": "proposals/s", "cores": n_proc, "kind": "port",
                          "sample": "%d processes x <= %.0f s of step_sampler calls (%d steps, %d proposals), wall %.1f s"
                                    % (n_proc, budget, n_steps, n_prop, wall)},
