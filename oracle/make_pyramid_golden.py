@@ -17,10 +17,10 @@ ROOT = os.path.dirname(HERE)
 OUT = os.path.join(ROOT, "tests", "golden", "pyramid")
 
 
-def write_input(folder, seed=7):
+def write_input(folder, seed=7, n_frags=(1, 2, 3, 4, 7, 9, 10, 30, 61, 100, 5, 2, 140)):
     """what instagraal-pre writes (pre.py:244-292): fragments_list.txt, info_contigs.txt, abs_fragments_contacts_weighted.txt"""
     rng = np.random.RandomState(seed)
-    n_frags = [1, 2, 3, 4, 7, 9, 10, 30, 61, 100, 5, 2, 140]
+    n_frags = list(n_frags)
     os.makedirs(folder, exist_ok=True)
     with open(os.path.join(folder, "info_contigs.txt"), "w") as fc, open(os.path.join(folder, "fragments_list.txt"), "w") as ff:
         fc.write("contig\tlength\tn_frags\tcumul_length\n")

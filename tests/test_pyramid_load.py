@@ -160,3 +160,52 @@ def test_contacts_rebuilt_from_the_text_levels_when_h5py_is_missing(built):
         assert np.array_equal(lev.sparse_mat_csr.indices, g["L%d_csr_indices" % l])
         assert float(lev.mean_value_trans) == float(g["L%d_mean_value_trans" % l])
     pyr.close()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/instagraal"), reason="differential run against the live reference (build container only)")
+@pytest.mark.parametrize("seed,n_frags", [(11, (40,)), (12, (3, 1, 1, 25, 2)), (13, (9, 9, 9, 9, 9, 9, 9, 1))])
+def test_differential_against_the_live_reference_classes(tmp_path, seed, n_frags):
+    """fresh pyramid folders written by the reference's own build functions, loaded by the reference's classes and by ours:
+    a single contig (NaN -> min/10 fallback of mean_value_trans), one-fragment contigs, equal-length contigs"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, os, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "import oracle.make_pyramid_load_golden as ML, oracle.make_pyramid_golden as MG\n"
+        "PS = ML.reference_module()\n"
+        "base, out = %r, %r\n"
+        "MG.write_input(base, seed=%d, n_frags=%r)\n"
+        "res = MG.run(PS, base, out)\n"
+        "np.savez(os.path.join(out, 'hdf5_arrays.npz'), **res)\n"
+        "ML.FOLDER = out\n"
+        "import warnings; warnings.simplefilter('ignore')\n"
+        "np.savez(os.path.join(out, 'load.npz'), **ML.dump(PS.pyramid(out, ML.N_LEVELS), {}))\n"
+    ) % (root, str(tmp_path / "in"), str(tmp_path / "pyr"), seed, tuple(n_frags))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(tmp_path), timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    from instagraal_b200.pyramid_load import pyramid
+    out = str(tmp_path / "pyr")
+    g = np.load(os.path.join(out, "load.npz"))
+
+    class Rec(RecordedHdf5):
+        def __init__(self):
+            z = np.load(os.path.join(out, "hdf5_arrays.npz"))
+            self.g = {}
+            for k in z.files:
+                kind, lvl = k.rsplit("_", 1)
+                self.g.setdefault(lvl, {})[kind] = z[k] if kind == "data" else np.array([[int(z[k])]], dtype=np.int32)
+    pyr = pyramid(out, N_LEVELS, data=Rec())
+    for l in range(N_LEVELS):
+        lev = pyr.get_level(l)
+        assert lev.n_frags == int(g["L%d_n_frags" % l]) and lev.n_contigs == int(g["L%d_n_contigs" % l])
+        assert float(lev.mean_value_trans) == float(g["L%d_mean_value_trans" % l]), (l, lev.mean_value_trans)
+        assert type(lev.mean_value_trans).__name__ == str(g["L%d_mean_value_trans_type" % l])
+        for k in SOA_KEYS:
+            assert np.array_equal(lev.S_o_A_frags[k], g["L%d_soa_%s" % (l, k)]), (l, k)
+        assert np.array_equal(lev.sparse_mat_csr.data, g["L%d_csr_data" % l]) and np.array_equal(lev.sparse_mat_csr.indices, g["L%d_csr_indices" % l])
+        assert np.array_equal(lev.col_vect_frags_4_GL, g["L%d_col_gl" % l]) and np.array_equal(lev.pos_vect_frags_4_GL, g["L%d_pos_gl" % l])
+        fd = pyr.spec_level[str(l)]["fragments_dict"]
+        for k in FRAG_INFO_KEYS:
+            assert [fd[i][k] for i in sorted(fd)] == list(g["L%d_fd_%s" % (l, k)]), (l, k)
