@@ -7,6 +7,8 @@ Mirrors ``instagraal/pyramid_sparse.py`` (same function names, same arguments, s
   * ``subsample_data_set``        PS:468-724   contig list, fragment list, contact file and old->new index of the next level
   * ``fill_sparse_pyramid_level`` PS:331-397   the (3, nnz) int32 array + fragment count of a level's HDF5 group
   * ``build``                     PS:178-277   the level loop (text levels always; ``pyramid.hdf5`` when h5py is importable)
+  * ``remove_problematic_fragments`` PS:731-1030  the filtering step (locked fragments merged forward or destroyed)
+  * ``build_and_filter``          PS:30-176    what ``simulation.select_data_set`` calls: unfiltered level, filter, level loop, load
 
 The reference walks every contact line through nested Python dictionaries, once per level (hours at 1e8 contacts).  Here the
 bookkeeping of contigs / fragments is vectorised NumPy on the host and the contacts are binned on the GPU by
@@ -247,3 +249,172 @@ def build(base_folder, size_pyramid, factor, min_bin_per_contig, output_folder=N
     if pyramid_handle is not None:
         pyramid_handle.close()
     return nfrags_per_level
+
+
+def remove_problematic_fragments(contig_info, fragments_list, abs_fragments_contacts, new_contig_list_file, new_fragments_list_file,
+                                 new_abs_fragments_contacts_file, pyramid, thresh_factor=1, device=0):
+    """PS:731-1030, same arguments, files and return value (the sparsity threshold): the filtering step every real run starts
+    with (``build_and_filter``).  Fragments whose row of the symmetrised level-0 matrix is too empty (<= mean - thresh_factor *
+    std of the fill ratio), implausibly full (> mean + 50 std) or shorter than 50 bp are *locked*: a locked fragment is merged
+    into the next unlocked fragment of its contig, a trailing run of locked fragments is destroyed together with its contacts.
+
+    ``pyramid`` is the open HDF5 file of the unfiltered 1-level pyramid or any mapping with ``["0"]["data"]`` (3, nnz) and
+    ``["0"]["nfrags"]`` (1, 1).  The reference's two diagnostic PDF plots (written into the working directory) are not made.
+
+    Reference behaviours kept on purpose: a contig starts where the index column says 1; the first fragment written for a
+    contig starts at 0 whatever the file says, later ones at the END of the previously written fragment as spelled in the file;
+    ``accu_frag`` is the only accumulator that is not reset at a contig start, so the counts of a destroyed trailing run leak
+    into the first fragment written for the next contig (PS:880-893 vs. 948); the ``size <= 1`` lock never takes effect
+    (PS:909-910 sets the flag that the write overwrites); mean GC content via ``np.array(list).mean()``."""
+    import scipy.sparse as sp
+    lvl = pyramid["0"]
+    d = np.asarray(lvl["data"])
+    nfrags = int(np.asarray(lvl["nfrags"])[0, 0])
+    m = sp.csr_matrix((d[2, :], d[0:2, :]), shape=(nfrags, nfrags))
+    full = m + m.transpose()
+    sparsity = np.float32(np.diff(full.indptr)) / np.float32(nfrags)
+    mean_s, std_s = sparsity.mean(), sparsity.std()
+    thresh_max = mean_s + 50 * std_s
+    thresh = mean_s - thresh_factor * std_s
+    # ---- the fragment table (file order)
+    with open(fragments_list, "r") as h:
+        h.readline()
+        rows = [ln.split("\t") for ln in h if ln]
+    n_old = len(rows)
+    idx = np.fromiter((int(r[0]) for r in rows), dtype=np.int64, count=n_old)
+    chrom = [r[1] for r in rows]
+    end_s = [r[3] for r in rows]
+    size = np.fromiter((int(r[4]) for r in rows), dtype=np.int64, count=n_old)
+    gc = np.fromiter((float(r[5]) for r in rows), dtype=np.float64, count=n_old)
+    accu = np.fromiter((int(r[6]) for r in rows), dtype=np.int64, count=n_old)
+    length = np.fromiter((int(r[3]) - int(r[2]) for r in rows), dtype=np.int64, count=n_old)
+    lock = np.zeros(n_old, dtype=bool)
+    lock[np.flatnonzero(sparsity <= thresh)] = True
+    lock[np.flatnonzero(sparsity > thresh_max)] = True
+    lock[length < 50] = True
+    # ---- who is written, who merges into whom, who is destroyed
+    seg = np.cumsum(idx == 1)                         # contig segment of every line
+    wr = ~lock
+    widx = np.flatnonzero(wr)                         # lines that close a new fragment
+    n_new = widx.size
+    grp = np.cumsum(wr) - wr                          # new fragment (0-based) a line would end up in
+    has_writer = grp < n_new
+    writer_seg = np.full(n_old, -1, dtype=np.int64)
+    writer_seg[has_writer] = seg[widx[grp[has_writer]]]
+    merged = has_writer & (writer_seg == seg)         # same contig segment as the closing line
+    destroyed = ~merged
+    new_size = np.bincount(grp[merged], weights=size[merged], minlength=n_new).astype(np.int64)[:n_new]
+    new_accu = np.bincount(grp[has_writer], weights=accu[has_writer], minlength=n_new).astype(np.int64)[:n_new]   # (not reset at a contig start)
+    n_run = np.bincount(grp[merged], minlength=n_new)[:n_new]
+    first_in_seg = np.ones(n_new, dtype=bool)
+    if n_new > 1:
+        first_in_seg[1:] = seg[widx[1:]] != seg[widx[:-1]]
+    seg_start = np.flatnonzero(first_in_seg)
+    new_rel = np.arange(n_new) - np.repeat(seg_start, np.diff(np.r_[seg_start, n_new])) + 1
+    merged_idx = np.flatnonzero(merged)
+    run_start = np.searchsorted(grp[merged_idx], np.arange(n_new), side="left")
+    names, n_new_c, len_c = [], {}, {}
+    with open(contig_info, "r") as h:
+        h.readline()
+        for ln in h:
+            if ln:
+                dat = ln.split("\t")
+                int(dat[1]); int(dat[2]); int(dat[3])     # the reference parses them (get_contig_info_from_file)
+                names.append(dat[0]); n_new_c[dat[0]] = 0; len_c[dat[0]] = 0
+    with open(new_fragments_list_file, "w") as h:
+        h.write("%s\t%s\t%s\t%s\t%s\t%s\t%s\t%s\t%s\n" % ("id", "chrom", "start_pos", "end_pos", "size", "gc_content", "accu_frag",
+                                                            "frag_start", "frag_end"))
+        out = []
+        for k in range(n_new):
+            i = int(widx[k])
+            if n_run[k] == 1:
+                g = np.float64(gc[i])
+            else:
+                g = np.array(gc[merged_idx[run_start[k]:run_start[k] + n_run[k]]].tolist()).mean()
+            start = 0 if first_in_seg[k] else end_s[int(widx[k - 1])]
+            out.append("%s\t%s\t%s\t%s\t%s\t%s\t%s\t%s\t%s\n" % (str(int(new_rel[k])), chrom[i], start, end_s[i], str(int(new_size[k])), str(g),
+                                                                int(new_accu[k]), str(int(new_rel[k])), str(int(new_rel[k]))))
+            n_new_c[chrom[i]] += 1
+            len_c[chrom[i]] += int(new_size[k])
+        h.write("".join(out))
+    with open(new_contig_list_file, "w") as h:
+        h.write("%s\t%s\t%s\t%s\n" % ("contig", "length_kb", "n_frags", "cumul_length"))
+        cumul = 0
+        for c in names:
+            if n_new_c[c] > 0:
+                h.write("%s\t%s\t%s\t%s\n" % (c, str(len_c[c]), str(n_new_c[c]), str(cumul)))
+                cumul += n_new_c[c]
+    # ---- contacts: both ends must survive; re-binned on the GPU
+    fa, fb, nc = _read_contacts(abs_fragments_contacts, skip_first_data_line=False)
+    keep = ~(destroyed[fa] | destroyed[fb])
+    a, b, n = bin_contacts(fa[keep], fb[keep], nc[keep], old2new=np.where(destroyed, 0, grp), first_appearance_order=False, device=device)
+    _write_contacts(new_abs_fragments_contacts_file, a, b, n)
+    return thresh
+
+
+def build_and_filter(base_folder, size_pyramid, factor, thresh_factor=1, output_folder=None, device=0):
+    """PS:30-176: the unfiltered 1-level pyramid, the filtered level 0 (``remove_problematic_fragments``), then the level loop,
+    in the folder layout of the reference (``pyramids/pyramid_1_no_thresh``, ``pyramids/pyramid_<n>_thresh_auto``); returns the
+    loaded ``pyramid`` object (``pyramid_load.pyramid``).  ``pyramid.hdf5`` is written and read when h5py is importable;
+    without it the text levels are the cache and the contact arrays are rebuilt from them on load."""
+    from .pyramid_load import pyramid
+    try:
+        import h5py
+    except ImportError:
+        h5py = None
+    min_bin_per_contig = 1
+    pyramid_root = output_folder if output_folder is not None else base_folder
+    all_pyramid_folder = os.path.join(pyramid_root, "pyramids")
+    os.makedirs(all_pyramid_folder, exist_ok=True)
+    init_pyramid_folder = os.path.join(all_pyramid_folder, "pyramid_1_no_thresh")
+    if not os.path.exists(init_pyramid_folder):
+        build(base_folder, 1, factor, min_bin_per_contig, output_folder=pyramid_root, device=device)
+    init0 = os.path.join(init_pyramid_folder, "level_0")
+    contig_info = os.path.join(init0, "0_contig_info.txt")
+    fragments_list = os.path.join(init0, "0_fragments_list.txt")
+    init_contacts = os.path.join(init0, "0_abs_frag_contacts.txt")
+    pyramid_folder = os.path.join(all_pyramid_folder, "pyramid_" + str(size_pyramid) + "_thresh_auto")
+    level_folder = os.path.join(pyramid_folder, "level_0")
+    os.makedirs(level_folder, exist_ok=True)
+    cur_contigs = os.path.join(level_folder, "0_contig_info.txt")
+    cur_frags = os.path.join(level_folder, "0_fragments_list.txt")
+    cur_contacts = os.path.join(level_folder, "0_abs_frag_contacts.txt")
+    if not all(os.path.exists(p) for p in (cur_contigs, cur_frags, cur_contacts)):
+        if h5py is not None:
+            pyramid_0 = h5py.File(os.path.join(init_pyramid_folder, "pyramid.hdf5"), "r")
+        else:
+            n0 = file_len(fragments_list) - 1
+            pyramid_0 = {"0": {"data": fill_sparse_pyramid_level(None, 0, init_contacts, n0, device=device),
+                               "nfrags": np.array([[n0]], dtype=np.int32)}}
+        remove_problematic_fragments(contig_info, fragments_list, init_contacts, cur_contigs, cur_frags, cur_contacts, pyramid_0,
+                                     thresh_factor=thresh_factor, device=device)
+        if h5py is not None:
+            pyramid_0.close()
+    pyramid_handle = h5py.File(os.path.join(pyramid_folder, "pyramid.hdf5"), "a") if h5py is not None else None
+    sub_2_super = os.path.join(level_folder, "0_sub_2_super_index_frag.txt")
+    for level in range(0, size_pyramid):
+        level_folder = os.path.join(pyramid_folder, "level_" + str(level))
+        os.makedirs(level_folder, exist_ok=True)
+        pre = str(level) + "_"
+        new_contigs = os.path.join(level_folder, pre + "contig_info.txt")
+        new_frags = os.path.join(level_folder, pre + "fragments_list.txt")
+        new_contacts = os.path.join(level_folder, pre + "abs_frag_contacts.txt")
+        if level > 0 and not all(os.path.exists(p) for p in (new_contigs, new_frags, new_contacts, sub_2_super)):
+            nfrags = subsample_data_set(cur_contigs, cur_frags, factor, cur_contacts, new_contacts, min_bin_per_contig, new_contigs,
+                                        new_frags, sub_2_super, device=device)
+        else:
+            nfrags = file_len(new_frags) - 1
+        if pyramid_handle is not None:
+            try:
+                status = pyramid_handle.attrs[str(level)] == "done"
+            except KeyError:
+                pyramid_handle.attrs[str(level)] = "pending"
+                status = False
+            if not status:
+                fill_sparse_pyramid_level(pyramid_handle, level, new_contacts, nfrags, device=device)
+                pyramid_handle.attrs[str(level)] = "done"
+        cur_frags, cur_contigs, cur_contacts = new_frags, new_contigs, new_contacts
+        sub_2_super = os.path.join(level_folder, pre + "sub_2_super_index_frag.txt")
+    if pyramid_handle is not None:
+        pyramid_handle.close()
+    return pyramid(pyramid_folder, size_pyramid, device=device)

@@ -108,14 +108,39 @@ def run(PS, base, out, n_levels=4, factor=3, min_bin=1):
     return res
 
 
+class _NoPlot:
+    """remove_problematic_fragments draws two diagnostic plots into the working directory (PS:764-770); not part of any format"""
+
+    def __getattr__(self, name):
+        return lambda *a, **k: None
+
+
+def run_filter(PS, level0_dir, data0, nfrags0, out_dir, thresh_factor=1):
+    """the UNMODIFIED reference remove_problematic_fragments (PS:731-1030) on a level-0 folder; returns the threshold"""
+    PS.plt = _NoPlot()
+    os.makedirs(out_dir, exist_ok=True)
+    src = {k: os.path.join(level0_dir, "0_" + k) for k in ("contig_info.txt", "fragments_list.txt", "abs_frag_contacts.txt")}
+    dst = {k: os.path.join(out_dir, "0_" + k) for k in src}
+    pyr0 = {"0": {"data": data0, "nfrags": np.array([[int(nfrags0)]], dtype=np.int32)}}
+    return PS.remove_problematic_fragments(src["contig_info.txt"], src["fragments_list.txt"], src["abs_frag_contacts.txt"],
+                                           dst["contig_info.txt"], dst["fragments_list.txt"], dst["abs_frag_contacts.txt"], pyr0,
+                                           thresh_factor=thresh_factor)
+
+
 if __name__ == "__main__":
     PS = reference_module()
-    if os.path.isdir(OUT):
-        shutil.rmtree(OUT)
+    for sub in (os.listdir(OUT) if os.path.isdir(OUT) else []):   # (load_golden.npz is written by make_pyramid_load_golden)
+        if sub in ("input", "expected") or sub.startswith("filtered_"):
+            shutil.rmtree(os.path.join(OUT, sub))
     base = os.path.join(OUT, "input")
     write_input(base)
     res = run(PS, base, os.path.join(OUT, "expected"))
     np.savez_compressed(os.path.join(OUT, "expected", "hdf5_arrays.npz"), **res)
+    for tf in (1, 0.25):   # the filtering step of build_and_filter on the level-0 files
+        fdir = os.path.join(OUT, "filtered_%s" % str(tf).replace(".", "p"))
+        th = run_filter(PS, os.path.join(OUT, "expected", "level_0"), res["data_0"], res["nfrags_0"], fdir, thresh_factor=tf)
+        with open(os.path.join(fdir, "thresh.txt"), "w") as fh:
+            fh.write(repr(float(th)) + "\n")
     for f in os.listdir(ROOT):   # the reference's logger drops a file into the working directory
         if f.startswith("instagraal-") and f.endswith(".log"):
             os.remove(os.path.join(ROOT, f))

@@ -122,3 +122,97 @@ def test_bin_contacts_edge_cases(built):
     uk, inv = np.unique(key, return_inverse=True)
     assert np.array_equal(a.astype(np.int64) * 1700 + b, uk)
     assert np.array_equal(n, np.bincount(inv, weights=nc).astype(np.int64))
+
+
+# ---- the filtering step of build_and_filter (PS:731-1030) ------------------------------------------------------------------
+def _numpy_bin_contacts(fa, fb, nc, old2new=None, first_appearance_order=False, device=0):
+    """test-local NumPy statement of what ig_bin_contacts returns, so that the HOST logic around it is checked without a GPU"""
+    fa, fb, nc = np.asarray(fa, np.int64), np.asarray(fb, np.int64), np.asarray(nc, np.int64)
+    if old2new is not None:
+        m = np.asarray(old2new, np.int64)
+        fa, fb = m[fa], m[fb]
+    lo, hi = np.minimum(fa, fb), np.maximum(fa, fb)
+    key = lo * (1 << 32) + hi
+    uk, first, inv = np.unique(key, return_index=True, return_inverse=True)
+    sums = np.bincount(inv, weights=nc, minlength=len(uk)).astype(np.int64)
+    order = np.lexsort((first, uk >> 32)) if first_appearance_order else np.arange(len(uk))
+    return (uk[order] >> 32).astype(np.int32), (uk[order] & 0xffffffff).astype(np.int32), sums[order]
+
+
+def _filter_paths(d):
+    return {k: os.path.join(d, "0_" + k) for k in ("contig_info.txt", "fragments_list.txt", "abs_frag_contacts.txt")}
+
+
+def _run_filter(tmp, thresh_factor):
+    z = np.load(os.path.join(G, "expected", "hdf5_arrays.npz"))
+    src, dst = _filter_paths(os.path.join(G, "expected", "level_0")), _filter_paths(str(tmp))
+    pyr0 = {"0": {"data": z["data_0"], "nfrags": np.array([[int(z["nfrags_0"])]], dtype=np.int32)}}
+    th = pb.remove_problematic_fragments(src["contig_info.txt"], src["fragments_list.txt"], src["abs_frag_contacts.txt"], dst["contig_info.txt"],
+                                         dst["fragments_list.txt"], dst["abs_frag_contacts.txt"], pyr0, thresh_factor=thresh_factor)
+    return th, dst
+
+
+@pytest.mark.parametrize("tf,folder", [(1, "filtered_1"), (0.25, "filtered_0p25")])
+def test_filtering_bookkeeping_matches_reference(tmp_path, monkeypatch, tf, folder):
+    """host part: locked fragments merged forward, trailing runs and whole contigs destroyed, the accu_frag leak across a contig
+    start, GC means, contig list, threshold -- against files written by the reference's own remove_problematic_fragments"""
+    monkeypatch.setattr(pb, "bin_contacts", _numpy_bin_contacts)
+    th, dst = _run_filter(tmp_path, tf)
+    exp = _filter_paths(os.path.join(G, folder))
+    assert repr(float(th)) == open(os.path.join(G, folder, "thresh.txt")).read().strip()
+    for k in dst:
+        _same(dst[k], exp[k])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/instagraal"), reason="differential run against the live reference (build container only)")
+@pytest.mark.parametrize("seed,n_frags,tf", [(21, (30, 1, 2, 50, 3), 1), (22, (5, 5, 5, 5, 80), 0.0), (23, (120,), 0.5), (24, (2, 2, 2, 2, 2, 2, 40), -0.5)])
+def test_filtering_differential_against_the_live_reference(tmp_path, monkeypatch, seed, n_frags, tf):
+    import subprocess
+    import sys
+    root = os.path.dirname(G.rstrip("/").rsplit("/tests/", 1)[0] + "/x")
+    code = (
+        "import sys, os, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "import oracle.make_pyramid_golden as MG\n"
+        "PS = MG.reference_module()\n"
+        "base, out = %r, %r\n"
+        "MG.write_input(base, seed=%d, n_frags=%r)\n"
+        "res = MG.run(PS, base, out, n_levels=1)\n"
+        "np.savez(os.path.join(out, 'h5.npz'), **res)\n"
+        "th = MG.run_filter(PS, os.path.join(out, 'level_0'), res['data_0'], res['nfrags_0'], os.path.join(out, 'filt'), thresh_factor=%r)\n"
+        "open(os.path.join(out, 'filt', 'thresh.txt'), 'w').write(repr(float(th)))\n"
+    ) % (root, str(tmp_path / "in"), str(tmp_path / "pyr"), seed, tuple(n_frags), tf)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(tmp_path), timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    monkeypatch.setattr(pb, "bin_contacts", _numpy_bin_contacts)
+    out = str(tmp_path / "pyr")
+    z = np.load(os.path.join(out, "h5.npz"))
+    src, dst = _filter_paths(os.path.join(out, "level_0")), _filter_paths(str(tmp_path / "mine"))
+    os.makedirs(tmp_path / "mine")
+    pyr0 = {"0": {"data": z["data_0"], "nfrags": np.array([[int(z["nfrags_0"])]], dtype=np.int32)}}
+    th = pb.remove_problematic_fragments(src["contig_info.txt"], src["fragments_list.txt"], src["abs_frag_contacts.txt"], dst["contig_info.txt"],
+                                         dst["fragments_list.txt"], dst["abs_frag_contacts.txt"], pyr0, thresh_factor=tf)
+    exp = _filter_paths(os.path.join(out, "filt"))
+    assert repr(float(th)) == open(os.path.join(out, "filt", "thresh.txt")).read()
+    for k in dst:
+        _same(dst[k], exp[k])
+
+
+@pytest.mark.gpu
+def test_build_and_filter_end_to_end(built, tmp_path):
+    """pre-processing output -> unfiltered level -> filtered level 0 (== the reference's files) -> level loop -> loaded pyramid"""
+    pyr = pb.build_and_filter(os.path.join(G, "input"), 3, 3, thresh_factor=1, output_folder=str(tmp_path))
+    root = os.path.join(str(tmp_path), "pyramids", "pyramid_3_thresh_auto")
+    got, exp = _filter_paths(os.path.join(root, "level_0")), _filter_paths(os.path.join(G, "filtered_1"))
+    for k in got:
+        _same(got[k], exp[k])
+    assert os.path.isdir(os.path.join(str(tmp_path), "pyramids", "pyramid_1_no_thresh", "level_0"))
+    n0 = pb.file_len(got["fragments_list.txt"]) - 1
+    lev0, lev1 = pyr.get_level(0), pyr.get_level(1)
+    assert lev0.n_frags == n0 == 311 and lev0.n_contigs == 11
+    assert lev1.n_frags == pb.file_len(os.path.join(root, "level_1", "1_fragments_list.txt")) - 1
+    assert int(lev1.S_o_A_frags["sub_len"].sum()) == n0           # every level-0 fragment sits in exactly one level-1 bin
+    assert lev1.sparse_mat_csr.sum() <= lev0.sparse_mat_csr.sum()  # (Q13: each binning step drops the first data line)
+    # a second call finds everything built and only loads
+    pyr2 = pb.build_and_filter(os.path.join(G, "input"), 3, 3, thresh_factor=1, output_folder=str(tmp_path))
+    assert pyr2.get_level(1).n_frags == lev1.n_frags
