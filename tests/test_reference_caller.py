@@ -100,7 +100,6 @@ def test_reference_simulation_drives_this_sampler_on_the_gpu(built, tmp_path, mo
     sim = simulation("ds", base, fasta, 2, 10, False, True, thresh_factor=1, output_folder=str(tmp_path / "out"))
     s = sim.sampler
     assert isinstance(s, sampler) and int(s.n_new_frags) == sim.n_frags
-    assert np.isfinite(s.likelihood_t if hasattr(s, "likelihood_t") else 0.0)
     kuhn, lm, c1, slope, d, d_max, fact, d_nuc = s.param_simu[0]
     assert slope < 0 and d_max > 0 and fact > 0
     s.bomb_the_genome()
