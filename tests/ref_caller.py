@@ -75,6 +75,10 @@ class _NoPlot(types.ModuleType):
             raise AttributeError(name)
         return lambda *a, **k: None
 
+    @staticmethod
+    def subplots(*a, **k):   # what this repo's display_current_matrix asks for first: no matplotlib here -> its PGM branch
+        raise ImportError("matplotlib stand-in: no drawing")
+
 
 def _purge():
     for k in [k for k in sys.modules if k == "instagraal" or k.startswith("instagraal.")]:
@@ -165,3 +169,19 @@ def write_dataset(folder, seed=5, n_frags=(60, 90, 130, 40, 200, 7)):
                 out.write(s[i:i + 80] + "\n")
         out.write("\n")   # (load_reference_sequence drops the file's last line, PS:1649: keep the last record whole)
     return fasta
+
+
+def load_run_instagraal(sampler_cls):
+    """the reference's whole program, `instagraal.run_instagraal` (IG:502-600: what the `instagraal` command line calls),
+    unmodified, wired to this repo's pyramid modules and `sampler_cls`.  Stubbed besides: `pycuda.autoinit` (a context for
+    pycuda, which nothing here uses) and the post-run report `assembly_stats` (Biopython, not installed)."""
+    load_simulation("ours", sampler_cls)
+    for name in ("pycuda", "pycuda.autoinit"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    st = types.ModuleType("instagraal.assembly_stats")
+    st.print_assembly_stats = lambda *a, **k: None
+    sys.modules["instagraal.assembly_stats"] = st
+    sys.modules["instagraal"].assembly_stats = st
+    ig = importlib.import_module("instagraal.instagraal")
+    return ig.run_instagraal

@@ -122,3 +122,35 @@ def test_reference_simulation_drives_this_sampler_on_the_gpu(built, tmp_path, mo
     assert total - 2 * txt.count(">") <= n_bases <= total      # (the writer's 1-character last-line quirk can drop a base per contig)
     assert open(sim.info_frags).read().count("init_contig\tid_frag") == txt.count(">")
     s.free_gpu()
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_the_reference_program_runs_end_to_end_on_this_repo(built, tmp_path, monkeypatch):
+    """`instagraal.run_instagraal` itself (IG:502-600, the body of the `instagraal` command), unmodified: pyramid build with
+    filtering, load, sampler construction, p(s) fit, bomb, 6 cycles of full_em (the nuisance step from cycle 5 on), per-cycle
+    FASTA / info_frags / thumbnails / behaviour files -- every collaborator below `simulation` is this repo's"""
+    monkeypatch.chdir(tmp_path)
+    base = str(tmp_path / "pre")
+    fasta = RC.write_dataset(base)
+    from instagraal_b200.cuda_lib_gl_single import sampler
+    run = RC.load_run_instagraal(sampler)
+    np.random.seed(11)
+    run(base, fasta, str(tmp_path / "out"), level=2, cycles=6, coverage_std=1, neighborhood=5, device=0, bomb=True, save_matrix=True)
+    res = os.path.join(str(tmp_path / "out"), "pre", "test_mcmc_2")
+    n_frags = sum(1 for _ in open(os.path.join(res, "save_simu_step_5.txt")))
+    assert n_frags > 20
+    lik = [float(x) for x in open(os.path.join(res, "list_likelihood.txt"))]
+    assert len(lik) == 6 * n_frags and np.all(np.isfinite(lik))
+    assert lik[-1] > lik[0]                                           # the assembly improves from the exploded start
+    n_contigs = [int(x) for x in open(os.path.join(res, "list_n_contigs.txt"))]
+    assert n_contigs[-1] < n_frags // 2
+    assert len(open(os.path.join(res, "list_fact.txt")).readlines()) == n_frags          # nuisance steps: cycle 5 only (j > 4)
+    assert set(open(os.path.join(res, "list_success.txt")).read().split()) <= {"0", "1"}
+    muts = open(os.path.join(res, "list_mutations.txt")).read().splitlines()
+    assert muts[0] == "id_fA\tid_fB\tid_mutation" and len(muts) == 1 + 6 * n_frags
+    fa = open(os.path.join(res, "genome.fasta")).read()
+    assert fa.count(">3C-assembly-contig_") == n_contigs[-1]
+    assert open(os.path.join(res, "info_frags.txt")).read().count(">3C-assembly|contig_") == n_contigs[-1]
+    for j in range(6):
+        assert os.path.getsize(os.path.join(res, "matrix_cycle_%d.png" % j)) > 1000   # (PGM bytes under the reference's file name: no matplotlib here)
