@@ -21,6 +21,20 @@ ARG_NAMES = ["use_rippe", "S_o_A_frags", "collector_id_repeats", "frag_dispatche
              "mean_value_trans", "n_iterations", "is_simu", "vel", "pos"]
 
 
+@pytest.fixture(autouse=True)
+def _restore_modules():
+    """the harness plants stand-ins (h5py, matplotlib, pycuda, instagraal.*) in sys.modules: take them out again"""
+    import sys
+    before = dict(sys.modules)
+    yield
+    for k in list(sys.modules):
+        if k.split(".")[0] in ("h5py", "matplotlib", "pycuda", "instagraal"):
+            if k in before:
+                sys.modules[k] = before[k]
+            else:
+                del sys.modules[k]
+
+
 def same(a, b, path):
     if sp.issparse(a) or sp.issparse(b):
         assert sp.issparse(a) and sp.issparse(b) and a.shape == b.shape and a.dtype == b.dtype and a.format == b.format, path
