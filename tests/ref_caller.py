@@ -123,9 +123,14 @@ def load_simulation(pyr="reference", sampler_cls=RecordingSampler):
     _purge()
     if src not in sys.path:
         sys.path.insert(0, src)
-    try:
-        import matplotlib.pyplot  # noqa: F401
+    try:   # a real matplotlib, if there is one; the raising stub of oracle/ref_harness (which other harnesses put on sys.path) is not
+        import matplotlib
+        real = hasattr(matplotlib, "__version__")
+        if real:
+            import matplotlib.pyplot  # noqa: F401
     except Exception:
+        real = False
+    if not real:
         mp = types.ModuleType("matplotlib")
         mp.pyplot = _NoPlot("matplotlib.pyplot")
         mp.use = lambda *a, **k: None
