@@ -127,36 +127,35 @@ class pyramid:
             fh.readline()
             rows = [ln.split("\t") for ln in fh if ln]
         n = len(rows)
-        col = lambda j, dt: np.fromiter((dt(r[j]) for r in rows), dtype=np.int64 if dt is int else np.float64, count=n)
-        index, start, end, size = col(0, int), col(2, int), col(3, int), col(4, int)
-        gc, n_accu, init_lo, init_hi = col(5, float), col(6, int), col(7, int), col(8, int)
-        if lvl > 0:
-            sub_lo, sub_hi = col(9, int), col(10, int)
-        else:
-            sub_lo, sub_hi = index.copy(), index.copy()
-        names_of = [r[1] for r in rows]
         contig_dict, list_contigs, list_contigs_id = dict(), [], []
-        contig_id = np.empty(n, dtype=np.int64)
-        for k, nm in enumerate(names_of):
+        fragments_info = dict()
+        table = np.empty((n, 10), dtype=np.int64)    # index start end size n_accu init_lo init_hi sub_lo sub_hi contig_id
+        gc = np.empty(n, dtype=np.float64)
+        names_of = [None] * n
+        initiate = basic_fragment.initiate
+        for k, r in enumerate(rows):
+            ci, nm = int(r[0]), r[1]
+            start, end, size, g, n_accu, init_lo, init_hi = int(r[2]), int(r[3]), int(r[4]), float(r[5]), int(r[6]), int(r[7]), int(r[8])
+            sub_lo, sub_hi = (int(r[9]), int(r[10])) if lvl > 0 else (ci, ci)
             c = contig_dict.get(nm)
             if c is None:
                 list_contigs.append(nm)
                 list_contigs_id.append(len(list_contigs))
                 c = contig_dict[nm] = {"frag": [], "id_contig": len(list_contigs)}
                 contig_dict[len(list_contigs)] = []
-            contig_id[k] = c["id_contig"]
-        fragments_info = dict()
-        for k in range(n):
-            r, cid, ci = rows[k], int(contig_id[k]), int(index[k])
-            fragments_info[k + 1] = {"init_contig": r[1], "index": ci, "tag": r[0] + "-" + r[1], "start_pos(bp)": int(start[k]),
-                                     "end_pos(bp)": int(end[k]), "size(bp)": int(size[k]), "sub_low_index": int(sub_lo[k]),
-                                     "sub_high_index": int(sub_hi[k]), "super_index": ci, "n_accu_frags": int(n_accu[k])}
-            f = basic_fragment.initiate(k + 1, ci, r[1], ci, int(start[k]), int(end[k]), int(size[k]), float(gc[k]), int(init_lo[k]),
-                                        int(init_hi[k]), int(sub_lo[k]), int(sub_hi[k]), ci, cid, int(n_accu[k]))
-            contig_dict[r[1]]["frag"].append(f)
+            cid = c["id_contig"]
+            fragments_info[k + 1] = {"init_contig": nm, "index": ci, "tag": r[0] + "-" + nm, "start_pos(bp)": start, "end_pos(bp)": end,
+                                     "size(bp)": size, "sub_low_index": sub_lo, "sub_high_index": sub_hi, "super_index": ci,
+                                     "n_accu_frags": n_accu}
+            f = initiate(k + 1, ci, nm, ci, start, end, size, g, init_lo, init_hi, sub_lo, sub_hi, ci, cid, n_accu)
+            c["frag"].append(f)
             contig_dict[cid].append(f)
-        cols = {"index": index, "start": start, "end": end, "size": size, "gc": gc, "n_accu": n_accu, "sub_lo": sub_lo, "sub_hi": sub_hi,
-                "contig_id": contig_id, "init_contig": names_of, "super_index": index.copy()}
+            table[k] = (ci, start, end, size, n_accu, init_lo, init_hi, sub_lo, sub_hi, cid)
+            gc[k] = g
+            names_of[k] = nm
+        cols = {"index": table[:, 0].copy(), "start": table[:, 1].copy(), "end": table[:, 2].copy(), "size": table[:, 3].copy(), "gc": gc,
+                "n_accu": table[:, 4].copy(), "sub_lo": table[:, 7].copy(), "sub_hi": table[:, 8].copy(), "contig_id": table[:, 9].copy(),
+                "init_contig": names_of, "super_index": table[:, 0].copy()}
         return fragments_info, contig_dict, list_contigs, list_contigs_id, cols
 
     def build_frag_dictionnary(self, fragments_list, level):
