@@ -168,3 +168,57 @@ def test_the_reference_program_runs_end_to_end_on_this_repo(built, tmp_path, mon
     assert open(os.path.join(res, "info_frags.txt")).read().count(">3C-assembly|contig_") == n_contigs[-1]
     for j in range(6):
         assert os.path.getsize(os.path.join(res, "matrix_cycle_%d.png" % j)) > 1000   # (PGM bytes under the reference's file name: no matplotlib here)
+    _structural_pins_of_the_reference_gpu_tests(res, n_cycles=6, n_frags=n_frags)
+
+
+def _structural_pins_of_the_reference_gpu_tests(res, n_cycles, n_frags):
+    """the assertions of the reference's own tests/test_instagraal_gpu.py:128-330 (its only pins of this path: structural),
+    on this run's output folder"""
+    import glob
+    import math
+    n_iters = n_cycles * n_frags
+    for fname in ("genome.fasta", "info_frags.txt", "list_likelihood.txt", "list_n_contigs.txt", "list_mean_len.txt", "list_dist_init_genome.txt",
+                  "list_mutations.txt", "save_simu_step_0.txt", "save_simu_step_%d.txt" % (n_cycles - 1), "matrix_cycle_0.png",
+                  "matrix_cycle_%d.png" % (n_cycles - 1)):
+        assert os.path.exists(os.path.join(res, fname)), fname
+    lines = open(os.path.join(res, "genome.fasta")).read().splitlines()
+    headers = [l for l in lines if l.startswith(">")]
+    assert len(headers) >= 1
+    for h in headers:
+        assert h[1:].startswith("3C-assembly-contig_") and h[1:].split("3C-assembly-contig_")[1].isdigit()
+    assert all(set(l) <= set("ACGTNacgtn") for l in lines if not l.startswith(">"))
+    current, started = None, False
+    for l in lines:
+        if l.startswith(">"):
+            assert current is None or started, "empty sequence for %s" % current
+            current, started = l, False
+        elif l.strip():
+            started = True
+    assert started
+    blocks = [b.strip() for b in open(os.path.join(res, "info_frags.txt")).read().split(">") if b.strip()]
+    assert len(blocks) >= 1
+    for b in blocks:
+        bl = b.splitlines()
+        assert len(bl) >= 2 and set(bl[1].split()) == {"init_contig", "id_frag", "orientation", "start", "end"}
+        for row in bl[2:]:
+            f = row.split()
+            assert len(f) == 5 and int(f[2]) in (1, -1)
+    assert len(glob.glob(os.path.join(res, "save_simu_step_*.txt"))) == n_cycles
+    for i in range(n_cycles):
+        rows = open(os.path.join(res, "save_simu_step_%d.txt" % i)).read().splitlines()
+        assert len(rows) == n_frags
+    for l in open(os.path.join(res, "save_simu_step_0.txt")).read().splitlines():
+        f = l.split()
+        assert len(f) == 4 and int(f[3]) in (1, -1) and all(int(x) == int(x) for x in f)
+    for name in ("list_likelihood.txt", "list_n_contigs.txt", "list_mean_len.txt", "list_dist_init_genome.txt"):
+        vals = [v for v in open(os.path.join(res, name)).read().splitlines() if v.strip()]
+        assert len(vals) == n_iters, name
+        if name == "list_likelihood.txt":
+            assert all(math.isfinite(float(v)) for v in vals)
+        if name == "list_n_contigs.txt":
+            assert all(int(v) > 0 for v in vals)
+    mut = [l.split("\t") for l in open(os.path.join(res, "list_mutations.txt")).read().splitlines()]
+    assert mut[0] == ["id_fA", "id_fB", "id_mutation"] and len(mut) - 1 == n_iters
+    body = np.array(mut[1:], dtype=np.int64)
+    assert body[:, :2].min() >= 0 and body[:, :2].max() <= n_frags - 1 and body[:, 2].min() >= 0
+    assert len(glob.glob(os.path.join(res, "matrix_cycle_*.png"))) == n_cycles
