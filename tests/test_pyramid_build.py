@@ -216,3 +216,48 @@ def test_build_and_filter_end_to_end(built, tmp_path):
     # a second call finds everything built and only loads
     pyr2 = pb.build_and_filter(os.path.join(G, "input"), 3, 3, thresh_factor=1, output_folder=str(tmp_path))
     assert pyr2.get_level(1).n_frags == lev1.n_frags
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/instagraal"), reason="differential run against the live reference (build container only)")
+@pytest.mark.parametrize("seed,n_frags,factor,min_bin", [(31, (1, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 27, 28), 3, 1), (32, (100, 3, 50), 2, 1),
+                                                           (33, (10, 20, 30, 2), 3, 4), (34, (64, 65, 1), 4, 1), (35, (200,), 9, 1)])
+def test_level_loop_differential_against_the_live_reference(tmp_path, monkeypatch, seed, n_frags, factor, min_bin):
+    """init_frag_list + subsample_data_set + fill_sparse_pyramid_level for 4 levels on fresh inputs, other binning factors
+    (>= 8 exercises NumPy's pairwise mean of the GC contents) and min_bin_per_contig > 1 (contigs left unbinned)"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, os, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "import oracle.make_pyramid_golden as MG\n"
+        "PS = MG.reference_module()\n"
+        "MG.write_input(%r, seed=%d, n_frags=%r)\n"
+        "res = MG.run(PS, %r, %r, n_levels=4, factor=%d, min_bin=%d)\n"
+        "np.savez(os.path.join(%r, 'h5.npz'), **res)\n"
+    ) % (root, str(tmp_path / "in"), seed, tuple(n_frags), str(tmp_path / "in"), str(tmp_path / "ref"), factor, min_bin, str(tmp_path / "ref"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(tmp_path), timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    monkeypatch.setattr(pb, "bin_contacts", _numpy_bin_contacts)
+    want = np.load(os.path.join(str(tmp_path / "ref"), "h5.npz"))
+    base, out = str(tmp_path / "in"), str(tmp_path / "mine")
+    cur = None
+    for level in range(4):
+        os.makedirs(os.path.join(out, "level_%d" % level))
+        got, exp = _paths(out, level), _paths(str(tmp_path / "ref"), level)
+        if level == 0:
+            import shutil
+            shutil.copyfile(os.path.join(base, "info_contigs.txt"), got["contig_info.txt"])
+            shutil.copyfile(os.path.join(base, "abs_fragments_contacts_weighted.txt"), got["abs_frag_contacts.txt"])
+            nfr = pb.init_frag_list(os.path.join(base, "fragments_list.txt"), got["fragments_list.txt"])
+        else:
+            nfr = pb.subsample_data_set(cur["contig_info.txt"], cur["fragments_list.txt"], factor, cur["abs_frag_contacts.txt"],
+                                        got["abs_frag_contacts.txt"], min_bin, got["contig_info.txt"], got["fragments_list.txt"],
+                                        cur["sub_2_super_index_frag.txt"])
+            _same(cur["sub_2_super_index_frag.txt"], _paths(str(tmp_path / "ref"), level - 1)["sub_2_super_index_frag.txt"])
+        assert nfr == int(want["nfrags_%d" % level])
+        for k in ("contig_info.txt", "fragments_list.txt", "abs_frag_contacts.txt"):
+            _same(got[k], exp[k])
+        arr = pb.fill_sparse_pyramid_level(None, level, got["abs_frag_contacts.txt"], nfr)
+        assert np.array_equal(arr, want["data_%d" % level]), level
+        cur = got
