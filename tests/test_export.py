@@ -101,3 +101,34 @@ def test_against_files_written_by_the_reference_method(tmp_path, seed):
         impl.generate_new_fasta(lvl, types.SimpleNamespace(**vf), fa, tx)
         assert filecmp.cmp(fa, os.path.join(g, "genome_%d.fasta" % seed), shallow=False), tag
         assert filecmp.cmp(tx, os.path.join(g, "info_frags_%d.txt" % seed), shallow=False), tag
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference/src/instagraal"), reason="differential run against the live reference (build container only)")
+def test_differential_against_the_live_reference_method(tmp_path):
+    """more seeds and shapes than the two committed goldens, written by the reference's own method in a child process:
+    one contig, many one-fragment contigs, a larger scaffold"""
+    import os
+    import pickle
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cases = [(7, 1, 1), (8, 60, 60), (9, 500, 23), (10, 37, 3), (11, 900, 2)]
+    code = (
+        "import sys, os, types, pickle\n"
+        "sys.path.insert(0, %r)\n"
+        "from oracle.make_export_golden import make_case, stand_in_level\n"
+        "from oracle.make_pyramid_golden import reference_module\n"
+        "PS = reference_module()\n"
+        "for seed, n, n_init in %r:\n"
+        "    names, starts, ends, seqs, vf = make_case(seed, n=n, n_init=n_init)\n"
+        "    PS.level.generate_new_fasta(stand_in_level(names, starts, ends, seqs), types.SimpleNamespace(**vf), 'g_%%d.fa' %% seed, 'i_%%d.txt' %% seed)\n"
+    ) % (root, cases)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(tmp_path), timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    from oracle.make_export_golden import make_case, stand_in_level
+    for seed, n, n_init in cases:
+        names, starts, ends, seqs, vf = make_case(seed, n=n, n_init=n_init)
+        fa, tx = str(tmp_path / ("mine_%d.fa" % seed)), str(tmp_path / ("mine_%d.txt" % seed))
+        export.generate_new_fasta(stand_in_level(names, starts, ends, seqs), types.SimpleNamespace(**vf), fa, tx)
+        assert filecmp.cmp(fa, str(tmp_path / ("g_%d.fa" % seed)), shallow=False), seed
+        assert filecmp.cmp(tx, str(tmp_path / ("i_%d.txt" % seed)), shallow=False), seed
